@@ -1,0 +1,328 @@
+#!/usr/bin/env python
+"""bench.py — accessibility nt/s of the `db` hot path on B200 (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+  torchrun --nproc-per-node N ... bench.py --gpus N ...          (one rank per GPU, launched by the driver)
+
+A *step* is one pass of the hot path (inside + outside + accessibility, everything the reference's
+`Raccess::Run` does) over one batch of synthetic transcripts of config 1 of BASELINE.json (cfg2 of
+SURVEY §8d: GENCODE-like lognormal lengths 200-5,000 nt, GC 0.45, W=70, delta=5).  Each rank works on its
+own slice of the 100k-transcript stream (weak scaling, no data-path collective: sequences are
+independent).  `value` is timed on the device with inputs already resident in HBM; `e2e` goes through the
+public C-ABI call (`Raccess.run_batch` -> prib_acc_run) with host buffers, H2D and D2H inside the timed
+region.
+
+`--impl reference` times the reference's own CPU implementation (oracle/_ref, the unmodified raccess.cpp
+compiled with OpenMP, all host threads) on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+W_SPAN = 70
+DELTA = 5
+SEQS_PER_STEP = 1536          # transcripts per rank per step (~2.9 M nt; DP state ~30 GB >> L2)
+WORKLOAD = ("cfg2: GENCODE-like synthetic transcripts, length=clip(round(LogNormal(ln1500,0.75)),200,5000), "
+            "GC=0.45, W=70, delta=5")
+
+
+def host_cores() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def work_per_nt(key="cfg2_W70"):
+    with open(os.path.join(ROOT, "priblast_b200", "data", "work_per_nt.json")) as f:
+        return json.load(f)[key]
+
+
+def rank_slice(rank: int, n_per_rank: int):
+    from priblast_b200 import workloads
+    seqs = workloads.cfg2(first=(rank + 1) * n_per_rank)
+    return seqs[rank * n_per_rank:(rank + 1) * n_per_rank]
+
+
+# ------------------------------------------------------------------------------------------------
+# reference CPU arm / cpu_baseline
+# ------------------------------------------------------------------------------------------------
+def cpu_sample(seqs, cores: int, seconds: float = 15.0):
+    """A bounded sample of the step's batch: about `seconds` of work for `cores` threads at the
+    surveyed ~1.6 k nt/s/core; at least one sequence per core so every thread has work."""
+    budget = 1600.0 * cores * seconds
+    take, nt = [], 0
+    # stride through the batch so the length mix of the sample matches the batch
+    stride = max(1, len(seqs) // max(cores * 2, 1))
+    for s in seqs[::stride]:
+        if nt + len(s) > budget and len(take) >= cores:
+            break
+        take.append(s)
+        nt += len(s)
+    return take, nt
+
+
+def run_cpu_reference(seqs, threads: int):
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    from oracle_py import OracleLib, RefLib
+    if RefLib.available(fast=True):
+        lib, kind = RefLib(fast=True), "reference"
+    else:
+        lib, kind = OracleLib(), "port"
+    order = sorted(range(len(seqs)), key=lambda k: -len(seqs[k]))  # longest first, utils.cpp:53-60
+    t0 = time.perf_counter()
+    _, used = lib.run_batch([seqs[k] for k in order], W_SPAN, DELTA, nthreads=threads)
+    dt = time.perf_counter() - t0
+    return dt, used, kind
+
+
+def reference_arm(args, rank: int, world: int) -> None:
+    if rank != 0:
+        return
+    cores = host_cores()
+    seqs = rank_slice(0, SEQS_PER_STEP)
+    sample, nt = cpu_sample(seqs, cores, seconds=max(4.0, 40.0 / max(args.steps + args.warmup, 1)))
+    times, used, kind = [], cores, "port"
+    for it in range(args.warmup + args.steps):
+        dt, used, kind = run_cpu_reference(sample, cores)
+        if it >= args.warmup:
+            times.append(dt)
+    ms = 1e3 * sum(times) / len(times)
+    value = nt / (ms / 1e3)
+    sample_desc = f"{len(sample)} transcripts / {nt} nt strided from the step's {len(seqs)}-transcript batch"
+    line = {
+        "impl": "reference", "metric": "db-step accessibility throughput", "value": value, "unit": "nt/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sample": sample_desc, "span": W_SPAN, "delta": DELTA},
+        "cpu_baseline": {"value": value, "unit": "nt/s", "cores": used, "kind": kind, "sample": sample_desc},
+        "e2e": {"value": value, "unit": "nt/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampler
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for ln in self.proc.stdout:
+            self.rows.append((time.perf_counter(), ln.strip()))
+
+    def stop(self, t0: float, t1: float) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, mx, reasons, pw = [], None, set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for t, ln in self.rows:
+            if t < t0 or t > t1 + 0.3:
+                continue
+            f = [x.strip() for x in ln.split(",")]
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+                pw.append(float(f[2]))
+            except (ValueError, IndexError):
+                continue
+            for nme, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm), "power_w_max": max(pw) if pw else None}
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def ours(args, rank: int, local_rank: int, world: int) -> None:
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from priblast_b200 import Raccess, _capi, packed_layout
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    seqs = rank_slice(rank, SEQS_PER_STEP)
+    lens = np.array([len(s) for s in seqs], dtype=np.int64)
+    nt_rank = int(lens.sum())
+
+    r = Raccess(W_SPAN, DELTA, device=local_rank)
+    # a real (non-default) torch stream: handle 0 would mean "the context's own stream" to the library, and
+    # torch events on the legacy default stream would not bracket kernels launched elsewhere
+    stream = torch.cuda.Stream(device=local_rank)
+    assert stream.cuda_stream != 0
+    r.set_stream(stream.cuda_stream)
+
+    # -- device-resident timing: stage once, then K x compute ----------------------------------------
+    r.stage(seqs)
+    for _ in range(max(args.warmup, 3)):
+        r.compute()
+    r.sync()
+    c0 = r.counters()
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    t_wall0 = time.perf_counter()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        r.compute()
+    e1.record(stream)
+    barrier()
+    t_wall1 = time.perf_counter()
+    r.sync()
+    c1 = r.counters()
+    ms_total = e0.elapsed_time(e1)
+    clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
+    ms_step = ms_total / args.steps
+    if world > 1:
+        t = torch.tensor([ms_step], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_step_max = float(t.item())
+        tot = torch.tensor([float(nt_rank)], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+        nt_all = float(tot.item())
+    else:
+        ms_step_max, nt_all = ms_step, float(nt_rank)
+    value = nt_all / (ms_step_max / 1e3)
+    launches = int(c1["kernel_launches"] - c0["kernel_launches"])
+    phases = {k: (c1["phase_ms"][k] - c0["phase_ms"][k]) / args.steps for k in c1["phase_ms"]}
+
+    # -- end to end through the public API with host buffers -----------------------------------------
+    acc_off, cond_off, total = packed_layout(lens)
+    out = torch.empty(max(total, 1), dtype=torch.float32).pin_memory().numpy()
+    r.run_batch(seqs, out=out)  # warm (allocations of the pinned staging buffer)
+    e2e_steps = max(1, min(args.steps, 3))
+    c2 = r.counters()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        r.run_batch(seqs, out=out)
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / e2e_steps
+    c3 = r.counters()
+    if world > 1:
+        t = torch.tensor([dt], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+    e2e_value = nt_all / dt
+    h2d = int((c3["h2d_bytes"] - c2["h2d_bytes"]) / e2e_steps)
+    d2h = int((c3["d2h_bytes"] - c2["d2h_bytes"]) / e2e_steps)
+    checksum = float(np.float64(out[:total]).sum())
+
+    if rank == 0:
+        # -- roofline of the dominant kernel (SFU-issue bound on algorithmic terms) --------
+        lib = _capi.load()
+        import ctypes
+        mufu, ffma, dfma = ctypes.c_double(), ctypes.c_double(), ctypes.c_double()
+        _capi.check(lib.prib_peak_probe(local_rank, ctypes.byref(mufu), ctypes.byref(ffma), ctypes.byref(dfma)))
+        wk = work_per_nt()
+        dom = max((k for k in phases if k != "memset"), key=lambda k: phases[k])
+        # whole-step algorithmic SFU work / whole-step device time (all kernels of the step together
+        # evaluate the recurrences; per-phase shares are given beside it)
+        sfu_ops = wk["sfu_ops_per_nt"] * nt_rank
+        achieved = sfu_ops / (ms_step * 1e-3) / 1e9
+        peaks = {}
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+                peaks = json.load(f)
+        except Exception:
+            pass
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        used_state = c1["dp_state_bytes_used"]
+        roofline = {
+            "bound": "sfu", "achieved": achieved, "peak": mufu.value, "unit": "Gop/s", "frac": achieved / mufu.value,
+            "traffic": None,
+            "definition": "algorithmic terms x 1 EX2 + reduction outputs x 1 LG2 per second (SURVEY 8d) over the "
+                          "measured MUFU ex2.approx issue peak of this GPU (prib_peak_probe, same run)",
+            "sfu_ops_per_nt": wk["sfu_ops_per_nt"], "terms_per_nt": wk["terms_per_nt"],
+            "fp32_frac": (6 * wk["terms_per_nt"] * nt_rank / (ms_step * 1e-3) / 1e9) / ffma.value,
+            "peaks_measured_gops": {"mufu_ex2": mufu.value, "ffma": ffma.value, "dfma": dfma.value},
+            "dominant_phase": dom, "phase_ms_per_step": phases,
+            "hbm": {"peak_gbs": hbm_peak, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
+                    "algorithmic_bytes_per_nt": 9.0,
+                    "achieved_gbs": 9.0 * nt_rank / (ms_step * 1e-3) / 1e9},
+        }
+        # -- CPU baseline beside it (N=1 only) ---------------------------------------------------------
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            cores = host_cores()
+            sample, nt_s = cpu_sample(seqs, cores, seconds=15.0)
+            dtc, used, kind = run_cpu_reference(sample, cores)
+            cpu = {"value": nt_s / dtc, "unit": "nt/s", "cores": used, "kind": kind,
+                   "sample": f"{len(sample)} transcripts / {nt_s} nt strided from the step's batch, {dtc:.1f} s"}
+        line = {
+            "metric": "db-step accessibility throughput", "value": value, "unit": "nt/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step_max,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "transcripts_per_gpu_per_step": SEQS_PER_STEP,
+                       "nt_per_gpu_per_step": nt_rank, "span": W_SPAN, "delta": DELTA,
+                       "l2_policy": f"no flush needed: each step rewrites {used_state / 2**30:.1f} GiB of DP state "
+                                    "(>> 126 MB L2)",
+                       "parallelism": f"{world} independent shard(s), no collective"},
+            "e2e": {"value": e2e_value, "unit": "nt/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "steps": e2e_steps, "checksum": checksum},
+            "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    r.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        reference_arm(args, rank, world)
+    else:
+        ours(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

@@ -137,7 +137,7 @@ class OracleLib(_BatchMixin):
 
     def count_terms(self, seq: str, W: int = 70, delta: int = 5):
         """Algorithmic work of one sequence: dict of counters."""
-        b = seq.encode()
+        b = seq.encode() if isinstance(seq, str) else bytes(seq)
         c = np.zeros(8, dtype=np.int64)
         self.lib.oracle_raccess_count(b, len(b), W, delta, _as(_i64p, c))
         keys = ["lse_inside", "lse_outside", "lse_access", "expd_access", "loop_energy", "cells",
@@ -146,7 +146,7 @@ class OracleLib(_BatchMixin):
 
     def run_exact(self, seq: str, W: int = 70, delta: int = 5):
         """Same recurrences with exact libm log1p(exp()) in place of the fmath tables (noise probe)."""
-        b = seq.encode()
+        b = seq.encode() if isinstance(seq, str) else bytes(seq)
         L = len(b)
         acc = np.zeros(max(L, 1), dtype=np.float32)
         cond = np.zeros(max(L, 1), dtype=np.float32)

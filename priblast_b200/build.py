@@ -1,0 +1,58 @@
+"""Builds libpriblast_acc.so in-tree with nvcc for sm_100a (no JIT cache, no torch extension machinery:
+the library is a plain C-ABI shared object so non-Python hosts can link it)."""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(PKG, "csrc")
+LIB = os.path.join(PKG, "libpriblast_acc.so")
+BLOB = os.path.join(PKG, "data", "turner99.bin")
+HOST_CXX = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+HOST_CC = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc"
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-lineinfo", "-O3", "-std=c++17",
+    "-Xcompiler", "-fPIC", "-Xcompiler", "-O2",
+    "-ccbin", HOST_CXX,
+]
+
+SOURCES = ["acc_kernels.cu", "acc_tables.cpp"]
+DEPS = SOURCES + ["acc_core.h", "acc_tables.h", "turner_params.h", "turner_blob.c",
+                  os.path.join("..", "..", "include", "priblast_acc.h")]
+
+
+def nvcc_path() -> str:
+    p = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(p):
+        raise RuntimeError("nvcc not found: libpriblast_acc.so cannot be built (there is no CPU fallback)")
+    return p
+
+
+def is_stale() -> bool:
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    return any(os.path.getmtime(os.path.join(CSRC, d)) > t for d in DEPS) or os.path.getmtime(BLOB) > t
+
+
+def build_library(force: bool = False, verbose: bool = False, extra: list[str] | None = None) -> str:
+    if not force and not is_stale():
+        return LIB
+    obj = os.path.join(CSRC, "turner_blob.o")
+    subprocess.run([HOST_CC, "-O2", "-fPIC", "-c", os.path.join(CSRC, "turner_blob.c"),
+                    f'-DPRIB_TURNER_BIN="{BLOB}"', "-o", obj], check=True)
+    cmd = [nvcc_path(), *NVCC_FLAGS, *(extra or []), "-shared",
+           *[os.path.join(CSRC, s) for s in SOURCES], obj, "-o", LIB]
+    if verbose:
+        print(" ".join(cmd))
+    subprocess.run(cmd, check=True)
+    return LIB
+
+
+if __name__ == "__main__":
+    import sys
+    print(build_library(force=True, verbose=True, extra=sys.argv[1:]))

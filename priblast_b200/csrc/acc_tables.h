@@ -1,0 +1,48 @@
+// Host-side construction of the Boltzmann-factor tables and of the batch column layout.
+#pragma once
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "acc_core.h"
+
+namespace prib {
+
+struct HostTables {
+  SmallTables small;
+  std::vector<real> e_int11, e_int21, e_int22;
+  std::vector<float> log_tbl;  // 2048 x (app, rev)
+};
+
+// Scales the embedded Turner parameters exactly like Raccess::set_energy_parameters
+// (raccess.hpp:105-158) and exponentiates them.  Returns false if the blob is missing.
+bool build_tables(int W, HostTables &out, std::string &err);
+
+// Column layout of one batch: sequence k occupies columns seq_off[k] .. seq_off[k]+len[k]
+// (left indices 0..L), followed by >= kPad zero columns; the first sequence starts at kPad.
+struct BatchLayout {
+  long long NC = 0;
+  std::vector<long long> seq_off;
+  std::vector<int32_t> seq_len;
+  std::vector<int32_t> col_seq;
+  std::vector<uint8_t> S;
+};
+
+// Base coding of Raccess::Initiallize (raccess.cpp:55-68).
+inline uint8_t encode_base(char ch) {
+  switch (ch) {
+    case 'A': case 'a': return 1;
+    case 'C': case 'c': return 2;
+    case 'G': case 'g': return 3;
+    case 'T': case 't': case 'U': case 'u': return 4;
+    default: return 0;
+  }
+}
+
+void build_layout(int n, const char *const *seqs, const int32_t *lens, BatchLayout &out);
+
+// Columns a sequence of length L costs in a batch (for batch sizing).
+inline long long layout_columns(int L) { return (((long long)L + 1 + kPad) + 31) / 32 * 32; }
+
+}  // namespace prib

@@ -1,0 +1,140 @@
+// TEST INFRASTRUCTURE — CPU emulation of the CUDA kernels' per-thread bodies.
+//
+// The device code in priblast_b200/csrc/acc_kernels.cu is a set of "one thread = one column" kernels
+// whose bodies are the PRIB_HD functions of acc_core.h.  This harness runs the very same functions in
+// plain loops (same launch order as the device driver) so the restructured mathematics can be checked
+// against the oracle in a container without a GPU.  It is NOT linked into libpriblast_acc.so, is not
+// reachable from the C ABI, and is not a fallback: the product fails loudly without CUDA.
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../priblast_b200/csrc/acc_core.h"
+#include "../../priblast_b200/csrc/acc_tables.h"
+
+using namespace prib;
+
+namespace {
+
+struct Emu {
+  HostTables tab;
+  BatchLayout lay;
+  std::vector<std::vector<real>> arr;
+  std::vector<double> lao, lbo;
+  Ctx c;
+};
+
+bool setup(Emu &e, int n, const char *const *seqs, const int32_t *lens, int W, int delta, float *out,
+           const int64_t *acc_off, const int64_t *cond_off) {
+  std::string err;
+  if (!build_tables(W, e.tab, err)) return false;
+  build_layout(n, seqs, lens, e.lay);
+  Ctx &c = e.c;
+  std::memset(&c, 0, sizeof(c));
+  c.NC = e.lay.NC;
+  c.W = W;
+  c.delta = delta;
+  c.rows = W + 4;
+  c.nseq = n;
+  c.S = e.lay.S.data();
+  c.col_seq = e.lay.col_seq.data();
+  c.seq_len = e.lay.seq_len.data();
+  c.seq_off = e.lay.seq_off.data();
+  c.T = &e.tab.small;
+  c.e_int11 = e.tab.e_int11.data();
+  c.e_int21 = e.tab.e_int21.data();
+  c.e_int22 = e.tab.e_int22.data();
+  c.log_tbl = e.tab.log_tbl.data();
+  e.arr.resize(kNumArr);
+  for (int a = 0; a < kNumArr; a++) {
+    int rows = (a == X_ML || a == X_MR) ? 32 : c.rows;
+    e.arr[a].assign((size_t)rows * (size_t)c.NC, 0.0);
+    c.arr[a] = e.arr[a].data();
+  }
+  e.lao.assign((size_t)c.NC, 0.0);
+  e.lbo.assign((size_t)c.NC, 0.0);
+  c.lao = e.lao.data();
+  c.lbo = e.lbo.data();
+  c.acc_off = (const long long *)acc_off;
+  c.cond_off = (const long long *)cond_off;
+  c.out = out;
+  return true;
+}
+
+void run_dp(Emu &e) {
+  const Ctx &c = e.c;
+  double ring[256];
+  for (int d = kTurn; d <= c.W + 1; d++)
+    for (long long g = 0; g < c.NC; g++) inside_cell(c, g, d);
+  for (int k = 0; k < c.nseq; k++) {
+    scan_alpha_outer(c, k, ring);
+    scan_beta_outer(c, k, ring);
+  }
+  for (int d = c.W + 1; d >= kTurn; d--)
+    for (long long g = 0; g < c.NC; g++) outside_cell(c, g, d);
+}
+
+void run_acc(Emu &e) {
+  const Ctx &c = e.c;
+  for (long long g = 0; g < c.NC; g++) {
+    biloop_left(c, g);
+    biloop_right(c, g);
+    hairpin_suffix(c, g);
+  }
+  for (long long g = 0; g < c.NC; g++) finalize_position(c, g);
+}
+
+}  // namespace
+
+extern "C" {
+
+int hostemu_run_batch(int n, const char *const *seqs, const int32_t *lens, int W, int delta, float *out,
+                      const int64_t *acc_off, const int64_t *cond_off, int /*nthreads*/) {
+  Emu e;
+  for (int k = 0; k < n; k++) {
+    std::memset(out + acc_off[k], 0, sizeof(float) * (size_t)lens[k]);
+    std::memset(out + cond_off[k], 0, sizeof(float) * (size_t)lens[k]);
+  }
+  if (!setup(e, n, seqs, lens, W, delta, out, acc_off, cond_off)) return -1;
+  run_dp(e);
+  run_acc(e);
+  return 1;
+}
+
+int hostemu_run(const char *seq, int L, int W, int delta, float *acc, float *cond) {
+  std::vector<float> out(2 * (size_t)L + 2, 0.f);
+  int64_t ao = 0, co = L;
+  int32_t len = L;
+  const char *sp = seq;
+  int rc = hostemu_run_batch(1, &sp, &len, W, delta, out.data(), &ao, &co, 1);
+  std::memcpy(acc, out.data(), sizeof(float) * (size_t)L);
+  std::memcpy(cond, out.data() + L, sizeof(float) * (size_t)L);
+  return rc > 0 ? 0 : rc;
+}
+
+// Debug: band state of one sequence, arrays as [kNumArr][W+4][L+1] (left index fastest), plus logs.
+int hostemu_dump(const char *seq, int L, int W, int delta, double *band, double *lao, double *lbo) {
+  Emu e;
+  std::vector<float> out(2 * (size_t)L + 2, 0.f);
+  int64_t ao = 0, co = L;
+  int32_t len = L;
+  const char *sp = seq;
+  if (!setup(e, 1, &sp, &len, W, delta, out.data(), &ao, &co)) return -1;
+  run_dp(e);
+  const long long off = e.lay.seq_off[0];
+  for (int a = 0; a < X_ML; a++)
+    for (int d = 0; d < W + 4; d++)
+      for (int i = 0; i <= L; i++)
+        band[((size_t)a * (W + 4) + d) * (L + 1) + i] = e.arr[a][(size_t)d * e.c.NC + off + i];
+  for (int i = 0; i <= L; i++) {
+    lao[i] = e.lao[(size_t)(off + i)];
+    lbo[i] = e.lbo[(size_t)(off + i)];
+  }
+  return 0;
+}
+
+int hostemu_num_arrays() { return X_ML; }
+
+}  // extern "C"

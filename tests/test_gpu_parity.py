@@ -1,0 +1,163 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (priblast_b200.Raccess -> libpriblast_acc.so),
+against the committed reference fixtures, the oracle on fresh inputs, and size-independent properties."""
+import numpy as np
+import pytest
+
+from conftest import ATOL_VS_EXACT, ATOL_VS_REF, GOLDEN, RTOL_VS_EXACT, RTOL_VS_REF, assert_close_kcal
+
+pytestmark = pytest.mark.gpu
+
+_ctx_cache = {}
+
+
+def rac(W, delta, **kw):
+    """One context per (W, delta); each gets a bounded DP budget so a dozen of them fit one GPU."""
+    from priblast_b200 import Raccess
+    kw.setdefault("max_batch_bytes", 8 << 30)
+    key = (W, delta, tuple(sorted(kw.items())))
+    if key not in _ctx_cache:
+        _ctx_cache[key] = Raccess(W, delta, **kw)
+    return _ctx_cache[key]
+
+
+def _groups():
+    g = {}
+    for c in GOLDEN:
+        g.setdefault((c["W"], c["delta"]), []).append(c)
+    return sorted(g.items())
+
+
+@pytest.mark.parametrize("key,cases", _groups(), ids=lambda x: f"W{x[0]}_d{x[1]}" if isinstance(x, tuple) else "")
+def test_golden_fixtures(key, cases):
+    """Every committed reference vector (all of tests/golden), one batched C-ABI call per (W, delta)."""
+    W, delta = key
+    res = rac(W, delta).run_batch([c["seq"] for c in cases])
+    worst = 0.0
+    for c, (acc, cond) in zip(cases, res):
+        worst = max(worst, assert_close_kcal(acc, c["acc"], ATOL_VS_REF, RTOL_VS_REF, c["name"] + " acc"))
+        worst = max(worst, assert_close_kcal(cond, c["cond"], ATOL_VS_REF, RTOL_VS_REF, c["name"] + " cond"))
+        d = c["delta"]
+        assert np.all(cond[:d] == 0) and np.all(acc[len(acc) - d + 1:] == 0), c["name"]
+    print(f"W={W} delta={delta}: {len(cases)} cases, max |d| vs reference = {worst:.3e} kcal/mol")
+
+
+def test_fresh_random_vs_oracle(oracle_lib):
+    rng = np.random.default_rng(4242)
+    seqs = ["".join("ACGU"[k] for k in rng.integers(0, 4, L)) for L in (17, 64, 129, 257, 400, 511, 777)]
+    seqs.append("".join("ACGUNacgut"[k] for k in rng.integers(0, 10, 300)))
+    res = rac(70, 5).run_batch(seqs)
+    ora, _ = oracle_lib.run_batch(seqs, 70, 5)
+    for s, (a, c), (oa, oc) in zip(seqs, res, ora):
+        assert_close_kcal(a, oa, ATOL_VS_REF, RTOL_VS_REF, f"L={len(s)} acc")
+        assert_close_kcal(c, oc, ATOL_VS_REF, RTOL_VS_REF, f"L={len(s)} cond")
+
+
+def test_vs_exact_math_twin(oracle_lib):
+    """Against exact libm the CUDA path is at float-rounding level (the reference is not)."""
+    rng = np.random.default_rng(99)
+    seq = "".join("ACGU"[k] for k in rng.integers(0, 4, 900))
+    a, c = rac(70, 5).run(seq)
+    ea, ec = oracle_lib.run_exact(seq, 70, 5)
+    assert_close_kcal(a, ea, ATOL_VS_EXACT, RTOL_VS_EXACT, "acc")
+    assert_close_kcal(c, ec, ATOL_VS_EXACT, RTOL_VS_EXACT, "cond")
+
+
+def _cfg2_sample(n):
+    from priblast_b200 import workloads
+    return workloads.cfg2(first=n)
+
+
+def test_batch_split_and_order_invariance():
+    """Results must not depend on batching or input order (bit-identical)."""
+    seqs = _cfg2_sample(48)
+    big = rac(70, 5).run_batch(seqs)
+    small = rac(70, 5, max_batch_bytes=400 << 20).run_batch(seqs)  # forces several device batches
+    assert rac(70, 5, max_batch_bytes=400 << 20).counters()["batches"] > 1
+    perm = np.random.default_rng(5).permutation(len(seqs))
+    shuf = rac(70, 5).run_batch([seqs[k] for k in perm])
+    for k in range(len(seqs)):
+        assert np.array_equal(big[k][0].view(np.uint32), small[k][0].view(np.uint32))
+        assert np.array_equal(big[k][1].view(np.uint32), small[k][1].view(np.uint32))
+    for j, k in enumerate(perm):
+        assert np.array_equal(big[k][0].view(np.uint32), shuf[j][0].view(np.uint32))
+        assert np.array_equal(big[k][1].view(np.uint32), shuf[j][1].view(np.uint32))
+
+
+def test_alphabet_equivalences():
+    """raccess.cpp:55-68: case-insensitive, T == U, anything else is 'unknown'."""
+    rng = np.random.default_rng(8)
+    s = "".join("ACGU"[k] for k in rng.integers(0, 4, 350))
+    r = rac(70, 5)
+    base = r.run(s)
+    for variant in (s.lower(), s.replace("U", "T"), s.replace("U", "t")):
+        got = r.run(variant)
+        assert np.array_equal(base[0].view(np.uint32), got[0].view(np.uint32))
+        assert np.array_equal(base[1].view(np.uint32), got[1].view(np.uint32))
+    a_n, _ = r.run(s[:100] + "N" + s[101:])
+    a_x, _ = r.run(s[:100] + "X" + s[101:])
+    assert np.array_equal(a_n.view(np.uint32), a_x.view(np.uint32))
+
+
+def test_full_size_cfg1_sample_vs_reference(oracle_lib):
+    """cfg1 (1,000 x 500 nt, W=70, delta=5: the Q1 clamp regime) — all 1,000 on the GPU, a slice checked
+    against the compiled reference (or the restatement), the rest through properties."""
+    from priblast_b200 import workloads
+    from oracle_py import RefLib
+    seqs = workloads.cfg1()
+    res = rac(70, 5).run_batch(seqs)
+    assert len(res) == 1000
+    idx = list(range(0, 1000, 40))
+    checker = RefLib() if RefLib.available() else oracle_lib
+    ora, _ = checker.run_batch([seqs[k] for k in idx], 70, 5)
+    for k, (oa, oc) in zip(idx, ora):
+        assert_close_kcal(res[k][0], oa, ATOL_VS_REF, RTOL_VS_REF, f"seq {k} acc")
+        assert_close_kcal(res[k][1], oc, ATOL_VS_REF, RTOL_VS_REF, f"seq {k} cond")
+    allv = np.concatenate([np.concatenate(r) for r in res])
+    assert np.all(np.isfinite(allv))
+    for a, c in res:
+        assert np.all(a[:496] > -1.0) and np.all(a[:496] < 60.0)
+        assert np.all(c[:5] == 0) and np.all(a[496:] == 0)
+
+
+def test_long_sequence_log_path(oracle_lib):
+    """Z > 690 (log-sum biloop path of raccess.cpp:683-771) on an 6 kb sequence."""
+    from priblast_b200 import workloads
+    seq = workloads.cfg3(first=1)[0][:6000]
+    a, c = rac(70, 5).run(seq)
+    ea, ec = oracle_lib.run_exact(seq, 70, 5)
+    assert_close_kcal(a, ea, ATOL_VS_EXACT, RTOL_VS_EXACT, "acc")
+    assert_close_kcal(c, ec, ATOL_VS_EXACT, RTOL_VS_EXACT, "cond")
+
+
+def test_edge_lengths():
+    r = rac(70, 5)
+    res = r.run_batch(["", "A", "ACG", "ACGU", "ACGUA", "GGGAAACCC"])
+    assert [len(a) for a, _ in res] == [0, 1, 3, 4, 5, 9]
+    for a, c in res[:4]:  # L < delta: the vector form returns zeros (raccess.cpp:510-527 never iterate)
+        assert np.all(a == 0) and np.all(c == 0)
+    assert res[4][0][0] != 0 and np.all(res[4][0][1:] == 0)
+
+
+def test_staged_api_and_counters():
+    seqs = _cfg2_sample(16)
+    r = rac(70, 5)
+    want = r.run_batch(seqs)
+    nt = r.stage(seqs)
+    r.compute()
+    r.sync()
+    got = r.fetch()
+    for (a, c), (b, d) in zip(want, got):
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32)) and np.array_equal(c.view(np.uint32), d.view(np.uint32))
+    cnt = r.counters()
+    assert cnt["nucleotides"] >= nt and cnt["kernel_ms"] > 0 and cnt["kernel_launches"] > 0
+
+
+def test_record_bytes_match_reference_file():
+    """`.acc` record of one sequence equals the fixture's record layout with GPU numbers inside."""
+    case = next(c for c in GOLDEN if c["name"] == "rand_L100_W70_d5")
+    r = rac(70, 5)
+    acc, cond = r.run(case["seq"])
+    rec = r.record_bytes(acc, cond)
+    n1 = np.frombuffer(rec[:4], np.int32)[0]
+    assert n1 == 96 and len(rec) == 8 + 4 * (200 - 5 + 1)
+    assert_close_kcal(np.frombuffer(rec[4:4 + 4 * n1], np.float32), case["acc"][:n1], ATOL_VS_REF, RTOL_VS_REF)
