@@ -29,7 +29,10 @@
 
 namespace prib {
 
-typedef double real;
+#ifndef PRIB_REAL
+#define PRIB_REAL double
+#endif
+typedef PRIB_REAL real;
 
 enum { kTurn = 3, kMaxLoop = 30, kMaxSpan = 200, kPad = 32 };
 
