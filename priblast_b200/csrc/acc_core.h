@@ -29,11 +29,6 @@
 
 namespace prib {
 
-#ifndef PRIB_REAL
-#define PRIB_REAL double
-#endif
-typedef PRIB_REAL real;
-
 enum { kTurn = 3, kMaxLoop = 30, kMaxSpan = 200, kPad = 32 };
 
 // Band arrays (see DESIGN.md §3 for who reads what).
@@ -59,6 +54,38 @@ enum Arr {
   kNumArr
 };
 
+PRIB_HD int imin(int a, int b) { return a < b ? a : b; }
+PRIB_HD int imax(int a, int b) { return a > b ? a : b; }
+
+PRIB_HD int idx11(int t, int t2, int a, int b) { return ((t * 8 + t2) * 5 + a) * 5 + b; }
+PRIB_HD int idx21(int t, int t2, int a, int b, int c) { return (((t * 8 + t2) * 5 + a) * 5 + b) * 5 + c; }
+PRIB_HD int idx22(int t, int t2, int a, int b, int c, int d) {
+  return ((((t * 8 + t2) * 5 + a) * 5 + b) * 5 + c) * 5 + d;
+}
+
+
+// Uniformly indexed stencil coefficients live in __constant__ memory on the device (one LDC broadcast
+// per warp instead of a load through L1); filled by the host at context creation.
+#if defined(__CUDACC__)
+static __constant__ double g_conv_d[32 * 32];
+static __constant__ float g_conv_f[32 * 32];
+static __constant__ double g_bulge_d[32];
+static __constant__ float g_bulge_f[32];
+template <typename real> struct ConstTab;
+template <> struct ConstTab<double> {
+  static __device__ __forceinline__ const double *conv() { return g_conv_d; }
+  static __device__ __forceinline__ const double *bulge() { return g_bulge_d; }
+};
+template <> struct ConstTab<float> {
+  static __device__ __forceinline__ const float *conv() { return g_conv_f; }
+  static __device__ __forceinline__ const float *bulge() { return g_bulge_f; }
+};
+#endif
+
+// Everything below is generic in the scalar type of the band arithmetic: Core<double> is the reference
+// precision path, Core<float> the fast path.
+template <typename real>
+struct Core {
 // Boltzmann factors exp(-E/kT) of the scaled tables of raccess.hpp:105-158 (built on the host).
 struct SmallTables {
   real e_hairpin[kMaxSpan + 8];  // [loop size], incl. the lxc37 extrapolation of raccess.cpp:823
@@ -99,11 +126,25 @@ struct Ctx {
   PRIB_HD real ld(int a, int d, long long g) const { return arr[a][(long long)d * NC + g]; }
 };
 
-PRIB_HD int imin(int a, int b) { return a < b ? a : b; }
-PRIB_HD int imax(int a, int b) { return a > b ? a : b; }
 
 // exp(CalcDangleEnergy(type,a,b)), raccess.cpp:244-256.  sa = s[a], sb1 = s[b+1].
-PRIB_HD real e_dangle(const SmallTables &T, int t, bool a_gt0, int sa, bool b_lt_L, int sb1) {
+// stencil coefficient tables: constant memory on the device, the SmallTables copy on the host
+static PRIB_HD const real *conv_tab(const SmallTables &T) {
+#if defined(__CUDA_ARCH__)
+  return ConstTab<real>::conv();
+#else
+  return &T.conv[0][0];
+#endif
+}
+static PRIB_HD const real *bulge_tab(const SmallTables &T) {
+#if defined(__CUDA_ARCH__)
+  return ConstTab<real>::bulge();
+#else
+  return T.e_bulge;
+#endif
+}
+
+static PRIB_HD real e_dangle(const SmallTables &T, int t, bool a_gt0, int sa, bool b_lt_L, int sb1) {
   real x = 1;
   if (a_gt0) x *= T.e_d5[t][sa];
   if (b_lt_L) x *= T.e_d3[t][sb1];
@@ -111,16 +152,10 @@ PRIB_HD real e_dangle(const SmallTables &T, int t, bool a_gt0, int sa, bool b_lt
   return x;
 }
 
-PRIB_HD int idx11(int t, int t2, int a, int b) { return ((t * 8 + t2) * 5 + a) * 5 + b; }
-PRIB_HD int idx21(int t, int t2, int a, int b, int c) { return (((t * 8 + t2) * 5 + a) * 5 + b) * 5 + c; }
-PRIB_HD int idx22(int t, int t2, int a, int b, int c, int d) {
-  return ((((t * 8 + t2) * 5 + a) * 5 + b) * 5 + c) * 5 + d;
-}
-
 struct ColInfo {
   int sq, L, i;
 };
-PRIB_HD bool col_info(const Ctx &c, long long g, ColInfo &ci) {
+static PRIB_HD bool col_info(const Ctx &c, long long g, ColInfo &ci) {
   int sq = c.col_seq[g];
   if (sq < 0) return false;
   ci.sq = sq;
@@ -133,7 +168,7 @@ PRIB_HD bool col_info(const Ctx &c, long long g, ColInfo &ci) {
 // Inside: one cell (i, j = i + d) of CalcInsideVariable (raccess.cpp:99-228), span-wavefront order.
 // Every source lies at a smaller span (validated bit-identical for the reference).
 // ------------------------------------------------------------------------------------------------
-PRIB_HD void inside_cell(const Ctx &c, long long g, int d) {
+static PRIB_HD void inside_cell(const Ctx &c, long long g, int d) {
   ColInfo ci;
   if (!col_info(c, g, ci)) return;
   const int L = ci.L, i = ci.i, j = i + d;
@@ -211,7 +246,7 @@ PRIB_HD void inside_cell(const Ctx &c, long long g, int d) {
 // Outer arrays (raccess.cpp:230-241 and :260-271) as scaled linear recurrences; results stored as logs.
 // ring: 256 doubles of scratch.  One caller per sequence.
 // ------------------------------------------------------------------------------------------------
-PRIB_HD void scan_alpha_outer(const Ctx &c, int sq, double *ring) {
+static PRIB_HD void scan_alpha_outer(const Ctx &c, int sq, double *ring) {
   const int L = c.seq_len[sq], W = c.W;
   const long long off = c.seq_off[sq];
   const double kBig = 1.3407807929942597e154;  // 2^512
@@ -232,7 +267,7 @@ PRIB_HD void scan_alpha_outer(const Ctx &c, int sq, double *ring) {
   }
 }
 
-PRIB_HD void scan_beta_outer(const Ctx &c, int sq, double *ring) {
+static PRIB_HD void scan_beta_outer(const Ctx &c, int sq, double *ring) {
   const int L = c.seq_len[sq], W = c.W;
   const long long off = c.seq_off[sq];
   const double kBig = 1.3407807929942597e154;
@@ -258,7 +293,7 @@ PRIB_HD void scan_beta_outer(const Ctx &c, int sq, double *ring) {
 // All values are Beta / Z.  Beta_stemend(i,j) == B_STEM[d+2][g-1] (rows above W+1 are zero, which is
 // the `q - p >= W ? -INF` of :278-279).
 // ------------------------------------------------------------------------------------------------
-PRIB_HD void outside_cell(const Ctx &c, long long g, int d) {
+static PRIB_HD void outside_cell(const Ctx &c, long long g, int d) {
   ColInfo ci;
   if (!col_info(c, g, ci)) return;
   const int L = ci.L, p = ci.i, q = p + d, W = c.W;
@@ -347,7 +382,7 @@ PRIB_HD void outside_cell(const Ctx &c, long long g, int d) {
 // The reference's k-loops (:644-658) add T to every window start k inside a strand; summing the strand
 // weights first and gathering per k afterwards gives the same sums.
 // ------------------------------------------------------------------------------------------------
-PRIB_HD real loop_weight(const Ctx &c, const SmallTables &T, const uint8_t *s, long long g, int dp, int te,
+static PRIB_HD real loop_weight(const Ctx &c, const SmallTables &T, const uint8_t *s, long long g, int dp, int te,
                          real bse, real bseO, real bseB, int u1, int u2) {
   // s = S + column of i; outer pair (i, j'+1) with j' = i + dp; inner cell (i+u1, j'-u2).
   const int sum = u1 + u2;
@@ -375,7 +410,7 @@ PRIB_HD real loop_weight(const Ctx &c, const SmallTables &T, const uint8_t *s, l
 }
 
 // thread = left index i; writes ML[u1][g] for u1 in [delta, 30]
-PRIB_HD void biloop_left(const Ctx &c, long long g) {
+static PRIB_HD void biloop_left(const Ctx &c, long long g) {
   ColInfo ci;
   if (!col_info(c, g, ci)) return;
   const int L = ci.L, i = ci.i, W = c.W;
@@ -399,7 +434,7 @@ PRIB_HD void biloop_left(const Ctx &c, long long g) {
 }
 
 // thread = right end j' of the outer cell; writes MR[u2][g'] for u2 in [delta, 30]
-PRIB_HD void biloop_right(const Ctx &c, long long g2) {
+static PRIB_HD void biloop_right(const Ctx &c, long long g2) {
   ColInfo ci;
   if (!col_info(c, g2, ci)) return;
   const int L = ci.L, jp = ci.i, W = c.W;
@@ -424,7 +459,7 @@ PRIB_HD void biloop_right(const Ctx &c, long long g2) {
 }
 
 // thread = i; X_SUFH[dd][g] = sum over j >= i+dd of Beta_stemend(i,j-1) * exp(Hairpin(i,j))   (:546-561)
-PRIB_HD void hairpin_suffix(const Ctx &c, long long g) {
+static PRIB_HD void hairpin_suffix(const Ctx &c, long long g) {
   ColInfo ci;
   if (!col_info(c, g, ci)) return;
   const int L = ci.L, i = ci.i, W = c.W;
@@ -444,7 +479,7 @@ PRIB_HD void hairpin_suffix(const Ctx &c, long long g) {
 }
 
 // fmath::log(float), fmath.hpp:738-752, with the host-built table.  No FMA contraction.
-PRIB_HD float fmath_logf(const Ctx &c, float x) {
+static PRIB_HD float fmath_logf(const Ctx &c, float x) {
   union { float f; uint32_t u; } v;
   v.f = x;
   const int a = (int)(v.u & (0xFFu << 23));
@@ -469,7 +504,7 @@ struct WindowProb {
   real ext, hp, multi, loop_b, loop_c;
 };
 
-PRIB_HD real multi_prob(const Ctx &c, long long off, int L, int x, int w) {  // :581-612
+static PRIB_HD real multi_prob(const Ctx &c, long long off, int L, int x, int w) {  // :581-612
   const int W = c.W;
   real v = 0;
   const int hi = imin(x + W, L);
@@ -481,7 +516,7 @@ PRIB_HD real multi_prob(const Ctx &c, long long off, int L, int x, int w) {  // 
   return v;
 }
 
-PRIB_HD real hairpin_prob(const Ctx &c, long long off, int x, int w) {  // :536-579
+static PRIB_HD real hairpin_prob(const Ctx &c, long long off, int x, int w) {  // :536-579
   real v = 0;
   for (int i = imax(1, x - c.W); i < x; ++i) {
     const int dd = x + w - i;
@@ -491,7 +526,7 @@ PRIB_HD real hairpin_prob(const Ctx &c, long long off, int x, int w) {  // :536-
 }
 
 // b[k]: strands that end exactly at the window end; c[k]: strands that extend beyond it (:644-658)
-PRIB_HD void biloop_gather(const Ctx &c, long long off, int L, int k, real &b, real &cc) {
+static PRIB_HD void biloop_gather(const Ctx &c, long long off, int L, int k, real &b, real &cc) {
   const int w = c.delta;
   b = 0;
   cc = 0;
@@ -512,7 +547,7 @@ PRIB_HD void biloop_gather(const Ctx &c, long long off, int L, int k, real &b, r
 
 // Final per-position step: CalcAccessibility :484-528 incl. the finalisation quirks of :667-680 (Q1, Q3)
 // and :754-770 (Q4).  thread = x (1-based start position) = left index of column g.
-PRIB_HD void finalize_position(const Ctx &c, long long g) {
+static PRIB_HD void finalize_position(const Ctx &c, long long g) {
   ColInfo ci;
   if (!col_info(c, g, ci)) return;
   const int L = ci.L, x = ci.i, w = c.delta;
@@ -552,5 +587,7 @@ PRIB_HD void finalize_position(const Ctx &c, long long g) {
     cond[x + w - 1] = (float)((-(double)fmath_logf(c, (float)pc) * kT) / 1000 - a);
   }
 }
+
+};  // struct Core
 
 }  // namespace prib

@@ -8,6 +8,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <numeric>
@@ -17,8 +18,14 @@
 #include "../../include/priblast_acc.h"
 #include "acc_core.h"
 #include "acc_tables.h"
+#include "acc_tile.h"
 
 using namespace prib;
+typedef double real;
+typedef Core<real> K;
+typedef K::Ctx Ctx;
+typedef K::SmallTables SmallTables;
+typedef Tile<real> TL;
 
 // ---------------------------------------------------------------------------------------------
 // kernels
@@ -29,42 +36,168 @@ constexpr int kThreads = 128;
 
 __global__ void __launch_bounds__(kThreads) k_inside(Ctx c, int d) {
   const long long g = (long long)blockIdx.x * kThreads + threadIdx.x;
-  if (g < c.NC) inside_cell(c, g, d);
+  if (g < c.NC) K::inside_cell(c, g, d);
 }
 
 __global__ void __launch_bounds__(kThreads) k_outside(Ctx c, int d) {
   const long long g = (long long)blockIdx.x * kThreads + threadIdx.x;
-  if (g < c.NC) outside_cell(c, g, d);
+  if (g < c.NC) K::outside_cell(c, g, d);
 }
 
 __global__ void __launch_bounds__(32) k_outer_scans(Ctx c) {
   const int sq = blockIdx.x * 32 + threadIdx.x;
   if (sq >= c.nseq) return;
   double ring[256];
-  scan_alpha_outer(c, sq, ring);
-  scan_beta_outer(c, sq, ring);
+  K::scan_alpha_outer(c, sq, ring);
+  K::scan_beta_outer(c, sq, ring);
 }
 
 __global__ void __launch_bounds__(kThreads) k_biloop_left(Ctx c) {
   const long long g = (long long)blockIdx.x * kThreads + threadIdx.x;
-  if (g < c.NC) biloop_left(c, g);
+  if (g < c.NC) K::biloop_left(c, g);
 }
 
 __global__ void __launch_bounds__(kThreads) k_biloop_right(Ctx c) {
   const long long g = (long long)blockIdx.x * kThreads + threadIdx.x;
-  if (g < c.NC) biloop_right(c, g);
+  if (g < c.NC) K::biloop_right(c, g);
 }
 
 __global__ void __launch_bounds__(kThreads) k_hairpin_suffix(Ctx c) {
   const long long g = (long long)blockIdx.x * kThreads + threadIdx.x;
-  if (g < c.NC) hairpin_suffix(c, g);
+  if (g < c.NC) K::hairpin_suffix(c, g);
 }
 
 __global__ void __launch_bounds__(kThreads) k_finalize(Ctx c) {
   const long long g = (long long)blockIdx.x * kThreads + threadIdx.x;
-  if (g < c.NC) finalize_position(c, g);
+  if (g < c.NC) K::finalize_position(c, g);
 }
 
+
+
+// ---- kernel set v2: tile-persistent span march (acc_tile.h) ------------------------------------
+// grid = resident CTAs (one per SM: the rings take ~all shared memory), blockDim = TC, tiles round-robin.
+// dynamic smem: kTileRows * TC reals + (TC + 16) base codes.
+__global__ void __launch_bounds__(1024, 1) k_inside_tile(Ctx c, int TX, long long ntiles, real *scratch) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int TC = blockDim.x, t = threadIdx.x, W = c.W;
+  real *base = reinterpret_cast<real *>(smem_raw);
+  uint8_t *sS = reinterpret_cast<uint8_t *>(base + (size_t)kTileRows * TC);
+  real *scrM1 = scratch + (size_t)blockIdx.x * 2 * (W + 4) * TC;
+  real *scrM2 = scrM1 + (size_t)(W + 4) * TC;
+  const TL::InSmem sm = TL::carve_in(base, TC, sS);
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    TL::Geo ge;
+    ge.g0 = tile * TX;
+    ge.TC = TC;
+    ge.TX = TX;
+    ge.H = W + 1;
+    __syncthreads();  // previous tile fully consumed
+    for (int r = 0; r < kTileRows; r++) base[(size_t)r * TC + t] = 0;
+    for (int k = t; k < TC + 8; k += TC) sS[k] = (ge.g0 + k < c.NC) ? c.S[ge.g0 + k] : 0;
+    TL::ColState cs;
+    TL::col_state(c, ge.g0 + t, cs);
+    __syncthreads();
+    for (int d = kTurn; d <= W + 1; d++) {
+      TL::inside_span(c, ge, sm, scrM1, scrM2, t, cs, d);
+      __syncthreads();
+    }
+  }
+}
+
+__global__ void __launch_bounds__(1024, 1) k_outside_tile(Ctx c, int TX, long long ntiles, real *scratch) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int TC = blockDim.x, t = threadIdx.x, W = c.W;
+  real *base = reinterpret_cast<real *>(smem_raw);
+  real *scrBif = scratch + (size_t)blockIdx.x * 2 * (W + 4) * TC;
+  const TL::OutSmem sm = TL::carve_out(base, TC);
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    TL::Geo ge;
+    ge.g0 = tile * TX;
+    ge.TC = TC;
+    ge.TX = TX;
+    ge.H = W + 1;
+    __syncthreads();
+    for (int r = 0; r < kTileRows; r++) base[(size_t)r * TC + t] = 0;
+    TL::ColState cs;
+    TL::col_state(c, ge.g0 - ge.H + t, cs);
+    __syncthreads();
+    int slot = (W + 1) % kRingOut;
+    for (int d = W + 1; d >= kTurn; d--) {
+      TL::outside_span(c, ge, sm, scrBif, t, cs, d, slot);
+      slot = slot == 0 ? kRingOut - 1 : slot - 1;
+      __syncthreads();
+    }
+  }
+}
+
+// ---- outer arrays: one warp per sequence (raccess.cpp:230-241, 260-271) ------------------------
+// The recurrence is serial in the position but each step is a W-term dot product: lanes split the
+// terms, a butterfly adds them, the window of scaled values lives in shared memory.  Values are kept
+// linear with an exact power-of-two rescale; logs are taken 32 positions at a time by all lanes.
+constexpr int kScanWarps = 4;
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+template <bool ALPHA>
+__device__ void warp_scan(const Ctx &c, int sq, double *ring, int lane) {
+  const int L = c.seq_len[sq], W = c.W;
+  const long long off = c.seq_off[sq];
+  const double kBig = 1.3407807929942597e154, kLn2 = 0.6931471805599453094;
+  double *dst = ALPHA ? c.lao : c.lbo;
+  const real *src = c.arr[ALPHA ? A_STEMDE : A_STEMD];
+  long long e2 = 0;
+  const int start = ALPHA ? 0 : L;
+  if (lane == 0) {
+    ring[start & 255] = 1.0;
+    dst[off + start] = 0.0;
+  }
+  __syncwarp();
+  double keep_v = 1.0;   // value of the position this lane will take the log of
+  long long keep_e = 0;
+  int keep_pos = -1;
+  for (int step = 1; step <= L; ++step) {
+    const int i = ALPHA ? step : L - step;
+    const long long col = off + i;
+    const int dmax = ALPHA ? imin(W + 1, i) : imin(W + 1, L - i);
+    double part = 0;
+    for (int d = 5 + lane; d <= dmax; d += 32) {
+      const int j = ALPHA ? i - d : i + d;
+      part += (double)src[(long long)d * c.NC + col] * ring[j & 255];
+    }
+    double v = warp_sum(part) + ring[(ALPHA ? i - 1 : i + 1) & 255];
+    if (v > kBig) {  // uniform: every lane holds the same v
+      const int lo = ALPHA ? imax(0, i - W - 2) : i + 1, hi = ALPHA ? i - 1 : imin(L, i + W + 2);
+      for (int k = lo + lane; k <= hi; k += 32) ring[k & 255] *= 1.0 / kBig;
+      v *= 1.0 / kBig;
+      e2 += 512;
+    }
+    if (lane == 0) ring[i & 255] = v;
+    if ((step & 31) == lane) {
+      keep_v = v;
+      keep_e = e2;
+      keep_pos = i;
+    }
+    __syncwarp();
+    if ((step & 31) == 31 || step == L) {
+      if (keep_pos >= 0) dst[off + keep_pos] = log(keep_v) + (double)keep_e * kLn2;
+      keep_pos = -1;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(32 * kScanWarps) k_outer_scans_warp(Ctx c) {
+  __shared__ double rings[kScanWarps][256];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int sq = blockIdx.x * kScanWarps + warp;
+  if (sq >= c.nseq) return;
+  warp_scan<true>(c, sq, rings[warp], lane);
+  __syncwarp();
+  warp_scan<false>(c, sq, rings[warp], lane);
+}
 
 // Issue-rate probes for the roofline denominators (MEASURED_PEAKS.json has no SFU / FP32 /
 // FP64 figure, so they are measured here): 8 independent dependency chains per thread.
@@ -150,6 +283,11 @@ struct prib_ctx {
   SmallTables *d_small = nullptr;
   real *d_int11 = nullptr, *d_int21 = nullptr, *d_int22 = nullptr;
   float *d_log = nullptr;
+  // tile kernels
+  int kernel_set = 2;  // 1 = per-span launches (v1), 2 = tile-persistent (v2)
+  int TC = 0, grid_tiles = 0;
+  size_t tile_smem = 0;
+  real *d_tile_scratch = nullptr;
   // DP scratch
   char *d_state = nullptr;
   long long state_cap_bytes = 0, max_cols = 0;
@@ -236,11 +374,28 @@ int run_batch(prib_ctx *c, const Batch &b) {
   CU(cudaMemsetAsync(c->d_state, 0, (size_t)used, st));
   const unsigned grid = (unsigned)((b.NC + kThreads - 1) / kThreads);
   CU(cudaEventRecord(c->evp[1], st));
-  for (int d = kTurn; d <= c->W + 1; d++) k_inside<<<grid, kThreads, 0, st>>>(k, d);
+  const int TX = c->TC - (c->W + 1);
+  const long long ntiles = (b.NC + TX - 1) / TX;
+  const int tgrid = (int)std::min<long long>(ntiles, c->grid_tiles);
+  long long launches = 5;
+  if (c->kernel_set == 1) {
+    for (int d = kTurn; d <= c->W + 1; d++) k_inside<<<grid, kThreads, 0, st>>>(k, d);
+    launches += c->W - 1;
+  } else {
+    k_inside_tile<<<tgrid, c->TC, c->tile_smem, st>>>(k, TX, ntiles, c->d_tile_scratch);
+    launches += 1;
+  }
   CU(cudaEventRecord(c->evp[2], st));
-  k_outer_scans<<<(b.n + 31) / 32, 32, 0, st>>>(k);
+  if (c->kernel_set == 1) k_outer_scans<<<(b.n + 31) / 32, 32, 0, st>>>(k);
+  else k_outer_scans_warp<<<(b.n + kScanWarps - 1) / kScanWarps, 32 * kScanWarps, 0, st>>>(k);
   CU(cudaEventRecord(c->evp[3], st));
-  for (int d = c->W + 1; d >= kTurn; d--) k_outside<<<grid, kThreads, 0, st>>>(k, d);
+  if (c->kernel_set == 1) {
+    for (int d = c->W + 1; d >= kTurn; d--) k_outside<<<grid, kThreads, 0, st>>>(k, d);
+    launches += c->W - 1;
+  } else {
+    k_outside_tile<<<tgrid, c->TC, c->tile_smem, st>>>(k, TX, ntiles, c->d_tile_scratch);
+    launches += 1;
+  }
   CU(cudaEventRecord(c->evp[4], st));
   k_biloop_left<<<grid, kThreads, 0, st>>>(k);
   CU(cudaEventRecord(c->evp[5], st));
@@ -251,7 +406,7 @@ int run_batch(prib_ctx *c, const Batch &b) {
   CU(cudaEventRecord(c->evp[7], st));
   CU(cudaGetLastError());
   c->phases_pending = true;
-  c->cnt.kernel_launches += 2 * (c->W - 1) + 5;
+  c->cnt.kernel_launches += launches;
   c->cnt.batches += 1;
   return PRIB_OK;
 }
@@ -317,6 +472,27 @@ int prib_acc_create(prib_ctx **out, const prib_acc_params *params) {
   CUB(cudaMalloc(&c->d_log, tab.log_tbl.size() * sizeof(float)));
   CUB(cudaMemcpy(c->d_log, tab.log_tbl.data(), tab.log_tbl.size() * sizeof(float), cudaMemcpyHostToDevice));
 
+  CUB(cudaMemcpyToSymbol(g_conv_d, &tab.small.conv[0][0], sizeof(double) * 32 * 32));
+  CUB(cudaMemcpyToSymbol(g_bulge_d, tab.small.e_bulge, sizeof(double) * 32));
+  {
+    // tile kernels: the widest CTA whose rings fit the opt-in shared memory of this device
+    const char *ks = getenv("PRIB_KERNELS");
+    c->kernel_set = (ks && ks[0] == '1') ? 1 : 2;
+    cudaDeviceProp prop;
+    CUB(cudaGetDeviceProperties(&prop, params->device));
+    const size_t smem_max = prop.sharedMemPerBlockOptin;
+    int TC = (int)((smem_max - 64) / (kTileRows * sizeof(real) + 1)) / 32 * 32;
+    if (TC > 1024) TC = 1024;
+    const char *tce = getenv("PRIB_TILE_COLS");
+    if (tce && atoi(tce) >= c->W + 34 && atoi(tce) <= TC) TC = atoi(tce) / 32 * 32;
+    if (TC < c->W + 34) return bail(fail(PRIB_ECUDA, "shared memory too small for the tile kernels"));
+    c->TC = TC;
+    c->tile_smem = (size_t)kTileRows * TC * sizeof(real) + TC + 16;
+    c->grid_tiles = prop.multiProcessorCount;
+    CUB(cudaFuncSetAttribute(k_inside_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->tile_smem));
+    CUB(cudaFuncSetAttribute(k_outside_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->tile_smem));
+    CUB(cudaMalloc(&c->d_tile_scratch, (size_t)c->grid_tiles * 2 * (c->W + 4) * TC * sizeof(real)));
+  }
   size_t free_b = 0, total_b = 0;
   CUB(cudaMemGetInfo(&free_b, &total_b));
   long long budget = params->max_batch_bytes > 0 ? params->max_batch_bytes : (long long)(free_b * 0.6);
@@ -337,6 +513,7 @@ void prib_acc_destroy(prib_ctx *c) {
   cudaSetDevice(c->prm.device);
   free_batches(c);
   cudaFree(c->d_state);
+  cudaFree(c->d_tile_scratch);
   cudaFree(c->d_small);
   cudaFree(c->d_int11);
   cudaFree(c->d_int21);

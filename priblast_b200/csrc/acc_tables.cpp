@@ -7,7 +7,8 @@
 
 namespace prib {
 
-bool build_tables(int W, HostTables &out, std::string &err) {
+template <typename real>
+bool build_tables(int W, HostTablesT<real> &out, std::string &err) {
   const prib_turner_params *p = prib_turner_embedded();
   if (!p) {
     err = "embedded Turner parameter blob missing or corrupt";
@@ -17,7 +18,7 @@ bool build_tables(int W, HostTables &out, std::string &err) {
     err = "maximal span out of range (1.." + std::to_string((int)kMaxSpan) + ")";
     return false;
   }
-  SmallTables &T = out.small;
+  typename Core<real>::SmallTables &T = out.small;
   std::memset(&T, 0, sizeof(T));
   // energy_par.hpp:12-13; every scaled value is (-E*10)/kT as in raccess.hpp:105-158
   const double kT = (p->temperature_c + p->k0) * p->gasconst;
@@ -99,6 +100,9 @@ bool build_tables(int W, HostTables &out, std::string &err) {
   }
   return true;
 }
+
+template bool build_tables<double>(int, HostTablesT<double> &, std::string &);
+template bool build_tables<float>(int, HostTablesT<float> &, std::string &);
 
 void build_layout(int n, const char *const *seqs, const int32_t *lens, BatchLayout &out) {
   out.seq_off.resize(n);

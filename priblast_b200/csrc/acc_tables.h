@@ -9,15 +9,19 @@
 
 namespace prib {
 
-struct HostTables {
-  SmallTables small;
+template <typename real>
+struct HostTablesT {
+  typename Core<real>::SmallTables small;
   std::vector<real> e_int11, e_int21, e_int22;
   std::vector<float> log_tbl;  // 2048 x (app, rev)
 };
+typedef HostTablesT<double> HostTables;
 
 // Scales the embedded Turner parameters exactly like Raccess::set_energy_parameters
-// (raccess.hpp:105-158) and exponentiates them.  Returns false if the blob is missing.
-bool build_tables(int W, HostTables &out, std::string &err);
+// (raccess.hpp:105-158) and exponentiates them (always in double; cast to `real` at the end).
+// Returns false if the blob is missing.  Instantiated for float and double.
+template <typename real>
+bool build_tables(int W, HostTablesT<real> &out, std::string &err);
 
 // Column layout of one batch: sequence k occupies columns seq_off[k] .. seq_off[k]+len[k]
 // (left indices 0..L), followed by >= kPad zero columns; the first sequence starts at kPad.

@@ -13,8 +13,12 @@
 
 #include "../../priblast_b200/csrc/acc_core.h"
 #include "../../priblast_b200/csrc/acc_tables.h"
+#include "../../priblast_b200/csrc/acc_tile.h"
 
 using namespace prib;
+typedef double real;
+typedef Core<real> K;
+typedef K::Ctx Ctx;
 
 namespace {
 
@@ -67,23 +71,57 @@ void run_dp(Emu &e) {
   const Ctx &c = e.c;
   double ring[256];
   for (int d = kTurn; d <= c.W + 1; d++)
-    for (long long g = 0; g < c.NC; g++) inside_cell(c, g, d);
+    for (long long g = 0; g < c.NC; g++) K::inside_cell(c, g, d);
   for (int k = 0; k < c.nseq; k++) {
-    scan_alpha_outer(c, k, ring);
-    scan_beta_outer(c, k, ring);
+    K::scan_alpha_outer(c, k, ring);
+    K::scan_beta_outer(c, k, ring);
   }
   for (int d = c.W + 1; d >= kTurn; d--)
-    for (long long g = 0; g < c.NC; g++) outside_cell(c, g, d);
+    for (long long g = 0; g < c.NC; g++) K::outside_cell(c, g, d);
+}
+
+// Emulation of the tile-persistent kernels (acc_tile.h): one "CTA" per tile, TC "threads", a barrier
+// (= end of the inner loop over t) after every span.
+void run_dp_tiled(Emu &e, int TC) {
+  typedef Tile<real> TL;
+  const Ctx &c = e.c;
+  const int W = c.W, H = W + 1, TX = TC - H;
+  const long long ntiles = (c.NC + TX - 1) / TX;
+  std::vector<real> smem((size_t)kTileRows * TC), scr((size_t)2 * (W + 4) * TC);
+  std::vector<uint8_t> sS((size_t)TC + 16);
+  std::vector<TL::ColState> cs(TC);
+  for (long long tile = 0; tile < ntiles; tile++) {
+    TL::Geo ge{tile * TX, TC, TX, H};
+    std::fill(smem.begin(), smem.end(), (real)0);
+    for (int k = 0; k < TC + 8; k++) sS[k] = (ge.g0 + k < c.NC) ? c.S[ge.g0 + k] : 0;
+    for (int t = 0; t < TC; t++) TL::col_state(c, ge.g0 + t, cs[t]);
+    TL::InSmem sm = TL::carve_in(smem.data(), TC, sS.data());
+    for (int d = kTurn; d <= W + 1; d++)
+      for (int t = 0; t < TC; t++) TL::inside_span(c, ge, sm, scr.data(), scr.data() + (size_t)(W + 4) * TC, t, cs[t], d);
+  }
+  double ring[256];
+  for (int k = 0; k < c.nseq; k++) {
+    K::scan_alpha_outer(c, k, ring);
+    K::scan_beta_outer(c, k, ring);
+  }
+  for (long long tile = 0; tile < ntiles; tile++) {
+    TL::Geo ge{tile * TX, TC, TX, H};
+    std::fill(smem.begin(), smem.end(), (real)0);
+    for (int t = 0; t < TC; t++) TL::col_state(c, ge.g0 - H + t, cs[t]);
+    TL::OutSmem sm = TL::carve_out(smem.data(), TC);
+    for (int d = W + 1; d >= kTurn; d--)
+      for (int t = 0; t < TC; t++) TL::outside_span(c, ge, sm, scr.data(), t, cs[t], d, d % kRingOut);
+  }
 }
 
 void run_acc(Emu &e) {
   const Ctx &c = e.c;
   for (long long g = 0; g < c.NC; g++) {
-    biloop_left(c, g);
-    biloop_right(c, g);
-    hairpin_suffix(c, g);
+    K::biloop_left(c, g);
+    K::biloop_right(c, g);
+    K::hairpin_suffix(c, g);
   }
-  for (long long g = 0; g < c.NC; g++) finalize_position(c, g);
+  for (long long g = 0; g < c.NC; g++) K::finalize_position(c, g);
 }
 
 }  // namespace
@@ -99,6 +137,21 @@ int hostemu_run_batch(int n, const char *const *seqs, const int32_t *lens, int W
   }
   if (!setup(e, n, seqs, lens, W, delta, out, acc_off, cond_off)) return -1;
   run_dp(e);
+  run_acc(e);
+  return 1;
+}
+
+// Same batch through the tile-persistent formulation; TC = emulated CTA width.
+int hostemu_run_batch_tiled(int n, const char *const *seqs, const int32_t *lens, int W, int delta, float *out,
+                            const int64_t *acc_off, const int64_t *cond_off, int TC) {
+  Emu e;
+  for (int k = 0; k < n; k++) {
+    std::memset(out + acc_off[k], 0, sizeof(float) * (size_t)lens[k]);
+    std::memset(out + cond_off[k], 0, sizeof(float) * (size_t)lens[k]);
+  }
+  if (!setup(e, n, seqs, lens, W, delta, out, acc_off, cond_off)) return -1;
+  if (TC <= W + 2) return -2;
+  run_dp_tiled(e, TC);
   run_acc(e);
   return 1;
 }
