@@ -36,7 +36,8 @@ typedef struct prib_acc_params {
   int32_t maximal_span;          /* W: reference `-w`, default 70 (db_construction_parameters.hpp:48) */
   int32_t min_accessible_length; /* delta: reference `-d`, default 5; must be > 1 (raccess.hpp:47)   */
   int32_t device;                /* CUDA device ordinal                                               */
-  int32_t mode;                  /* 0 = fast FP64 linear-domain path (the only mode in this round)    */
+  int32_t mode;                  /* 0 = auto: FP32 span-scaled engine (W <= 100) with on-GPU FP64 re-run
+                                    of range-flagged sequences; 1 = FP64 engine only                  */
   int64_t max_batch_bytes;       /* device-memory budget for DP state; 0 = 60 % of free memory        */
 } prib_acc_params;
 
@@ -55,6 +56,7 @@ typedef struct prib_acc_counters {
   int64_t dp_state_bytes; /* size of the DP scratch allocation */
   int64_t dp_state_bytes_used; /* part of it the largest batch so far used */
   double phase_ms[PRIB_NUM_PHASES]; /* device time per phase, summed over batches */
+  int64_t fp64_rerun_sequences;  /* sequences the FP32 engine flagged and the FP64 engine recomputed */
 } prib_acc_counters;
 
 /* Replaces the `Raccess` constructor.  One context per GPU; not re-entrant per context. */

@@ -98,6 +98,17 @@ struct SmallTables {
   real e_d3[8][5];               // includes TermAU for types > 2 (raccess.hpp:132-134)
   real tau[8];                   // exp(TermAU) for types > 2, else 1
   real e_mlbase, e_mlintern, e_mlclose;  // e_mlclose = exp(MLclosing + MLintern)
+  // Span scaling: stored Alpha-type values are cA * kappa^d * (true value), stored
+  // Beta-type values are cB * kappa^-d * (true value / Z).  kappa = cA = cB = 1 in the FP64 build; the
+  // FP32 build uses them to centre the dynamic range.  kappa^(u1+u2) is folded into conv / e_bulge /
+  // e_int11 / e_int21 / e_int22, kappa into e_mlbase, cA * kappa^d into e_hairpin[d].
+  real k2;                       // kappa^2
+  real inv_cA;                   // 1 / cA
+  real kacc;                     // kappa^2 / (cA cB): un-scales Beta_stemend * loop * Alpha_stem products
+  real kmul[2];                  // kappa^w / (cA cB) for w = delta, delta + 1 (CalcMultiProbability)
+  real sB[kMaxSpan + 8];         // cB * kappa^-d
+  real hpB[kMaxSpan + 8];        // [dd]: kappa^(dd+1) / cB * exp(hairpin length term of loop size dd-1)
+  double us[kMaxSpan + 8];       // kappa^-d / cA (outer-array scans run un-scaled in double)
   double kT;
   float log_c_log2;              // fmath LogVar::c_log2
   int8_t bp[5][5];
@@ -121,6 +132,7 @@ struct Ctx {
   double *lao, *lbo;       // log Alpha_outer / log Beta_outer per column
   const long long *acc_off, *cond_off;  // float offsets per sequence into out
   float *out;
+  int32_t *flags;          // per sequence: set when a stored value leaves the safe range (FP32 build)
 
   PRIB_HD real &at(int a, int d, long long g) const { return arr[a][(long long)d * NC + g]; }
   PRIB_HD real ld(int a, int d, long long g) const { return arr[a][(long long)d * NC + g]; }
@@ -142,6 +154,15 @@ static PRIB_HD const real *bulge_tab(const SmallTables &T) {
 #else
   return T.e_bulge;
 #endif
+}
+
+// Range guard of the FP32 build: stored band values must stay in [2^-55, 2^55] (or be exactly 0) so that
+// every product of two of them with a table factor, and every sum of a few hundred such products, stays
+// a normal float.  NaN and inf fail the first comparison.  Always true for double.
+static PRIB_HD bool in_safe_range(real v) {
+  if (sizeof(real) == 8) return true;
+  const real hi = (real)3.6028797018963968e16, lo = (real)2.7755575615628914e-17;
+  return (v <= hi) && (v == 0 || v >= lo);
 }
 
 static PRIB_HD real e_dangle(const SmallTables &T, int t, bool a_gt0, int sa, bool b_lt_L, int sb1) {
@@ -182,11 +203,12 @@ static PRIB_HD void inside_cell(const Ctx &c, long long g, int d) {
   real stem = 0;
   if (t) {
     const int t2 = T.bp[s[2]][s[d - 1]];
-    stem = c.ld(A_STEMEND, d - 2, g + 1) + c.ld(A_STEM, d - 2, g + 1) * T.e_stack[t][T.rt[t2]];
+    stem = T.k2 * (c.ld(A_STEMEND, d - 2, g + 1) + c.ld(A_STEM, d - 2, g + 1) * T.e_stack[t][T.rt[t2]]);
   }
   // Alpha_multibif :131-143  (multi1 / multi2 are zero below span 5)
   real mb = 0;
   for (int m = 5; m <= d - 5; ++m) mb += c.ld(A_MULTI1, m, g) * c.ld(A_MULTI2, d - m, g + m);
+  mb *= T.inv_cA;
   // Alpha_multi2 :145-162, multi1 :164-175, multi :177-191
   const real stemD = t ? stem * e_dangle(T, t, i > 0, si, j < L, sj1) : 0;
   const real m2 = stemD * T.e_mlintern + c.ld(A_MULTI2, d - 1, g) * T.e_mlbase;
@@ -256,7 +278,7 @@ static PRIB_HD void scan_alpha_outer(const Ctx &c, int sq, double *ring) {
   for (int i = 1; i <= L; ++i) {
     double v = ring[(i - 1) & 255];
     const int dmax = imin(W + 1, i);
-    for (int d = 5; d <= dmax; ++d) v += c.ld(A_STEMDE, d, off + i) * ring[(i - d) & 255];
+    for (int d = 5; d <= dmax; ++d) v += (double)c.ld(A_STEMDE, d, off + i) * c.T->us[d] * ring[(i - d) & 255];
     if (v > kBig) {
       for (int k = imax(0, i - W - 2); k < i; ++k) ring[k & 255] *= 1.0 / kBig;
       v *= 1.0 / kBig;
@@ -277,7 +299,7 @@ static PRIB_HD void scan_beta_outer(const Ctx &c, int sq, double *ring) {
   for (int i = L - 1; i >= 0; --i) {
     double v = ring[(i + 1) & 255];
     const int dmax = imin(W + 1, L - i);
-    for (int d = 5; d <= dmax; ++d) v += c.ld(A_STEMD, d, off + i) * ring[(i + d) & 255];
+    for (int d = 5; d <= dmax; ++d) v += (double)c.ld(A_STEMD, d, off + i) * c.T->us[d] * ring[(i + d) & 255];
     if (v > kBig) {
       for (int k = i + 1; k <= imin(L, i + W + 2); ++k) ring[k & 255] *= 1.0 / kBig;
       v *= 1.0 / kBig;
@@ -309,15 +331,17 @@ static PRIB_HD void outside_cell(const Ctx &c, long long g, int d) {
   if (inner) {
     // Beta_multi :281-308
     const int tt = T.rt[te];
-    bmulti = c.ld(B_MULTI, d + 1, g - 1) * T.e_mlbase + bse * T.e_mlclose * T.e_d3[tt][sp1] * T.e_d5[tt][sq_];
+    bmulti = c.ld(B_MULTI, d + 1, g - 1) * T.e_mlbase + T.k2 * bse * T.e_mlclose * T.e_d3[tt][sp1] * T.e_d5[tt][sq_];
     // Beta_multi1 :310-324   k = q + m
     real bm1 = 0;
     const int m1max = imin(L - q, W - d);
     for (int m = 5; m <= m1max; ++m) bm1 += c.ld(B_MULTIBIF, d + m, g) * c.ld(A_MULTI2, m, g + d);
+    bm1 *= T.inv_cA;
     // Beta_multi2 :326-352   k = p - m
-    bmulti2 = bm1 + c.ld(B_MULTI2, d + 1, g) * T.e_mlbase;
+    real ks = 0;
     const int m2max = imin(p, W - d);
-    for (int m = 5; m <= m2max; ++m) bmulti2 += c.ld(B_MULTIBIF, d + m, g - m) * c.ld(A_MULTI1, m, g - m);
+    for (int m = 5; m <= m2max; ++m) ks += c.ld(B_MULTIBIF, d + m, g - m) * c.ld(A_MULTI1, m, g - m);
+    bmulti2 = bm1 + c.ld(B_MULTI2, d + 1, g) * T.e_mlbase + ks * T.inv_cA;
     // Beta_multibif :354-364
     bmbif = bm1 + bmulti;
   }
@@ -328,41 +352,42 @@ static PRIB_HD void outside_cell(const Ctx &c, long long g, int d) {
   if (t2) {
     const int t2r = T.rt[t2];
     const real dang = e_dangle(T, t2, p > 0, sp, q < L, sq1);
-    bstem = exp(c.lao[g] + c.lbo[g + d] - c.lao[c.seq_off[ci.sq] + L]) * dang;  // :370
+    const real base = (real)exp(c.lao[g] + c.lbo[g + d] - c.lao[c.seq_off[ci.sq] + L]) * dang * T.sB[d];  // :370
+    real ls = 0;  // sum over enclosing loops; sources sit two spans further out than in the inside pass
     const int smax = imin(kMaxLoop, W - 1 - d);  // source row d + sum + 2 <= W + 1
     // stacking on (p, q+1) :388-398
-    if (smax >= 0) bstem += bse * T.e_stack[te][t2r];
+    if (smax >= 0) ls += bse * T.e_stack[te][t2r];
     if (smax >= 1) {  // 1-nt bulges: outer pairs (p-1, q+1) and (p, q+2)
       const int ta = T.bp[s[-1]][sq1];
       const int tb = T.bp[sp][s[d + 2]];
-      bstem += T.e_bulge[1] * (c.ld(B_STEM, d + 3, g - 2) * T.e_stack[ta][t2r] +
+      ls += T.e_bulge[1] * (c.ld(B_STEM, d + 3, g - 2) * T.e_stack[ta][t2r] +
                                c.ld(B_STEM, d + 3, g - 1) * T.e_stack[tb][t2r]);
     }
     if (smax >= 2) {
       const int to = T.bp[s[-1]][s[d + 2]];  // 1x1: outer (p-1, q+2)
-      bstem += c.ld(B_STEM, d + 4, g - 2) * c.e_int11[idx11(to, t2r, sp, sq1)];
+      ls += c.ld(B_STEM, d + 4, g - 2) * c.e_int11[idx11(to, t2r, sp, sq1)];
       real bs = 0;
       for (int u = 2; u <= smax; ++u)
         bs += T.e_bulge[u] * (c.ld(B_STEMB, d + u + 2, g - u - 1) + c.ld(B_STEMB, d + u + 2, g - 1));
-      bstem += T.tau[t2r] * bs;
+      ls += T.tau[t2r] * bs;
     }
     if (smax >= 3) {
       const int ta = T.bp[s[-1]][s[d + 3]];  // 1x2: outer (p-1, q+3)
-      bstem += c.ld(B_STEM, d + 5, g - 2) * c.e_int21[idx21(ta, t2r, sp, sq1, s[d + 2])];
+      ls += c.ld(B_STEM, d + 5, g - 2) * c.e_int21[idx21(ta, t2r, sp, sq1, s[d + 2])];
       const int tb = T.bp[s[-2]][s[d + 2]];  // 2x1: outer (p-2, q+2)
-      bstem += c.ld(B_STEM, d + 5, g - 3) * c.e_int21[idx21(t2r, tb, sq1, s[-1], sp)];
+      ls += c.ld(B_STEM, d + 5, g - 3) * c.e_int21[idx21(t2r, tb, sq1, s[-1], sp)];
     }
     if (smax >= 4) {
       const int tc = T.bp[s[-2]][s[d + 3]];  // 2x2: outer (p-2, q+3)
-      bstem += c.ld(B_STEM, d + 6, g - 3) * c.e_int22[idx22(tc, t2r, s[-1], sp, sq1, s[d + 2])];
+      ls += c.ld(B_STEM, d + 6, g - 3) * c.e_int22[idx22(tc, t2r, s[-1], sp, sq1, s[d + 2])];
       real gs = 0;
       for (int sum = 4; sum <= smax; ++sum) {
         const real *row = c.arr[B_STEMO] + (long long)(d + sum + 2) * c.NC + g - 1;
         for (int u1 = 1; u1 < sum; ++u1) gs += T.conv[u1][sum - u1] * row[-u1];
       }
-      bstem += T.e_mmI[t2r][sq1][sp] * gs;
+      ls += T.e_mmI[t2r][sq1][sp] * gs;
     }
-    bstem += bmulti2 * T.e_mlintern * dang;  // :401-406
+    bstem = base + T.k2 * ls + bmulti2 * T.e_mlintern * dang;  // :401-406
   }
 
   c.at(B_STEM, d, g) = bstem;
@@ -471,7 +496,7 @@ static PRIB_HD void hairpin_suffix(const Ctx &c, long long g) {
       const real bse = c.ld(B_STEM, dd + 1, g - 1);
       if (bse != 0) {
         const int t = T.bp[s[0]][s[dd]];
-        suf += bse * T.e_hairpin[dd - 1] * (dd - 1 != 3 ? T.e_mmH[t][s[1]][s[dd - 1]] : T.tau[t]);
+        suf += bse * T.hpB[dd] * (dd - 1 != 3 ? T.e_mmH[t][s[1]][s[dd - 1]] : T.tau[t]);
       }
     }
     c.at(X_SUFH, dd, g) = suf;
@@ -504,20 +529,20 @@ struct WindowProb {
   real ext, hp, multi, loop_b, loop_c;
 };
 
-static PRIB_HD real multi_prob(const Ctx &c, long long off, int L, int x, int w) {  // :581-612
+static PRIB_HD double multi_prob(const Ctx &c, long long off, int L, int x, int w) {  // :581-612
   const int W = c.W;
-  real v = 0;
+  double v = 0;
   const int hi = imin(x + W, L);
   for (int e = x + w - 1 + 5; e <= hi; ++e)  // Alpha_multi below span 5 is zero
-    v += c.ld(B_MULTI, e - x + 1, off + x - 1) * c.ld(A_MULTI, e - x - w + 1, off + x + w - 1);
+    v += (double)c.ld(B_MULTI, e - x + 1, off + x - 1) * (double)c.ld(A_MULTI, e - x - w + 1, off + x + w - 1);
   const int lo = imax(0, x + w - 1 - W);
   for (int b = lo; b <= x - 1 - 5; ++b)
-    v += c.ld(B_MULTI2, x + w - 1 - b, off + b) * c.ld(A_MULTI2, x - b - 1, off + b);
-  return v;
+    v += (double)c.ld(B_MULTI2, x + w - 1 - b, off + b) * (double)c.ld(A_MULTI2, x - b - 1, off + b);
+  return v * (double)c.T->kmul[w - c.delta];
 }
 
-static PRIB_HD real hairpin_prob(const Ctx &c, long long off, int x, int w) {  // :536-579
-  real v = 0;
+static PRIB_HD double hairpin_prob(const Ctx &c, long long off, int x, int w) {  // :536-579
+  double v = 0;
   for (int i = imax(1, x - c.W); i < x; ++i) {
     const int dd = x + w - i;
     if (dd <= c.W) v += c.ld(X_SUFH, dd < 4 ? 4 : dd, off + i);
@@ -526,7 +551,7 @@ static PRIB_HD real hairpin_prob(const Ctx &c, long long off, int x, int w) {  /
 }
 
 // b[k]: strands that end exactly at the window end; c[k]: strands that extend beyond it (:644-658)
-static PRIB_HD void biloop_gather(const Ctx &c, long long off, int L, int k, real &b, real &cc) {
+static PRIB_HD void biloop_gather(const Ctx &c, long long off, int L, int k, double &b, double &cc) {
   const int w = c.delta;
   b = 0;
   cc = 0;
@@ -543,6 +568,8 @@ static PRIB_HD void biloop_gather(const Ctx &c, long long off, int L, int k, rea
       for (int u2 = umin; u2 <= kMaxLoop; ++u2) cc += c.ld(X_MR, u2, off + jp);
     }
   }
+  b *= (double)c.T->kacc;
+  cc *= (double)c.T->kacc;
 }
 
 // Final per-position step: CalcAccessibility :484-528 incl. the finalisation quirks of :667-680 (Q1, Q3)
@@ -556,7 +583,7 @@ static PRIB_HD void finalize_position(const Ctx &c, long long g) {
   const double Z = c.lao[off + L];
   const double kT = c.T->kT;
 
-  real b, cc;
+  double b, cc;
   biloop_gather(c, off, L, x, b, cc);
   double bp = 0, cbp = 0;
   if (Z >= -690 && Z <= 690) {  // direct path :667-680 — the float cast of the UN-normalised sum is emulated

@@ -1,9 +1,14 @@
 // CUDA kernels (sm_100a) and the C ABI of libpriblast_acc.so.
 //
-// Kernel set, version 1: every kernel is "one thread = one column of the batch"; the
-// per-thread bodies are the PRIB_HD functions of acc_core.h.  The span wavefront is driven from the
-// host: one launch per span for the inside pass (ascending) and one per span for the outside pass
-// (descending), over ALL sequences of the batch at once, so a launch has (batch nucleotides) threads.
+// Kernel set:
+//   k_inside_tile / k_outside_tile   tile-persistent span march (acc_tile.h): one CTA per column tile,
+//                                    stencil source rows in shared-memory rings, halo recomputed
+//   k_outer_scans_warp               the two outer arrays, one warp per sequence
+//   k_biloop_left/right, k_hairpin_suffix, k_finalize   accessibility, one thread per column
+// Every kernel exists for float and double band arithmetic.  The float engine (span-scaled, range
+// guarded) is the fast path for W <= kFp32MaxSpan; sequences whose stored values leave the safe range
+// are flagged on the device and re-run by the double engine inside the same prib_acc_compute call, on
+// the GPU.  There is no CPU path.
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -21,72 +26,33 @@
 #include "acc_tile.h"
 
 using namespace prib;
-typedef double real;
-typedef Core<real> K;
-typedef K::Ctx Ctx;
-typedef K::SmallTables SmallTables;
-typedef Tile<real> TL;
+
+namespace {
+
+constexpr int kThreads = 128;
+constexpr int kScanWarps = 4;
+constexpr int kFp32MaxSpan = 100;
+// widest CTA of the tile kernels per precision (227 KB of rings / 80 rows): bounds the register budget
+template <typename real> struct TileMaxThreads { static constexpr int value = sizeof(real) == 4 ? 704 : 352; };
 
 // ---------------------------------------------------------------------------------------------
 // kernels
 // ---------------------------------------------------------------------------------------------
-namespace {
-
-constexpr int kThreads = 128;
-
-__global__ void __launch_bounds__(kThreads) k_inside(Ctx c, int d) {
-  const long long g = (long long)blockIdx.x * kThreads + threadIdx.x;
-  if (g < c.NC) K::inside_cell(c, g, d);
-}
-
-__global__ void __launch_bounds__(kThreads) k_outside(Ctx c, int d) {
-  const long long g = (long long)blockIdx.x * kThreads + threadIdx.x;
-  if (g < c.NC) K::outside_cell(c, g, d);
-}
-
-__global__ void __launch_bounds__(32) k_outer_scans(Ctx c) {
-  const int sq = blockIdx.x * 32 + threadIdx.x;
-  if (sq >= c.nseq) return;
-  double ring[256];
-  K::scan_alpha_outer(c, sq, ring);
-  K::scan_beta_outer(c, sq, ring);
-}
-
-__global__ void __launch_bounds__(kThreads) k_biloop_left(Ctx c) {
-  const long long g = (long long)blockIdx.x * kThreads + threadIdx.x;
-  if (g < c.NC) K::biloop_left(c, g);
-}
-
-__global__ void __launch_bounds__(kThreads) k_biloop_right(Ctx c) {
-  const long long g = (long long)blockIdx.x * kThreads + threadIdx.x;
-  if (g < c.NC) K::biloop_right(c, g);
-}
-
-__global__ void __launch_bounds__(kThreads) k_hairpin_suffix(Ctx c) {
-  const long long g = (long long)blockIdx.x * kThreads + threadIdx.x;
-  if (g < c.NC) K::hairpin_suffix(c, g);
-}
-
-__global__ void __launch_bounds__(kThreads) k_finalize(Ctx c) {
-  const long long g = (long long)blockIdx.x * kThreads + threadIdx.x;
-  if (g < c.NC) K::finalize_position(c, g);
-}
-
-
-
-// ---- kernel set v2: tile-persistent span march (acc_tile.h) ------------------------------------
 // grid = resident CTAs (one per SM: the rings take ~all shared memory), blockDim = TC, tiles round-robin.
 // dynamic smem: kTileRows * TC reals + (TC + 16) base codes.
-__global__ void __launch_bounds__(1024, 1) k_inside_tile(Ctx c, int TX, long long ntiles, real *scratch) {
+template <typename real>
+__global__ void __launch_bounds__(TileMaxThreads<real>::value, 1)
+k_inside_tile(typename Core<real>::Ctx c, int TX, long long ntiles, real *scratch) {
+  typedef Tile<real> TL;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int TC = blockDim.x, t = threadIdx.x, W = c.W;
   real *base = reinterpret_cast<real *>(smem_raw);
   uint8_t *sS = reinterpret_cast<uint8_t *>(base + (size_t)kTileRows * TC);
   real *scrM1 = scratch + (size_t)blockIdx.x * 2 * (W + 4) * TC;
   real *scrM2 = scrM1 + (size_t)(W + 4) * TC;
-  const TL::InSmem sm = TL::carve_in(base, TC, sS);
+  const typename TL::InSmem sm = TL::carve_in(base, TC, sS);
   for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    TL::Geo ge;
+    typename TL::Geo ge;
     ge.g0 = tile * TX;
     ge.TC = TC;
     ge.TX = TX;
@@ -94,7 +60,7 @@ __global__ void __launch_bounds__(1024, 1) k_inside_tile(Ctx c, int TX, long lon
     __syncthreads();  // previous tile fully consumed
     for (int r = 0; r < kTileRows; r++) base[(size_t)r * TC + t] = 0;
     for (int k = t; k < TC + 8; k += TC) sS[k] = (ge.g0 + k < c.NC) ? c.S[ge.g0 + k] : 0;
-    TL::ColState cs;
+    typename TL::ColState cs;
     TL::col_state(c, ge.g0 + t, cs);
     __syncthreads();
     for (int d = kTurn; d <= W + 1; d++) {
@@ -104,21 +70,24 @@ __global__ void __launch_bounds__(1024, 1) k_inside_tile(Ctx c, int TX, long lon
   }
 }
 
-__global__ void __launch_bounds__(1024, 1) k_outside_tile(Ctx c, int TX, long long ntiles, real *scratch) {
+template <typename real>
+__global__ void __launch_bounds__(TileMaxThreads<real>::value, 1)
+k_outside_tile(typename Core<real>::Ctx c, int TX, long long ntiles, real *scratch) {
+  typedef Tile<real> TL;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int TC = blockDim.x, t = threadIdx.x, W = c.W;
   real *base = reinterpret_cast<real *>(smem_raw);
   real *scrBif = scratch + (size_t)blockIdx.x * 2 * (W + 4) * TC;
-  const TL::OutSmem sm = TL::carve_out(base, TC);
+  const typename TL::OutSmem sm = TL::carve_out(base, TC);
   for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    TL::Geo ge;
+    typename TL::Geo ge;
     ge.g0 = tile * TX;
     ge.TC = TC;
     ge.TX = TX;
     ge.H = W + 1;
     __syncthreads();
     for (int r = 0; r < kTileRows; r++) base[(size_t)r * TC + t] = 0;
-    TL::ColState cs;
+    typename TL::ColState cs;
     TL::col_state(c, ge.g0 - ge.H + t, cs);
     __syncthreads();
     int slot = (W + 1) % kRingOut;
@@ -130,25 +99,23 @@ __global__ void __launch_bounds__(1024, 1) k_outside_tile(Ctx c, int TX, long lo
   }
 }
 
-// ---- outer arrays: one warp per sequence (raccess.cpp:230-241, 260-271) ------------------------
-// The recurrence is serial in the position but each step is a W-term dot product: lanes split the
-// terms, a butterfly adds them, the window of scaled values lives in shared memory.  Values are kept
-// linear with an exact power-of-two rescale; logs are taken 32 positions at a time by all lanes.
-constexpr int kScanWarps = 4;
-
+// Outer arrays (raccess.cpp:230-241, 260-271): serial in the position, but each step is a W-term dot
+// product: lanes split the terms, a butterfly adds them, the window of scaled values lives in shared
+// memory.  Values stay linear with an exact power-of-two rescale; logs are taken 32 positions at a time.
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
 
-template <bool ALPHA>
-__device__ void warp_scan(const Ctx &c, int sq, double *ring, int lane) {
+template <typename real, bool ALPHA>
+__device__ void warp_scan(const typename Core<real>::Ctx &c, int sq, double *ring, int lane) {
   const int L = c.seq_len[sq], W = c.W;
   const long long off = c.seq_off[sq];
   const double kBig = 1.3407807929942597e154, kLn2 = 0.6931471805599453094;
   double *dst = ALPHA ? c.lao : c.lbo;
   const real *src = c.arr[ALPHA ? A_STEMDE : A_STEMD];
+  const double *us = c.T->us;
   long long e2 = 0;
   const int start = ALPHA ? 0 : L;
   if (lane == 0) {
@@ -156,7 +123,7 @@ __device__ void warp_scan(const Ctx &c, int sq, double *ring, int lane) {
     dst[off + start] = 0.0;
   }
   __syncwarp();
-  double keep_v = 1.0;   // value of the position this lane will take the log of
+  double keep_v = 1.0;  // value of the position this lane will take the log of
   long long keep_e = 0;
   int keep_pos = -1;
   for (int step = 1; step <= L; ++step) {
@@ -166,7 +133,7 @@ __device__ void warp_scan(const Ctx &c, int sq, double *ring, int lane) {
     double part = 0;
     for (int d = 5 + lane; d <= dmax; d += 32) {
       const int j = ALPHA ? i - d : i + d;
-      part += (double)src[(long long)d * c.NC + col] * ring[j & 255];
+      part += (double)src[(long long)d * c.NC + col] * us[d] * ring[j & 255];
     }
     double v = warp_sum(part) + ring[(ALPHA ? i - 1 : i + 1) & 255];
     if (v > kBig) {  // uniform: every lane holds the same v
@@ -189,14 +156,36 @@ __device__ void warp_scan(const Ctx &c, int sq, double *ring, int lane) {
   }
 }
 
-__global__ void __launch_bounds__(32 * kScanWarps) k_outer_scans_warp(Ctx c) {
+template <typename real>
+__global__ void __launch_bounds__(32 * kScanWarps) k_outer_scans_warp(typename Core<real>::Ctx c) {
   __shared__ double rings[kScanWarps][256];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int sq = blockIdx.x * kScanWarps + warp;
   if (sq >= c.nseq) return;
-  warp_scan<true>(c, sq, rings[warp], lane);
+  warp_scan<real, true>(c, sq, rings[warp], lane);
   __syncwarp();
-  warp_scan<false>(c, sq, rings[warp], lane);
+  warp_scan<real, false>(c, sq, rings[warp], lane);
+}
+
+template <typename real>
+__global__ void __launch_bounds__(kThreads) k_biloop_left(typename Core<real>::Ctx c) {
+  const long long g = (long long)blockIdx.x * kThreads + threadIdx.x;
+  if (g < c.NC) Core<real>::biloop_left(c, g);
+}
+template <typename real>
+__global__ void __launch_bounds__(kThreads) k_biloop_right(typename Core<real>::Ctx c) {
+  const long long g = (long long)blockIdx.x * kThreads + threadIdx.x;
+  if (g < c.NC) Core<real>::biloop_right(c, g);
+}
+template <typename real>
+__global__ void __launch_bounds__(kThreads) k_hairpin_suffix(typename Core<real>::Ctx c) {
+  const long long g = (long long)blockIdx.x * kThreads + threadIdx.x;
+  if (g < c.NC) Core<real>::hairpin_suffix(c, g);
+}
+template <typename real>
+__global__ void __launch_bounds__(kThreads) k_finalize(typename Core<real>::Ctx c) {
+  const long long g = (long long)blockIdx.x * kThreads + threadIdx.x;
+  if (g < c.NC) Core<real>::finalize_position(c, g);
 }
 
 // Issue-rate probes for the roofline denominators (MEASURED_PEAKS.json has no SFU / FP32 /
@@ -236,6 +225,9 @@ __global__ void __launch_bounds__(256) k_probe(float *sink_f, double *sink_d, in
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
 thread_local std::string g_err;
 
 int fail(int code, const std::string &msg) {
@@ -252,21 +244,39 @@ int fail(int code, const std::string &msg) {
 
 int rows_of(int a, int W) { return (a == X_ML || a == X_MR) ? 32 : W + 4; }
 
-long long state_bytes_per_column(int W) {
+long long state_bytes_per_column(int W, size_t real_size) {
   long long r = 0;
   for (int a = 0; a < kNumArr; a++) r += rows_of(a, W);
-  return r * (long long)sizeof(real) + 2 * (long long)sizeof(double);
+  return r * (long long)real_size + 2 * (long long)sizeof(double);
 }
 
 struct Batch {
   int n = 0;
   long long NC = 0, nt = 0;
-  std::vector<int> ids;         // caller's sequence indices, batch order
-  long long out_base = 0;       // float offset of this batch in d_out
-  // device copies of the layout
+  std::vector<int> ids;                      // caller's sequence indices, batch order
+  std::vector<long long> acc_off, cond_off;  // absolute float offsets into d_out
   uint8_t *d_S = nullptr;
-  int32_t *d_col_seq = nullptr, *d_seq_len = nullptr;
+  int32_t *d_col_seq = nullptr, *d_seq_len = nullptr, *d_flags = nullptr;
   long long *d_seq_off = nullptr, *d_acc_off = nullptr, *d_cond_off = nullptr;
+};
+
+template <typename real>
+struct Engine {
+  typedef typename Core<real>::SmallTables ST;
+  ST *d_small = nullptr;
+  real *d_int11 = nullptr, *d_int21 = nullptr, *d_int22 = nullptr;
+  int TC = 0;
+  size_t tile_smem = 0;
+  long long max_cols = 0;
+
+  void release() {
+    cudaFree(d_small);
+    cudaFree(d_int11);
+    cudaFree(d_int21);
+    cudaFree(d_int22);
+    d_small = nullptr;
+    d_int11 = d_int21 = d_int22 = nullptr;
+  }
 };
 
 }  // namespace
@@ -274,54 +284,62 @@ struct Batch {
 struct prib_ctx {
   prib_acc_params prm{};
   int W = 70, delta = 5;
+  bool use_fp32 = true;
   cudaStream_t own_stream = nullptr, stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk0 = nullptr, evk1 = nullptr;
   cudaEvent_t evp[PRIB_NUM_PHASES + 1] = {};
-  bool phases_pending = false;
-  bool kernel_timed = true;
-  // tables
-  SmallTables *d_small = nullptr;
-  real *d_int11 = nullptr, *d_int21 = nullptr, *d_int22 = nullptr;
+  bool phases_pending = false, kernel_timed = true;
+  Engine<float> e32;
+  Engine<double> e64;
   float *d_log = nullptr;
-  // tile kernels
-  int kernel_set = 2;  // 1 = per-span launches (v1), 2 = tile-persistent (v2)
-  int TC = 0, grid_tiles = 0;
-  size_t tile_smem = 0;
-  real *d_tile_scratch = nullptr;
-  // DP scratch
+  int grid_tiles = 0;
+  char *d_tile_scratch = nullptr;
   char *d_state = nullptr;
-  long long state_cap_bytes = 0, max_cols = 0;
+  long long state_cap_bytes = 0;
   // staged work
   std::vector<Batch> batches;
-  std::vector<int32_t> lens;
+  std::vector<std::string> seqs;  // host copies (needed to re-run flagged sequences in double)
   float *d_out = nullptr;
   long long out_floats = 0;
   bool staged = false, computed = false;
   float *h_stage = nullptr;
   long long h_stage_floats = 0;
+  int32_t *h_flags = nullptr;
+  long long h_flags_cap = 0;
   prib_acc_counters cnt{};
 };
 
 namespace {
 
+void free_batch(Batch &b) {
+  cudaFree(b.d_S);
+  cudaFree(b.d_col_seq);
+  cudaFree(b.d_seq_len);
+  cudaFree(b.d_flags);
+  cudaFree(b.d_seq_off);
+  cudaFree(b.d_acc_off);
+  cudaFree(b.d_cond_off);
+  b = Batch();
+}
+
 void free_batches(prib_ctx *c) {
-  for (auto &b : c->batches) {
-    cudaFree(b.d_S);
-    cudaFree(b.d_col_seq);
-    cudaFree(b.d_seq_len);
-    cudaFree(b.d_seq_off);
-    cudaFree(b.d_acc_off);
-    cudaFree(b.d_cond_off);
-  }
+  for (auto &b : c->batches) free_batch(b);
   c->batches.clear();
   if (c->d_out) cudaFree(c->d_out);
   c->d_out = nullptr;
   c->out_floats = 0;
+  c->seqs.clear();
   c->staged = c->computed = false;
 }
 
-Ctx make_ctx(prib_ctx *c, const Batch &b) {
-  Ctx k;
+template <typename real> Engine<real> &engine(prib_ctx *c);
+template <> Engine<float> &engine<float>(prib_ctx *c) { return c->e32; }
+template <> Engine<double> &engine<double>(prib_ctx *c) { return c->e64; }
+
+template <typename real>
+typename Core<real>::Ctx make_ctx(prib_ctx *c, const Batch &b) {
+  Engine<real> &e = engine<real>(c);
+  typename Core<real>::Ctx k;
   std::memset(&k, 0, sizeof(k));
   k.NC = b.NC;
   k.W = c->W;
@@ -332,10 +350,10 @@ Ctx make_ctx(prib_ctx *c, const Batch &b) {
   k.col_seq = b.d_col_seq;
   k.seq_len = b.d_seq_len;
   k.seq_off = b.d_seq_off;
-  k.T = c->d_small;
-  k.e_int11 = c->d_int11;
-  k.e_int21 = c->d_int21;
-  k.e_int22 = c->d_int22;
+  k.T = e.d_small;
+  k.e_int11 = e.d_int11;
+  k.e_int21 = e.d_int21;
+  k.e_int22 = e.d_int22;
   k.log_tbl = c->d_log;
   char *p = c->d_state;
   for (int a = 0; a < kNumArr; a++) {
@@ -347,7 +365,8 @@ Ctx make_ctx(prib_ctx *c, const Batch &b) {
   k.lbo = (double *)p;
   k.acc_off = b.d_acc_off;
   k.cond_off = b.d_cond_off;
-  k.out = c->d_out + b.out_base;
+  k.out = c->d_out;
+  k.flags = b.d_flags;
   return k;
 }
 
@@ -363,51 +382,156 @@ int settle_phases(prib_ctx *c) {
   return PRIB_OK;
 }
 
-int run_batch(prib_ctx *c, const Batch &b) {
-  // phase events of the previous batch must be read before they are re-recorded
-  if (settle_phases(c) != PRIB_OK) return PRIB_ECUDA;
-  const Ctx k = make_ctx(c, b);
-  const long long used = state_bytes_per_column(c->W) * b.NC;
+// Builds the device-side layout of one batch.  ids: caller's indices; offsets absolute into d_out.
+int make_batch(prib_ctx *c, const std::vector<int> &ids, const std::vector<long long> &acc_off,
+               const std::vector<long long> &cond_off, Batch &b) {
+  b.ids = ids;
+  b.acc_off = acc_off;
+  b.cond_off = cond_off;
+  b.n = (int)ids.size();
+  std::vector<const char *> sp(b.n);
+  std::vector<int32_t> sl(b.n);
+  b.nt = 0;
+  for (int k = 0; k < b.n; k++) {
+    sp[k] = c->seqs[ids[k]].data();
+    sl[k] = (int32_t)c->seqs[ids[k]].size();
+    b.nt += sl[k];
+  }
+  BatchLayout lay;
+  build_layout(b.n, sp.data(), sl.data(), lay);
+  b.NC = lay.NC;
+  const size_t n1 = (size_t)std::max(b.n, 1);
+  CU(cudaMalloc(&b.d_S, (size_t)b.NC));
+  CU(cudaMalloc(&b.d_col_seq, (size_t)b.NC * sizeof(int32_t)));
+  CU(cudaMalloc(&b.d_seq_len, n1 * sizeof(int32_t)));
+  CU(cudaMalloc(&b.d_flags, n1 * sizeof(int32_t)));
+  CU(cudaMalloc(&b.d_seq_off, n1 * sizeof(long long)));
+  CU(cudaMalloc(&b.d_acc_off, n1 * sizeof(long long)));
+  CU(cudaMalloc(&b.d_cond_off, n1 * sizeof(long long)));
+  CU(cudaEventRecord(c->ev0, c->stream));
+  CU(cudaMemcpyAsync(b.d_S, lay.S.data(), (size_t)b.NC, cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemcpyAsync(b.d_col_seq, lay.col_seq.data(), (size_t)b.NC * 4, cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemcpyAsync(b.d_seq_len, sl.data(), (size_t)b.n * 4, cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemcpyAsync(b.d_seq_off, lay.seq_off.data(), (size_t)b.n * 8, cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemcpyAsync(b.d_acc_off, acc_off.data(), (size_t)b.n * 8, cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemcpyAsync(b.d_cond_off, cond_off.data(), (size_t)b.n * 8, cudaMemcpyHostToDevice, c->stream));
+  CU(cudaEventRecord(c->ev1, c->stream));
+  CU(cudaStreamSynchronize(c->stream));  // host staging vectors go out of scope
+  float ms = 0;
+  CU(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+  c->cnt.h2d_ms += ms;
+  c->cnt.h2d_bytes += b.NC * 5 + (long long)b.n * 28;
+  return PRIB_OK;
+}
+
+// Greedy partition of `order` (already longest-first) into batches that fit `max_cols` columns.
+int partition(prib_ctx *c, const std::vector<int> &order, long long max_cols, const std::vector<long long> &acc_abs,
+              const std::vector<long long> &cond_abs, std::vector<Batch> &out) {
+  size_t pos = 0;
+  while (pos < order.size()) {
+    std::vector<int> ids;
+    std::vector<long long> ao, co;
+    long long cols = 2 * kPad;
+    while (pos < order.size() && cols + layout_columns((int)c->seqs[order[pos]].size()) <= max_cols) {
+      cols += layout_columns((int)c->seqs[order[pos]].size());
+      ids.push_back(order[pos]);
+      ao.push_back(acc_abs[order[pos]]);
+      co.push_back(cond_abs[order[pos]]);
+      pos++;
+    }
+    if (ids.empty())
+      return fail(PRIB_ECUDA, "sequence " + std::to_string(order[pos]) + " does not fit the device DP budget");
+    out.emplace_back();
+    int rc = make_batch(c, ids, ao, co, out.back());
+    if (rc != PRIB_OK) return rc;
+  }
+  return PRIB_OK;
+}
+
+template <typename real>
+int run_batch(prib_ctx *c, const Batch &b, bool timed) {
+  Engine<real> &e = engine<real>(c);
+  if (timed && settle_phases(c) != PRIB_OK) return PRIB_ECUDA;
+  const typename Core<real>::Ctx k = make_ctx<real>(c, b);
+  const long long used = state_bytes_per_column(c->W, sizeof(real)) * b.NC;
+  if (used > c->state_cap_bytes) return fail(PRIB_ECUDA, "internal: batch exceeds the DP state allocation");
   cudaStream_t st = c->stream;
   if (used > c->cnt.dp_state_bytes_used) c->cnt.dp_state_bytes_used = used;
-  CU(cudaEventRecord(c->evp[0], st));
+  if (timed) CU(cudaEventRecord(c->evp[0], st));
   CU(cudaMemsetAsync(c->d_state, 0, (size_t)used, st));
+  CU(cudaMemsetAsync(b.d_flags, 0, sizeof(int32_t) * (size_t)std::max(b.n, 1), st));
   const unsigned grid = (unsigned)((b.NC + kThreads - 1) / kThreads);
-  CU(cudaEventRecord(c->evp[1], st));
-  const int TX = c->TC - (c->W + 1);
+  if (timed) CU(cudaEventRecord(c->evp[1], st));
+  const int TX = e.TC - (c->W + 1);
   const long long ntiles = (b.NC + TX - 1) / TX;
   const int tgrid = (int)std::min<long long>(ntiles, c->grid_tiles);
-  long long launches = 5;
-  if (c->kernel_set == 1) {
-    for (int d = kTurn; d <= c->W + 1; d++) k_inside<<<grid, kThreads, 0, st>>>(k, d);
-    launches += c->W - 1;
-  } else {
-    k_inside_tile<<<tgrid, c->TC, c->tile_smem, st>>>(k, TX, ntiles, c->d_tile_scratch);
-    launches += 1;
-  }
-  CU(cudaEventRecord(c->evp[2], st));
-  if (c->kernel_set == 1) k_outer_scans<<<(b.n + 31) / 32, 32, 0, st>>>(k);
-  else k_outer_scans_warp<<<(b.n + kScanWarps - 1) / kScanWarps, 32 * kScanWarps, 0, st>>>(k);
-  CU(cudaEventRecord(c->evp[3], st));
-  if (c->kernel_set == 1) {
-    for (int d = c->W + 1; d >= kTurn; d--) k_outside<<<grid, kThreads, 0, st>>>(k, d);
-    launches += c->W - 1;
-  } else {
-    k_outside_tile<<<tgrid, c->TC, c->tile_smem, st>>>(k, TX, ntiles, c->d_tile_scratch);
-    launches += 1;
-  }
-  CU(cudaEventRecord(c->evp[4], st));
-  k_biloop_left<<<grid, kThreads, 0, st>>>(k);
-  CU(cudaEventRecord(c->evp[5], st));
-  k_biloop_right<<<grid, kThreads, 0, st>>>(k);
-  CU(cudaEventRecord(c->evp[6], st));
-  k_hairpin_suffix<<<grid, kThreads, 0, st>>>(k);
-  k_finalize<<<grid, kThreads, 0, st>>>(k);
-  CU(cudaEventRecord(c->evp[7], st));
+  real *scratch = reinterpret_cast<real *>(c->d_tile_scratch);
+  k_inside_tile<real><<<tgrid, e.TC, e.tile_smem, st>>>(k, TX, ntiles, scratch);
+  if (timed) CU(cudaEventRecord(c->evp[2], st));
+  k_outer_scans_warp<real><<<(b.n + kScanWarps - 1) / kScanWarps, 32 * kScanWarps, 0, st>>>(k);
+  if (timed) CU(cudaEventRecord(c->evp[3], st));
+  k_outside_tile<real><<<tgrid, e.TC, e.tile_smem, st>>>(k, TX, ntiles, scratch);
+  if (timed) CU(cudaEventRecord(c->evp[4], st));
+  k_biloop_left<real><<<grid, kThreads, 0, st>>>(k);
+  if (timed) CU(cudaEventRecord(c->evp[5], st));
+  k_biloop_right<real><<<grid, kThreads, 0, st>>>(k);
+  if (timed) CU(cudaEventRecord(c->evp[6], st));
+  k_hairpin_suffix<real><<<grid, kThreads, 0, st>>>(k);
+  k_finalize<real><<<grid, kThreads, 0, st>>>(k);
+  if (timed) CU(cudaEventRecord(c->evp[7], st));
   CU(cudaGetLastError());
-  c->phases_pending = true;
-  c->cnt.kernel_launches += launches;
+  if (timed) c->phases_pending = true;
+  c->cnt.kernel_launches += 7;
   c->cnt.batches += 1;
+  return PRIB_OK;
+}
+
+template <typename real>
+int setup_engine(prib_ctx *c, const ScaleSpec &spec, size_t smem_max, std::string &err) {
+  Engine<real> &e = engine<real>(c);
+  HostTablesT<real> tab;
+  if (!build_tables(c->W, c->delta, spec, tab, err)) return PRIB_EINVAL;
+  typedef typename Core<real>::SmallTables ST;
+  CU(cudaMalloc(&e.d_small, sizeof(ST)));
+  CU(cudaMemcpy(e.d_small, &tab.small, sizeof(ST), cudaMemcpyHostToDevice));
+  CU(cudaMalloc(&e.d_int11, tab.e_int11.size() * sizeof(real)));
+  CU(cudaMemcpy(e.d_int11, tab.e_int11.data(), tab.e_int11.size() * sizeof(real), cudaMemcpyHostToDevice));
+  CU(cudaMalloc(&e.d_int21, tab.e_int21.size() * sizeof(real)));
+  CU(cudaMemcpy(e.d_int21, tab.e_int21.data(), tab.e_int21.size() * sizeof(real), cudaMemcpyHostToDevice));
+  CU(cudaMalloc(&e.d_int22, tab.e_int22.size() * sizeof(real)));
+  CU(cudaMemcpy(e.d_int22, tab.e_int22.data(), tab.e_int22.size() * sizeof(real), cudaMemcpyHostToDevice));
+  if (sizeof(real) == 8) {
+    CU(cudaMemcpyToSymbol(g_conv_d, &tab.small.conv[0][0], sizeof(real) * 32 * 32));
+    CU(cudaMemcpyToSymbol(g_bulge_d, tab.small.e_bulge, sizeof(real) * 32));
+  } else {
+    CU(cudaMemcpyToSymbol(g_conv_f, &tab.small.conv[0][0], sizeof(real) * 32 * 32));
+    CU(cudaMemcpyToSymbol(g_bulge_f, tab.small.e_bulge, sizeof(real) * 32));
+  }
+  if (c->d_log == nullptr) {
+    CU(cudaMalloc(&c->d_log, tab.log_tbl.size() * sizeof(float)));
+    CU(cudaMemcpy(c->d_log, tab.log_tbl.data(), tab.log_tbl.size() * sizeof(float), cudaMemcpyHostToDevice));
+  }
+  // the widest CTA whose rings fit the opt-in shared memory of this device
+  int TC = (int)((smem_max - 64) / (kTileRows * sizeof(real) + 1)) / 32 * 32;
+  if (TC > TileMaxThreads<real>::value) TC = TileMaxThreads<real>::value;
+  const char *tce = getenv("PRIB_TILE_COLS");
+  if (tce && atoi(tce) >= c->W + 34 && atoi(tce) <= TC) TC = atoi(tce) / 32 * 32;
+  if (TC < c->W + 34) return fail(PRIB_ECUDA, "shared memory too small for the tile kernels at this span");
+  e.TC = TC;
+  e.tile_smem = (size_t)kTileRows * TC * sizeof(real) + TC + 16;
+  CU(cudaFuncSetAttribute(k_inside_tile<real>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e.tile_smem));
+  CU(cudaFuncSetAttribute(k_outside_tile<real>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e.tile_smem));
+  return PRIB_OK;
+}
+
+int settle_kernel_time(prib_ctx *c) {
+  if (settle_phases(c) != PRIB_OK) return PRIB_ECUDA;
+  if (!c->kernel_timed) {
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, c->evk0, c->evk1));
+    c->cnt.kernel_ms += ms;
+    c->kernel_timed = true;
+  }
   return PRIB_OK;
 }
 
@@ -419,7 +543,7 @@ int run_batch(prib_ctx *c, const Batch &b) {
 extern "C" {
 
 const char *prib_last_error(void) { return g_err.c_str(); }
-const char *prib_version(void) { return "priblast-b200 0.1 (sm_100a, fp64 linear-domain)"; }
+const char *prib_version(void) { return "priblast-b200 0.2 (sm_100a; fp32 span-scaled tiles + fp64 re-run)"; }
 
 int prib_acc_create(prib_ctx **out, const prib_acc_params *params) {
   if (!out || !params) return fail(PRIB_EINVAL, "null argument");
@@ -428,24 +552,26 @@ int prib_acc_create(prib_ctx **out, const prib_acc_params *params) {
     return fail(PRIB_EINVAL, "Error: -d option must be greater than 1");  // raccess.hpp:47-50
   if (params->maximal_span < 1 || params->maximal_span > kMaxSpan)
     return fail(PRIB_EINVAL, "maximal span must be in 1.." + std::to_string((int)kMaxSpan));
-  if (params->mode != 0) return fail(PRIB_EINVAL, "only mode 0 (fast) is implemented");
+  if (params->min_accessible_length > kMaxLoop)
+    return fail(PRIB_EINVAL, "minimum accessible length above 30 is not supported");
+  if (params->mode != 0 && params->mode != 1) return fail(PRIB_EINVAL, "mode must be 0 (auto) or 1 (fp64 only)");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
     return fail(PRIB_ECUDA, "no CUDA device available (this library has no CPU fallback)");
   if (params->device < 0 || params->device >= ndev) return fail(PRIB_EINVAL, "device ordinal out of range");
   CU(cudaSetDevice(params->device));
 
-  HostTables tab;
-  std::string err;
-  if (!build_tables(params->maximal_span, tab, err)) return fail(PRIB_EINVAL, err);
-
   prib_ctx *c = new (std::nothrow) prib_ctx();
   if (!c) return fail(PRIB_ENOMEM, "out of host memory");
   c->prm = *params;
   c->W = params->maximal_span;
   c->delta = params->min_accessible_length;
+  const char *pe = getenv("PRIB_PRECISION");
+  c->use_fp32 = params->mode == 0 && c->W <= kFp32MaxSpan && !(pe && strcmp(pe, "fp64") == 0);
   auto bail = [&](int code) {
+    std::string keep = g_err;
     prib_acc_destroy(c);
+    g_err = keep;
     return code;
   };
 #define CUB(call)                                                                             \
@@ -461,46 +587,28 @@ int prib_acc_create(prib_ctx **out, const prib_acc_params *params) {
   CUB(cudaEventCreate(&c->evk0));
   CUB(cudaEventCreate(&c->evk1));
   for (auto &e : c->evp) CUB(cudaEventCreate(&e));
-  CUB(cudaMalloc(&c->d_small, sizeof(SmallTables)));
-  CUB(cudaMemcpy(c->d_small, &tab.small, sizeof(SmallTables), cudaMemcpyHostToDevice));
-  CUB(cudaMalloc(&c->d_int11, tab.e_int11.size() * sizeof(real)));
-  CUB(cudaMemcpy(c->d_int11, tab.e_int11.data(), tab.e_int11.size() * sizeof(real), cudaMemcpyHostToDevice));
-  CUB(cudaMalloc(&c->d_int21, tab.e_int21.size() * sizeof(real)));
-  CUB(cudaMemcpy(c->d_int21, tab.e_int21.data(), tab.e_int21.size() * sizeof(real), cudaMemcpyHostToDevice));
-  CUB(cudaMalloc(&c->d_int22, tab.e_int22.size() * sizeof(real)));
-  CUB(cudaMemcpy(c->d_int22, tab.e_int22.data(), tab.e_int22.size() * sizeof(real), cudaMemcpyHostToDevice));
-  CUB(cudaMalloc(&c->d_log, tab.log_tbl.size() * sizeof(float)));
-  CUB(cudaMemcpy(c->d_log, tab.log_tbl.data(), tab.log_tbl.size() * sizeof(float), cudaMemcpyHostToDevice));
-
-  CUB(cudaMemcpyToSymbol(g_conv_d, &tab.small.conv[0][0], sizeof(double) * 32 * 32));
-  CUB(cudaMemcpyToSymbol(g_bulge_d, tab.small.e_bulge, sizeof(double) * 32));
-  {
-    // tile kernels: the widest CTA whose rings fit the opt-in shared memory of this device
-    const char *ks = getenv("PRIB_KERNELS");
-    c->kernel_set = (ks && ks[0] == '1') ? 1 : 2;
-    cudaDeviceProp prop;
-    CUB(cudaGetDeviceProperties(&prop, params->device));
-    const size_t smem_max = prop.sharedMemPerBlockOptin;
-    int TC = (int)((smem_max - 64) / (kTileRows * sizeof(real) + 1)) / 32 * 32;
-    if (TC > 1024) TC = 1024;
-    const char *tce = getenv("PRIB_TILE_COLS");
-    if (tce && atoi(tce) >= c->W + 34 && atoi(tce) <= TC) TC = atoi(tce) / 32 * 32;
-    if (TC < c->W + 34) return bail(fail(PRIB_ECUDA, "shared memory too small for the tile kernels"));
-    c->TC = TC;
-    c->tile_smem = (size_t)kTileRows * TC * sizeof(real) + TC + 16;
-    c->grid_tiles = prop.multiProcessorCount;
-    CUB(cudaFuncSetAttribute(k_inside_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->tile_smem));
-    CUB(cudaFuncSetAttribute(k_outside_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->tile_smem));
-    CUB(cudaMalloc(&c->d_tile_scratch, (size_t)c->grid_tiles * 2 * (c->W + 4) * TC * sizeof(real)));
+  cudaDeviceProp prop;
+  CUB(cudaGetDeviceProperties(&prop, params->device));
+  c->grid_tiles = prop.multiProcessorCount;
+  std::string err;
+  int rc = setup_engine<double>(c, ScaleSpec(), prop.sharedMemPerBlockOptin, err);
+  if (rc != PRIB_OK) return bail(rc == PRIB_EINVAL ? fail(rc, err) : rc);
+  if (c->use_fp32) {
+    rc = setup_engine<float>(c, default_scale_fp32(), prop.sharedMemPerBlockOptin, err);
+    if (rc != PRIB_OK) return bail(rc == PRIB_EINVAL ? fail(rc, err) : rc);
   }
+  const size_t scr64 = (size_t)2 * (c->W + 4) * c->e64.TC * sizeof(double);
+  const size_t scr32 = (size_t)2 * (c->W + 4) * c->e32.TC * sizeof(float);
+  CUB(cudaMalloc(&c->d_tile_scratch, (size_t)c->grid_tiles * std::max(scr64, scr32)));
+
   size_t free_b = 0, total_b = 0;
   CUB(cudaMemGetInfo(&free_b, &total_b));
   long long budget = params->max_batch_bytes > 0 ? params->max_batch_bytes : (long long)(free_b * 0.6);
   if (budget > (long long)(free_b * 0.9)) budget = (long long)(free_b * 0.9);
-  const long long per_col = state_bytes_per_column(c->W);
-  c->max_cols = budget / per_col / 32 * 32;
-  if (c->max_cols < 4096) return bail(fail(PRIB_ECUDA, "device memory budget too small for the DP state"));
-  c->state_cap_bytes = c->max_cols * per_col;
+  c->e64.max_cols = budget / state_bytes_per_column(c->W, 8) / 32 * 32;
+  c->e32.max_cols = budget / state_bytes_per_column(c->W, 4) / 32 * 32;
+  if (c->e64.max_cols < 4096) return bail(fail(PRIB_ECUDA, "device memory budget too small for the DP state"));
+  c->state_cap_bytes = budget;
   CUB(cudaMalloc(&c->d_state, (size_t)c->state_cap_bytes));
   c->cnt.dp_state_bytes = c->state_cap_bytes;
 #undef CUB
@@ -514,17 +622,17 @@ void prib_acc_destroy(prib_ctx *c) {
   free_batches(c);
   cudaFree(c->d_state);
   cudaFree(c->d_tile_scratch);
-  cudaFree(c->d_small);
-  cudaFree(c->d_int11);
-  cudaFree(c->d_int21);
-  cudaFree(c->d_int22);
+  c->e32.release();
+  c->e64.release();
   cudaFree(c->d_log);
   if (c->h_stage) cudaFreeHost(c->h_stage);
+  if (c->h_flags) cudaFreeHost(c->h_flags);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
   if (c->evk0) cudaEventDestroy(c->evk0);
   if (c->evk1) cudaEventDestroy(c->evk1);
-  for (auto &e : c->evp) if (e) cudaEventDestroy(e);
+  for (auto &e : c->evp)
+    if (e) cudaEventDestroy(e);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
   delete c;
 }
@@ -539,67 +647,31 @@ int prib_acc_stage(prib_ctx *c, int32_t n, const char *const *seq, const int32_t
   if (!c || n < 0 || (n > 0 && (!seq || !len))) return fail(PRIB_EINVAL, "bad argument");
   CU(cudaSetDevice(c->prm.device));
   free_batches(c);
-  c->lens.assign(len, len + n);
+  const long long max_cols = c->use_fp32 ? c->e32.max_cols : c->e64.max_cols;
   for (int k = 0; k < n; k++) {
     if (len[k] < 0) return fail(PRIB_EINVAL, "negative sequence length");
-    if (layout_columns(len[k]) + 2 * kPad > c->max_cols)
+    if (layout_columns(len[k]) + 2 * kPad > c->e64.max_cols)
       return fail(PRIB_ECUDA, "sequence " + std::to_string(k) + " does not fit the device DP budget");
   }
+  c->seqs.resize(n);
+  for (int k = 0; k < n; k++) c->seqs[k].assign(seq[k], (size_t)len[k]);
+  // packed device output image: [acc L | cond L] per sequence in caller order
+  std::vector<long long> acc_abs(n), cond_abs(n);
+  long long o = 0;
+  for (int k = 0; k < n; k++) {
+    acc_abs[k] = o;
+    cond_abs[k] = o + len[k];
+    o += 2LL * len[k];
+  }
+  c->out_floats = o;
   // longest first (the order of SortSequences, utils.cpp:53-60), then greedy fill of column budgets:
   // neighbours in a batch have similar lengths, which keeps the per-sequence scan warps balanced.
   std::vector<int> order(n);
   std::iota(order.begin(), order.end(), 0);
   std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return len[a] > len[b]; });
-  long long out_base = 0;
-  size_t pos = 0;
-  while (pos < order.size()) {
-    Batch b;
-    long long cols = 2 * kPad;
-    while (pos < order.size() && cols + layout_columns(len[order[pos]]) <= c->max_cols) {
-      cols += layout_columns(len[order[pos]]);
-      b.ids.push_back(order[pos++]);
-    }
-    b.n = (int)b.ids.size();
-    std::vector<const char *> sp(b.n);
-    std::vector<int32_t> sl(b.n);
-    std::vector<long long> ao(b.n), co(b.n);
-    long long o = 0;
-    for (int k = 0; k < b.n; k++) {
-      sp[k] = seq[b.ids[k]];
-      sl[k] = len[b.ids[k]];
-      ao[k] = o;
-      co[k] = o + sl[k];
-      o += 2LL * sl[k];
-      b.nt += sl[k];
-    }
-    BatchLayout lay;
-    build_layout(b.n, sp.data(), sl.data(), lay);
-    b.NC = lay.NC;
-    b.out_base = out_base;
-    out_base += o;
-    CU(cudaMalloc(&b.d_S, (size_t)b.NC));
-    CU(cudaMalloc(&b.d_col_seq, (size_t)b.NC * sizeof(int32_t)));
-    CU(cudaMalloc(&b.d_seq_len, (size_t)std::max(b.n, 1) * sizeof(int32_t)));
-    CU(cudaMalloc(&b.d_seq_off, (size_t)std::max(b.n, 1) * sizeof(long long)));
-    CU(cudaMalloc(&b.d_acc_off, (size_t)std::max(b.n, 1) * sizeof(long long)));
-    CU(cudaMalloc(&b.d_cond_off, (size_t)std::max(b.n, 1) * sizeof(long long)));
-    CU(cudaEventRecord(c->ev0, c->stream));
-    CU(cudaMemcpyAsync(b.d_S, lay.S.data(), (size_t)b.NC, cudaMemcpyHostToDevice, c->stream));
-    CU(cudaMemcpyAsync(b.d_col_seq, lay.col_seq.data(), (size_t)b.NC * 4, cudaMemcpyHostToDevice, c->stream));
-    CU(cudaMemcpyAsync(b.d_seq_len, sl.data(), (size_t)b.n * 4, cudaMemcpyHostToDevice, c->stream));
-    CU(cudaMemcpyAsync(b.d_seq_off, lay.seq_off.data(), (size_t)b.n * 8, cudaMemcpyHostToDevice, c->stream));
-    CU(cudaMemcpyAsync(b.d_acc_off, ao.data(), (size_t)b.n * 8, cudaMemcpyHostToDevice, c->stream));
-    CU(cudaMemcpyAsync(b.d_cond_off, co.data(), (size_t)b.n * 8, cudaMemcpyHostToDevice, c->stream));
-    CU(cudaEventRecord(c->ev1, c->stream));
-    CU(cudaStreamSynchronize(c->stream));  // host vectors go out of scope
-    float ms = 0;
-    CU(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
-    c->cnt.h2d_ms += ms;
-    c->cnt.h2d_bytes += b.NC * 5 + (long long)b.n * 28;
-    c->batches.push_back(std::move(b));
-  }
-  c->out_floats = out_base;
-  CU(cudaMalloc(&c->d_out, (size_t)std::max<long long>(out_base, 1) * sizeof(float)));
+  int rc = partition(c, order, max_cols, acc_abs, cond_abs, c->batches);
+  if (rc != PRIB_OK) return rc;
+  CU(cudaMalloc(&c->d_out, (size_t)std::max<long long>(o, 1) * sizeof(float)));
   c->staged = true;
   return PRIB_OK;
 }
@@ -608,30 +680,55 @@ int prib_acc_compute(prib_ctx *c) {
   if (!c) return fail(PRIB_EINVAL, "null context");
   if (!c->staged) return fail(PRIB_ESTATE, "prib_acc_compute called before prib_acc_stage");
   CU(cudaSetDevice(c->prm.device));
-  // entries the kernels never write (acc tail, cond head) must read 0: raccess.cpp:487-488
+  if (settle_kernel_time(c) != PRIB_OK) return PRIB_ECUDA;
   CU(cudaEventRecord(c->evk0, c->stream));
+  // entries the kernels never write (acc tail, cond head) must read 0: raccess.cpp:487-488
   CU(cudaMemsetAsync(c->d_out, 0, (size_t)std::max<long long>(c->out_floats, 1) * sizeof(float), c->stream));
+  std::vector<int> flagged;
   for (const Batch &b : c->batches) {
     if (b.n == 0) continue;
-    int rc = run_batch(c, b);
+    int rc = c->use_fp32 ? run_batch<float>(c, b, true) : run_batch<double>(c, b, true);
     if (rc != PRIB_OK) return rc;
     c->cnt.sequences += b.n;
     c->cnt.nucleotides += b.nt;
+    if (c->use_fp32) {
+      // range flags of this batch (tiny D2H; the wait also keeps the next batch from overwriting state)
+      if (c->h_flags_cap < b.n) {
+        if (c->h_flags) cudaFreeHost(c->h_flags);
+        c->h_flags = nullptr;
+        CU(cudaMallocHost(&c->h_flags, sizeof(int32_t) * (size_t)b.n));
+        c->h_flags_cap = b.n;
+      }
+      CU(cudaMemcpyAsync(c->h_flags, b.d_flags, sizeof(int32_t) * (size_t)b.n, cudaMemcpyDeviceToHost, c->stream));
+      CU(cudaStreamSynchronize(c->stream));
+      for (int k = 0; k < b.n; k++)
+        if (c->h_flags[k]) flagged.push_back(b.ids[k]);
+    }
+  }
+  if (!flagged.empty()) {
+    // re-run in double, on the GPU, writing to the same places of the output image
+    std::vector<long long> acc_abs(c->seqs.size()), cond_abs(c->seqs.size());
+    long long o = 0;
+    for (size_t k = 0; k < c->seqs.size(); k++) {
+      acc_abs[k] = o;
+      cond_abs[k] = o + (long long)c->seqs[k].size();
+      o += 2LL * (long long)c->seqs[k].size();
+    }
+    std::stable_sort(flagged.begin(), flagged.end(),
+                     [&](int a, int b) { return c->seqs[a].size() > c->seqs[b].size(); });
+    std::vector<Batch> fb;
+    int rc = partition(c, flagged, c->e64.max_cols, acc_abs, cond_abs, fb);
+    for (Batch &b : fb) {
+      if (rc == PRIB_OK) rc = run_batch<double>(c, b, false);
+      if (rc == PRIB_OK && cudaStreamSynchronize(c->stream) != cudaSuccess) rc = fail(PRIB_ECUDA, "fp64 re-run failed");
+      free_batch(b);
+    }
+    if (rc != PRIB_OK) return rc;
+    c->cnt.fp64_rerun_sequences += (long long)flagged.size();
   }
   CU(cudaEventRecord(c->evk1, c->stream));
   c->kernel_timed = false;
   c->computed = true;
-  return PRIB_OK;
-}
-
-static int settle_kernel_time(prib_ctx *c) {
-  if (settle_phases(c) != PRIB_OK) return PRIB_ECUDA;
-  if (!c->kernel_timed) {
-    float ms = 0;
-    CU(cudaEventElapsedTime(&ms, c->evk0, c->evk1));
-    c->cnt.kernel_ms += ms;
-    c->kernel_timed = true;
-  }
   return PRIB_OK;
 }
 
@@ -666,15 +763,12 @@ int prib_acc_fetch(prib_ctx *c, float *out, const int64_t *acc_off, const int64_
     c->cnt.d2h_ms += ms;
     c->cnt.d2h_bytes += c->out_floats * (long long)sizeof(float);
   }
-  for (const Batch &b : c->batches) {
-    long long o = b.out_base;
-    for (int k = 0; k < b.n; k++) {
-      const int id = b.ids[k];
-      const int L = c->lens[id];
-      std::memcpy(out + acc_off[id], c->h_stage + o, sizeof(float) * (size_t)L);
-      std::memcpy(out + cond_off[id], c->h_stage + o + L, sizeof(float) * (size_t)L);
-      o += 2LL * L;
-    }
+  long long o = 0;
+  for (size_t k = 0; k < c->seqs.size(); k++) {
+    const size_t L = c->seqs[k].size();
+    std::memcpy(out + acc_off[k], c->h_stage + o, sizeof(float) * L);
+    std::memcpy(out + cond_off[k], c->h_stage + o + L, sizeof(float) * L);
+    o += 2LL * (long long)L;
   }
   return PRIB_OK;
 }

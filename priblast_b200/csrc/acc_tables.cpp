@@ -8,7 +8,7 @@
 namespace prib {
 
 template <typename real>
-bool build_tables(int W, HostTablesT<real> &out, std::string &err) {
+bool build_tables(int W, int delta, const ScaleSpec &spec, HostTablesT<real> &out, std::string &err) {
   const prib_turner_params *p = prib_turner_embedded();
   if (!p) {
     err = "embedded Turner parameter blob missing or corrupt";
@@ -26,7 +26,14 @@ bool build_tables(int W, HostTablesT<real> &out, std::string &err) {
   auto sc = [&](int e) { return (double)(-e) * 10. / kT; };
   const double MLclosing = sc(p->ml_closing), MLintern = sc(p->ml_intern), MLbase = sc(p->ml_base);
   const double TermAU = sc(p->terminal_au);
-  T.e_mlbase = std::exp(MLbase);
+  const double kap = std::exp2(-spec.klog2), cA = std::exp2(spec.alog2), cB = std::exp2(spec.blog2);
+  auto kpow = [&](int n) { return std::exp2(-spec.klog2 * n); };
+  T.k2 = kap * kap;
+  T.inv_cA = 1.0 / cA;
+  T.kacc = kap * kap / (cA * cB);
+  T.kmul[0] = kpow(delta) / (cA * cB);
+  T.kmul[1] = kpow(delta + 1) / (cA * cB);
+  T.e_mlbase = kap * std::exp(MLbase);
   T.e_mlintern = std::exp(MLintern);
   T.e_mlclose = std::exp(MLclosing + MLintern);
   for (int t = 0; t < 8; t++) T.tau[t] = t > 2 && t < 7 ? std::exp(TermAU) : 1.0;
@@ -44,14 +51,17 @@ bool build_tables(int W, HostTablesT<real> &out, std::string &err) {
   // HairpinEnergy length term incl. the logarithmic extrapolation (raccess.cpp:823)
   for (int d = 0; d < kMaxSpan + 8; d++) {
     double q = d <= 30 ? hairpin[d] : hairpin[30] - p->lxc37 * std::log(d / 30.) * 10. / kT;
-    T.e_hairpin[d] = std::exp(q);
+    T.e_hairpin[d] = cA * kpow(d) * std::exp(q);
+    T.sB[d] = cB * kpow(-d);
+    T.us[d] = kpow(-d) / cA;
+    if (d + 1 < kMaxSpan + 8) T.hpB[d + 1] = kpow(d + 2) / cB * std::exp(q);  // indexed by dd = loop size + 1
   }
-  for (int u = 0; u < 32; u++) T.e_bulge[u] = u <= 30 ? std::exp(bulge[u]) : 0.0;
+  for (int u = 0; u < 32; u++) T.e_bulge[u] = u <= 30 ? kpow(u) * std::exp(bulge[u]) : 0.0;
   // generic interior loops (raccess.cpp:808-812): everything except 1x1, 1x2, 2x1, 2x2 and bulges
   for (int u1 = 1; u1 <= 30; u1++)
     for (int u2 = 1; u1 + u2 <= 30; u2++) {
       if (u1 + u2 < 4 || (u1 == 2 && u2 == 2)) continue;
-      T.conv[u1][u2] = std::exp(internal[u1 + u2] + ninio[std::abs(u1 - u2)]);
+      T.conv[u1][u2] = kpow(u1 + u2) * std::exp(internal[u1 + u2] + ninio[std::abs(u1 - u2)]);
     }
   for (int i = 0; i < 7; i++) {
     for (int j = 0; j < 5; j++)
@@ -77,9 +87,9 @@ bool build_tables(int W, HostTablesT<real> &out, std::string &err) {
   out.e_int21.resize(8 * 8 * 5 * 5 * 5);
   out.e_int22.resize(8 * 8 * 5 * 5 * 5 * 5);
   const int32_t *i11 = &p->int11[0][0][0][0], *i21 = &p->int21[0][0][0][0][0], *i22 = &p->int22[0][0][0][0][0][0];
-  for (size_t k = 0; k < out.e_int11.size(); k++) out.e_int11[k] = std::exp(sc(i11[k]));
-  for (size_t k = 0; k < out.e_int21.size(); k++) out.e_int21[k] = std::exp(sc(i21[k]));
-  for (size_t k = 0; k < out.e_int22.size(); k++) out.e_int22[k] = std::exp(sc(i22[k]));
+  for (size_t k = 0; k < out.e_int11.size(); k++) out.e_int11[k] = kpow(2) * std::exp(sc(i11[k]));
+  for (size_t k = 0; k < out.e_int21.size(); k++) out.e_int21[k] = kpow(3) * std::exp(sc(i21[k]));
+  for (size_t k = 0; k < out.e_int22.size(); k++) out.e_int22[k] = kpow(4) * std::exp(sc(i22[k]));
 
   // fmath::log(float) table, built from the host libm like fmath's LogVar ctor (fmath.hpp:181-207) so the
   // final -kT*log(P) reproduces the reference's edge values (log(0f) = -88.03, log(inf) = 88.72)
@@ -101,8 +111,8 @@ bool build_tables(int W, HostTablesT<real> &out, std::string &err) {
   return true;
 }
 
-template bool build_tables<double>(int, HostTablesT<double> &, std::string &);
-template bool build_tables<float>(int, HostTablesT<float> &, std::string &);
+template bool build_tables<double>(int, int, const ScaleSpec &, HostTablesT<double> &, std::string &);
+template bool build_tables<float>(int, int, const ScaleSpec &, HostTablesT<float> &, std::string &);
 
 void build_layout(int n, const char *const *seqs, const int32_t *lens, BatchLayout &out) {
   out.seq_off.resize(n);

@@ -20,8 +20,20 @@ typedef HostTablesT<double> HostTables;
 // Scales the embedded Turner parameters exactly like Raccess::set_energy_parameters
 // (raccess.hpp:105-158) and exponentiates them (always in double; cast to `real` at the end).
 // Returns false if the blob is missing.  Instantiated for float and double.
+// Span scaling of the stored band values (see SmallTables): kappa = 2^-klog2, cA = 2^alog2, cB = 2^blog2.
+struct ScaleSpec {
+  double klog2 = 0, alog2 = 0, blog2 = 0;
+};
+inline ScaleSpec default_scale_fp32() {
+  ScaleSpec s;
+  s.klog2 = 0.3;   // random-sequence inside weights grow ~2^0.6 per nt at the top, ~2^0 at the bottom
+  s.alog2 = 4.0;
+  s.blog2 = 16.0;
+  return s;
+}
+
 template <typename real>
-bool build_tables(int W, HostTablesT<real> &out, std::string &err);
+bool build_tables(int W, int delta, const ScaleSpec &sc, HostTablesT<real> &out, std::string &err);
 
 // Column layout of one batch: sequence k occupies columns seq_off[k] .. seq_off[k]+len[k]
 // (left indices 0..L), followed by >= kPad zero columns; the first sequence starts at kPad.

@@ -36,17 +36,20 @@ struct Tile {
   };
 
   struct ColState {  // per thread, fixed for the whole tile
+    int sq;          // sequence id (-1: padding)
     int L, i;        // sequence length and left index of this column (i < 0: padding / outside batch)
     long long zcol;  // column holding log Z of this sequence (seq_off + L)
   };
 
   static PRIB_HD void col_state(const Ctx &c, long long g, ColState &cs) {
+    cs.sq = -1;
     cs.L = 0;
     cs.i = -1;
     cs.zcol = 0;
     if (g < 0 || g >= c.NC) return;
     const int sq = c.col_seq[g];
     if (sq < 0) return;
+    cs.sq = sq;
     cs.L = c.seq_len[sq];
     cs.i = (int)(g - c.seq_off[sq]);
     cs.zcol = c.seq_off[sq] + cs.L;
@@ -98,11 +101,12 @@ struct Tile {
       const int tp = T.bp[si1][sj];
       if (tp) {
         const int t2 = T.bp[s[2]][s[d - 1]];
-        stem = sm.se[((d - 2) & (kRingSE - 1)) * TC + t + 1] +
-               sm.stem[((d - 2) & (kRingStem - 1)) * TC + t + 1] * T.e_stack[tp][T.rt[t2]];
+        stem = T.k2 * (sm.se[((d - 2) & (kRingSE - 1)) * TC + t + 1] +
+                       sm.stem[((d - 2) & (kRingStem - 1)) * TC + t + 1] * T.e_stack[tp][T.rt[t2]]);
       }
       real mb = 0;
       for (int m = 5; m <= d - 5; ++m) mb += scrM1[m * TC + t] * scrM2[(d - m) * TC + t + m];
+      mb *= T.inv_cA;
       stemD = tp ? stem * K::e_dangle(T, tp, i > 0, si, j < L, sj1) : 0;
       m2 = stemD * T.e_mlintern + sm.m2[((d - 1) & 1) * TC + t] * T.e_mlbase;
       m1 = m2 + mb;
@@ -175,6 +179,9 @@ struct Tile {
       c.at(A_MULTI, d, g) = mu;
       c.at(A_MULTI1, d, g) = m1;
       c.at(A_MULTI2, d, g) = m2;
+      if (!(K::in_safe_range(stem) && K::in_safe_range(se) && K::in_safe_range(mu) && K::in_safe_range(m1) &&
+            K::in_safe_range(m2)))
+        c.flags[cs.sq] = 1;
     }
   }
 
@@ -204,22 +211,25 @@ struct Tile {
       if (inner) {
         const int tt = T.rt[te];
         bmulti = (d + 1 <= W + 1 ? sm.mu[((d + 1) & 1) * TC + t - 1] * T.e_mlbase : (real)0) +
-                 bse * T.e_mlclose * T.e_d3[tt][sp1] * T.e_d5[tt][sq_];
+                 T.k2 * bse * T.e_mlclose * T.e_d3[tt][sp1] * T.e_d5[tt][sq_];
         real bm1 = 0;
         const int m1max = imin(L - q, W - d);
         for (int m = 5; m <= m1max; ++m) bm1 += scrBif[(d + m) * TC + t] * c.ld(A_MULTI2, m, g + d);
-        bmulti2 = bm1 + sm.m2[((d + 1) & 1) * TC + t] * T.e_mlbase;
+        bm1 *= T.inv_cA;
+        real ks = 0;
         const int m2max = imin(p, W - d);
-        for (int m = 5; m <= m2max; ++m) bmulti2 += scrBif[(d + m) * TC + t - m] * c.ld(A_MULTI1, m, g - m);
+        for (int m = 5; m <= m2max; ++m) ks += scrBif[(d + m) * TC + t - m] * c.ld(A_MULTI1, m, g - m);
+        bmulti2 = bm1 + sm.m2[((d + 1) & 1) * TC + t] * T.e_mlbase + ks * T.inv_cA;
         bmbif = bm1 + bmulti;
       }
       const int t2 = T.bp[sp1][sq_];
       if (t2) {
         const int t2r = T.rt[t2];
         const real dang = K::e_dangle(T, t2, p > 0, sp, q < L, sq1);
-        bstem = (real)exp(c.lao[g] + c.lbo[g + d] - c.lao[cs.zcol]) * dang;
+        const real base = (real)exp(c.lao[g] + c.lbo[g + d] - c.lao[cs.zcol]) * dang * T.sB[d];
+        real ls = 0;
         const int smax = imin(kMaxLoop, W - 1 - d);
-        if (smax >= 0) bstem += bse * T.e_stack[te][t2r];
+        if (smax >= 0) ls += bse * T.e_stack[te][t2r];
         const real *b3 = sm.stem + ((d + 3) & (kRingStem - 1)) * TC + t;
         const real *b4 = sm.stem + ((d + 4) & (kRingStem - 1)) * TC + t;
         const real *b5 = sm.stem + ((d + 5) & (kRingStem - 1)) * TC + t;
@@ -227,11 +237,11 @@ struct Tile {
         if (smax >= 1) {
           const int ta = T.bp[s[-1]][sq1];
           const int tb = T.bp[sp][s[d + 2]];
-          bstem += bu[1] * (b3[-2] * T.e_stack[ta][t2r] + b3[-1] * T.e_stack[tb][t2r]);
+          ls += bu[1] * (b3[-2] * T.e_stack[ta][t2r] + b3[-1] * T.e_stack[tb][t2r]);
         }
         if (smax >= 2) {
           const int to = T.bp[s[-1]][s[d + 2]];
-          bstem += b4[-2] * c.e_int11[idx11(to, t2r, sp, sq1)];
+          ls += b4[-2] * c.e_int11[idx11(to, t2r, sp, sq1)];
           real bs = 0;
           int slot = wrap_out(slot_d + 4);
           for (int u = 2; u <= smax; ++u) {
@@ -239,17 +249,17 @@ struct Tile {
             bs += bu[u] * (row[-u] + row[0]);
             slot = wrap_out(slot + 1);
           }
-          bstem += T.tau[t2r] * bs;
+          ls += T.tau[t2r] * bs;
         }
         if (smax >= 3) {
           const int ta = T.bp[s[-1]][s[d + 3]];
-          bstem += b5[-2] * c.e_int21[idx21(ta, t2r, sp, sq1, s[d + 2])];
+          ls += b5[-2] * c.e_int21[idx21(ta, t2r, sp, sq1, s[d + 2])];
           const int tb = T.bp[s[-2]][s[d + 2]];
-          bstem += b5[-3] * c.e_int21[idx21(t2r, tb, sq1, s[-1], sp)];
+          ls += b5[-3] * c.e_int21[idx21(t2r, tb, sq1, s[-1], sp)];
         }
         if (smax >= 4) {
           const int tc = T.bp[s[-2]][s[d + 3]];
-          bstem += b6[-3] * c.e_int22[idx22(tc, t2r, s[-1], sp, sq1, s[d + 2])];
+          ls += b6[-3] * c.e_int22[idx22(tc, t2r, s[-1], sp, sq1, s[d + 2])];
           real gs = 0;
           int slot = wrap_out(slot_d + 6);
           for (int sum = 4; sum <= smax; ++sum) {
@@ -257,9 +267,9 @@ struct Tile {
             for (int u1 = 1; u1 < sum; ++u1) gs += cv[u1 * 32 + sum - u1] * row[-u1];
             slot = wrap_out(slot + 1);
           }
-          bstem += T.e_mmI[t2r][sq1][sp] * gs;
+          ls += T.e_mmI[t2r][sq1][sp] * gs;
         }
-        bstem += bmulti2 * T.e_mlintern * dang;
+        bstem = base + T.k2 * ls + bmulti2 * T.e_mlintern * dang;
         bstemO = bstem * T.e_mmI[t2][s[2]][s[d - 1]];
         bstemB = bstem * T.tau[t2];
       }
@@ -276,6 +286,9 @@ struct Tile {
       c.at(B_STEMB, d, g) = bstemB;
       c.at(B_MULTI, d, g) = bmulti;
       c.at(B_MULTI2, d, g) = bmulti2;
+      if (!(K::in_safe_range(bstem) && K::in_safe_range(bmulti) && K::in_safe_range(bmulti2) &&
+            K::in_safe_range(bmbif)))
+        c.flags[cs.sq] = 1;
     }
   }
 };

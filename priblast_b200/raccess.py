@@ -38,7 +38,7 @@ def packed_layout(lens: Sequence[int]):
 
 
 class Raccess:
-    def __init__(self, *args, device: int = 0, max_batch_bytes: int = 0):
+    def __init__(self, *args, device: int = 0, max_batch_bytes: int = 0, mode: int = 0):
         if len(args) == 2:
             w, delta = args
             db_name, path = "db", ""
@@ -56,7 +56,7 @@ class Raccess:
         self.rank = 0
         self._lib = _capi.load()
         self._ctx = ctypes.c_void_p()
-        prm = _capi.AccParams(self.maximal_span, self.min_accessible_length, int(device), 0, int(max_batch_bytes))
+        prm = _capi.AccParams(self.maximal_span, self.min_accessible_length, int(device), int(mode), int(max_batch_bytes))
         _capi.check(self._lib.prib_acc_create(ctypes.byref(self._ctx), ctypes.byref(prm)))
         self._staged_lens = None
 

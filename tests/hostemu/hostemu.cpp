@@ -16,26 +16,26 @@
 #include "../../priblast_b200/csrc/acc_tile.h"
 
 using namespace prib;
-typedef double real;
-typedef Core<real> K;
-typedef K::Ctx Ctx;
 
 namespace {
 
-struct Emu {
-  HostTables tab;
+template <typename real>
+struct EmuT {
+  HostTablesT<real> tab;
   BatchLayout lay;
   std::vector<std::vector<real>> arr;
   std::vector<double> lao, lbo;
-  Ctx c;
+  std::vector<int32_t> flags;
+  typename Core<real>::Ctx c;
 };
 
-bool setup(Emu &e, int n, const char *const *seqs, const int32_t *lens, int W, int delta, float *out,
-           const int64_t *acc_off, const int64_t *cond_off) {
+template <typename real>
+bool setup(EmuT<real> &e, int n, const char *const *seqs, const int32_t *lens, int W, int delta, float *out,
+           const int64_t *acc_off, const int64_t *cond_off, const ScaleSpec &spec = ScaleSpec()) {
   std::string err;
-  if (!build_tables(W, e.tab, err)) return false;
+  if (!build_tables(W, delta, spec, e.tab, err)) return false;
   build_layout(n, seqs, lens, e.lay);
-  Ctx &c = e.c;
+  typename Core<real>::Ctx &c = e.c;
   std::memset(&c, 0, sizeof(c));
   c.NC = e.lay.NC;
   c.W = W;
@@ -54,7 +54,7 @@ bool setup(Emu &e, int n, const char *const *seqs, const int32_t *lens, int W, i
   e.arr.resize(kNumArr);
   for (int a = 0; a < kNumArr; a++) {
     int rows = (a == X_ML || a == X_MR) ? 32 : c.rows;
-    e.arr[a].assign((size_t)rows * (size_t)c.NC, 0.0);
+    e.arr[a].assign((size_t)rows * (size_t)c.NC, (real)0);
     c.arr[a] = e.arr[a].data();
   }
   e.lao.assign((size_t)c.NC, 0.0);
@@ -64,11 +64,15 @@ bool setup(Emu &e, int n, const char *const *seqs, const int32_t *lens, int W, i
   c.acc_off = (const long long *)acc_off;
   c.cond_off = (const long long *)cond_off;
   c.out = out;
+  e.flags.assign((size_t)n + 1, 0);
+  c.flags = e.flags.data();
   return true;
 }
 
-void run_dp(Emu &e) {
-  const Ctx &c = e.c;
+template <typename real>
+void run_dp(EmuT<real> &e) {
+  typedef Core<real> K;
+  const typename K::Ctx &c = e.c;
   double ring[256];
   for (int d = kTurn; d <= c.W + 1; d++)
     for (long long g = 0; g < c.NC; g++) K::inside_cell(c, g, d);
@@ -82,20 +86,22 @@ void run_dp(Emu &e) {
 
 // Emulation of the tile-persistent kernels (acc_tile.h): one "CTA" per tile, TC "threads", a barrier
 // (= end of the inner loop over t) after every span.
-void run_dp_tiled(Emu &e, int TC) {
+template <typename real>
+void run_dp_tiled(EmuT<real> &e, int TC) {
   typedef Tile<real> TL;
-  const Ctx &c = e.c;
+  typedef Core<real> K;
+  const typename K::Ctx &c = e.c;
   const int W = c.W, H = W + 1, TX = TC - H;
   const long long ntiles = (c.NC + TX - 1) / TX;
   std::vector<real> smem((size_t)kTileRows * TC), scr((size_t)2 * (W + 4) * TC);
   std::vector<uint8_t> sS((size_t)TC + 16);
-  std::vector<TL::ColState> cs(TC);
+  std::vector<typename TL::ColState> cs(TC);
   for (long long tile = 0; tile < ntiles; tile++) {
-    TL::Geo ge{tile * TX, TC, TX, H};
+    typename TL::Geo ge{tile * TX, TC, TX, H};
     std::fill(smem.begin(), smem.end(), (real)0);
     for (int k = 0; k < TC + 8; k++) sS[k] = (ge.g0 + k < c.NC) ? c.S[ge.g0 + k] : 0;
     for (int t = 0; t < TC; t++) TL::col_state(c, ge.g0 + t, cs[t]);
-    TL::InSmem sm = TL::carve_in(smem.data(), TC, sS.data());
+    typename TL::InSmem sm = TL::carve_in(smem.data(), TC, sS.data());
     for (int d = kTurn; d <= W + 1; d++)
       for (int t = 0; t < TC; t++) TL::inside_span(c, ge, sm, scr.data(), scr.data() + (size_t)(W + 4) * TC, t, cs[t], d);
   }
@@ -105,17 +111,19 @@ void run_dp_tiled(Emu &e, int TC) {
     K::scan_beta_outer(c, k, ring);
   }
   for (long long tile = 0; tile < ntiles; tile++) {
-    TL::Geo ge{tile * TX, TC, TX, H};
+    typename TL::Geo ge{tile * TX, TC, TX, H};
     std::fill(smem.begin(), smem.end(), (real)0);
     for (int t = 0; t < TC; t++) TL::col_state(c, ge.g0 - H + t, cs[t]);
-    TL::OutSmem sm = TL::carve_out(smem.data(), TC);
+    typename TL::OutSmem sm = TL::carve_out(smem.data(), TC);
     for (int d = W + 1; d >= kTurn; d--)
       for (int t = 0; t < TC; t++) TL::outside_span(c, ge, sm, scr.data(), t, cs[t], d, d % kRingOut);
   }
 }
 
-void run_acc(Emu &e) {
-  const Ctx &c = e.c;
+template <typename real>
+void run_acc(EmuT<real> &e) {
+  typedef Core<real> K;
+  const typename K::Ctx &c = e.c;
   for (long long g = 0; g < c.NC; g++) {
     K::biloop_left(c, g);
     K::biloop_right(c, g);
@@ -130,7 +138,7 @@ extern "C" {
 
 int hostemu_run_batch(int n, const char *const *seqs, const int32_t *lens, int W, int delta, float *out,
                       const int64_t *acc_off, const int64_t *cond_off, int /*nthreads*/) {
-  Emu e;
+  EmuT<double> e;
   for (int k = 0; k < n; k++) {
     std::memset(out + acc_off[k], 0, sizeof(float) * (size_t)lens[k]);
     std::memset(out + cond_off[k], 0, sizeof(float) * (size_t)lens[k]);
@@ -141,19 +149,49 @@ int hostemu_run_batch(int n, const char *const *seqs, const int32_t *lens, int W
   return 1;
 }
 
-// Same batch through the tile-persistent formulation; TC = emulated CTA width.
-int hostemu_run_batch_tiled(int n, const char *const *seqs, const int32_t *lens, int W, int delta, float *out,
-                            const int64_t *acc_off, const int64_t *cond_off, int TC) {
-  Emu e;
+}  // extern "C"
+
+namespace {
+template <typename real>
+int run_tiled(int n, const char *const *seqs, const int32_t *lens, int W, int delta, float *out,
+              const int64_t *acc_off, const int64_t *cond_off, int TC, const ScaleSpec &spec, int32_t *flags_out) {
+  EmuT<real> e;
   for (int k = 0; k < n; k++) {
     std::memset(out + acc_off[k], 0, sizeof(float) * (size_t)lens[k]);
     std::memset(out + cond_off[k], 0, sizeof(float) * (size_t)lens[k]);
   }
-  if (!setup(e, n, seqs, lens, W, delta, out, acc_off, cond_off)) return -1;
+  if (!setup(e, n, seqs, lens, W, delta, out, acc_off, cond_off, spec)) return -1;
   if (TC <= W + 2) return -2;
   run_dp_tiled(e, TC);
   run_acc(e);
+  if (flags_out) std::memcpy(flags_out, e.flags.data(), sizeof(int32_t) * (size_t)n);
   return 1;
+}
+}  // namespace
+
+extern "C" {
+
+// FP32 band arithmetic with span scaling; flags_out[k] != 0 marks sequences whose stored values left
+// the safe range (the product re-runs those in FP64).
+int hostemu_run_batch_tiled_f32(int n, const char *const *seqs, const int32_t *lens, int W, int delta, float *out,
+                                const int64_t *acc_off, const int64_t *cond_off, int TC, double klog2,
+                                double alog2, double blog2, int32_t *flags_out) {
+  ScaleSpec spec;
+  spec.klog2 = klog2;
+  spec.alog2 = alog2;
+  spec.blog2 = blog2;
+  return run_tiled<float>(n, seqs, lens, W, delta, out, acc_off, cond_off, TC, spec, flags_out);
+}
+
+// Same batch through the tile-persistent formulation; TC = emulated CTA width.
+int hostemu_run_batch_tiled(int n, const char *const *seqs, const int32_t *lens, int W, int delta, float *out,
+                            const int64_t *acc_off, const int64_t *cond_off, int TC, double klog2, double alog2,
+                            double blog2) {
+  ScaleSpec spec;
+  spec.klog2 = klog2;
+  spec.alog2 = alog2;
+  spec.blog2 = blog2;
+  return run_tiled<double>(n, seqs, lens, W, delta, out, acc_off, cond_off, TC, spec, nullptr);
 }
 
 int hostemu_run(const char *seq, int L, int W, int delta, float *acc, float *cond) {
@@ -169,7 +207,7 @@ int hostemu_run(const char *seq, int L, int W, int delta, float *acc, float *con
 
 // Debug: band state of one sequence, arrays as [kNumArr][W+4][L+1] (left index fastest), plus logs.
 int hostemu_dump(const char *seq, int L, int W, int delta, double *band, double *lao, double *lbo) {
-  Emu e;
+  EmuT<double> e;
   std::vector<float> out(2 * (size_t)L + 2, 0.f);
   int64_t ao = 0, co = L;
   int32_t len = L;

@@ -129,6 +129,31 @@ def test_long_sequence_log_path(oracle_lib):
     assert_close_kcal(c, ec, ATOL_VS_EXACT, RTOL_VS_EXACT, "cond")
 
 
+def test_fp32_engine_flags_and_fp64_rerun():
+    """The float engine must flag sequences whose band values leave its safe range (perfect GC hairpins:
+    Boltzmann weights ~e^170) and the double engine must recompute exactly those, on the GPU."""
+    names = ["perfect_hairpin_L70", "rand_L500_W70_d5", "gcstem_polyA_L576", "rand_L300_W70_d5"]
+    cases = [next(c for c in GOLDEN if c["name"] == n) for n in names]
+    r = rac(70, 5)
+    before = r.counters()["fp64_rerun_sequences"]
+    res = r.run_batch([c["seq"] for c in cases])
+    rerun = r.counters()["fp64_rerun_sequences"] - before
+    assert 1 <= rerun <= 2, rerun  # the hairpin (and possibly the GC-stem repeat), never the random ones
+    for c, (a, cc) in zip(cases, res):
+        assert_close_kcal(a, c["acc"], ATOL_VS_REF, RTOL_VS_REF, c["name"])
+        assert_close_kcal(cc, c["cond"], ATOL_VS_REF, RTOL_VS_REF, c["name"])
+
+
+def test_fp64_only_mode_matches_auto_mode():
+    seqs = _cfg2_sample(12)
+    auto = rac(70, 5).run_batch(seqs)
+    f64 = rac(70, 5, mode=1).run_batch(seqs)
+    assert rac(70, 5, mode=1).counters()["fp64_rerun_sequences"] == 0
+    for (a, c), (b, d) in zip(auto, f64):
+        assert_close_kcal(a, b, 5e-6, 5e-7, "acc fp32 vs fp64 engine")
+        assert_close_kcal(c, d, 5e-6, 5e-7, "cond fp32 vs fp64 engine")
+
+
 def test_edge_lengths():
     r = rac(70, 5)
     res = r.run_batch(["", "A", "ACG", "ACGU", "ACGUA", "GGGAAACCC"])

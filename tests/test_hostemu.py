@@ -19,7 +19,6 @@ def emu():
     subprocess.run(["make", "-C", d], check=True, stdout=subprocess.DEVNULL)
     lib = ctypes.CDLL(os.path.join(d, "libhostemu.so"))
     lib.hostemu_run.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, _f32p, _f32p]
-
     def run(seq, W, delta):
         L = len(seq)
         a = np.zeros(max(L, 1), np.float32)
@@ -27,6 +26,7 @@ def emu():
         assert lib.hostemu_run(seq.encode(), L, W, delta, a.ctypes.data_as(_f32p), c.ctypes.data_as(_f32p)) == 0
         return a[:L], c[:L]
 
+    run.lib = lib
     return run
 
 
@@ -48,3 +48,58 @@ def test_formulation_vs_exact_math(emu, oracle_lib, name):
     acc, cond = emu(case["seq"], case["W"], case["delta"])
     assert_close_kcal(acc, ea, ATOL_VS_EXACT, RTOL_VS_EXACT, "acc")
     assert_close_kcal(cond, ec, ATOL_VS_EXACT, RTOL_VS_EXACT, "cond")
+
+
+def _tiled(lib, seqs, W, delta, TC, scale=(0.0, 0.0, 0.0), f32=False):
+    from oracle_py import acc_layout
+    i32p, i64p = ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int64)
+    bs = [s.encode() if isinstance(s, str) else bytes(s) for s in seqs]
+    n = len(bs)
+    lens = np.array([len(b) for b in bs], np.int32)
+    ao, co, tot = acc_layout(lens)
+    out = np.zeros(max(tot, 1), np.float32)
+    flags = np.zeros(n, np.int32)
+    arr = (ctypes.c_char_p * n)(*bs)
+    args = [n, arr, lens.ctypes.data_as(i32p), W, delta, out.ctypes.data_as(_f32p), ao.ctypes.data_as(i64p),
+            co.ctypes.data_as(i64p)]
+    if TC is None:
+        assert lib.hostemu_run_batch(*args, 1) == 1
+    elif f32:
+        assert lib.hostemu_run_batch_tiled_f32(*args, TC, *[ctypes.c_double(x) for x in scale],
+                                               flags.ctypes.data_as(i32p)) == 1
+    else:
+        assert lib.hostemu_run_batch_tiled(*args, TC, *[ctypes.c_double(x) for x in scale]) == 1
+    return out, flags, lens
+
+
+_MIX_NAMES = ["rand_L500_W70_d5", "rand_L300_W70_d2", "gcstem_polyA_L576", "mixed_case_N_L300", "tiny_L9",
+              "rand_L72_W70_d5", "perfect_hairpin_L70"]
+_MIX = [next(c["seq"] for c in GOLDEN if c["name"] == n) for n in _MIX_NAMES]
+
+
+@pytest.mark.parametrize("W,TC", [(70, 352), (70, 104), (20, 64), (150, 352)])
+def test_tile_march_is_bit_identical_to_per_span_formulation(emu, W, TC):
+    """Halo recomputation + ring buffers (acc_tile.h) must not change a single bit versus the
+    one-cell-at-a-time formulation (acc_core.h), for any tile width."""
+    ref, _, _ = _tiled(emu.lib, _MIX, W, 5, None)
+    got, _, _ = _tiled(emu.lib, _MIX, W, 5, TC)
+    assert np.array_equal(ref.view(np.uint32), got.view(np.uint32))
+
+
+def test_span_scaling_is_transparent_in_double(emu):
+    ref, _, _ = _tiled(emu.lib, _MIX, 70, 5, None)
+    got, _, _ = _tiled(emu.lib, _MIX, 70, 5, 352, scale=(0.3, 4.0, 16.0))
+    assert np.abs(ref - got).max() < 2e-6
+
+
+def test_fp32_engine_emulation_flags_out_of_range_sequences(emu):
+    ref, _, lens = _tiled(emu.lib, _MIX, 70, 5, None)
+    got, flags, _ = _tiled(emu.lib, _MIX, 70, 5, 704, scale=(0.3, 4.0, 16.0), f32=True)
+    off = 0
+    for k, L in enumerate(lens):
+        seg = slice(off, off + 2 * int(L))
+        off += 2 * int(L)
+        if not flags[k]:
+            assert np.abs(ref[seg] - got[seg]).max() < 6e-6, k
+    assert flags[len(_MIX) - 1] == 1      # perfect 33-bp GC hairpin overflows float: must be flagged
+    assert flags[0] == 0 and flags[1] == 0  # random sequences stay in range
