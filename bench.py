@@ -60,15 +60,12 @@ def cpu_sample(seqs, cores: int, seconds: float = 15.0):
     """A bounded sample of the step's batch: about `seconds` of work for `cores` threads at the
     surveyed ~1.6 k nt/s/core; at least one sequence per core so every thread has work."""
     budget = 1600.0 * cores * seconds
-    take, nt = [], 0
+    mean_len = max(1.0, sum(len(s) for s in seqs) / max(len(seqs), 1))
+    want = int(min(len(seqs), max(cores, budget / mean_len)))
     # stride through the batch so the length mix of the sample matches the batch
-    stride = max(1, len(seqs) // max(cores * 2, 1))
-    for s in seqs[::stride]:
-        if nt + len(s) > budget and len(take) >= cores:
-            break
-        take.append(s)
-        nt += len(s)
-    return take, nt
+    stride = max(1, len(seqs) // max(want, 1))
+    take = list(seqs[::stride][:want])
+    return take, sum(len(s) for s in take)
 
 
 def run_cpu_reference(seqs, threads: int):

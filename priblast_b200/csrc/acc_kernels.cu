@@ -177,6 +177,29 @@ __global__ void __launch_bounds__(kThreads) k_biloop_right(typename Core<real>::
   const long long g = (long long)blockIdx.x * kThreads + threadIdx.x;
   if (g < c.NC) Core<real>::biloop_right(c, g);
 }
+// Interior-loop strand weights, tile version (acc_tile.h BiTile): blockDim = TXb owned columns; dynamic smem =
+// (W-5) x (TXb+32) reals (Alpha_stemI tile) + W x TXb bytes (per-thread lists of closing spans).
+template <typename real, bool LEFT>
+__global__ void __launch_bounds__(512) k_biloop_tile(typename Core<real>::Ctx c) {
+  typedef BiTile<real> BT;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  typename BT::Geo ge;
+  ge.TXb = blockDim.x;
+  ge.g0 = (long long)blockIdx.x * ge.TXb;
+  ge.cols = ge.TXb + 32;
+  ge.rows = c.W - 5 > 0 ? c.W - 5 : 0;
+  real *tile = reinterpret_cast<real *>(smem_raw);
+  uint8_t *list = reinterpret_cast<uint8_t *>(tile + (size_t)ge.rows * ge.cols);
+  const int total = ge.rows * ge.cols;
+  for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+    const int r = idx / ge.cols + 5, x = idx - (r - 5) * ge.cols;
+    tile[idx] = LEFT ? BT::load_left(c, ge, r, x) : BT::load_right(c, ge, r, x);
+  }
+  __syncthreads();
+  if (LEFT) BT::left(c, ge, tile, list, threadIdx.x);
+  else BT::right(c, ge, tile, list, threadIdx.x);
+}
+
 template <typename real>
 __global__ void __launch_bounds__(kThreads) k_hairpin_suffix(typename Core<real>::Ctx c) {
   const long long g = (long long)blockIdx.x * kThreads + threadIdx.x;
@@ -267,6 +290,8 @@ struct Engine {
   real *d_int11 = nullptr, *d_int21 = nullptr, *d_int22 = nullptr;
   int TC = 0;
   size_t tile_smem = 0;
+  int TXb = 0;            // biloop tile width
+  size_t bi_smem = 0;
   long long max_cols = 0;
 
   void release() {
@@ -285,6 +310,7 @@ struct prib_ctx {
   prib_acc_params prm{};
   int W = 70, delta = 5;
   bool use_fp32 = true;
+  bool biloop_v1 = false;
   cudaStream_t own_stream = nullptr, stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk0 = nullptr, evk1 = nullptr;
   cudaEvent_t evp[PRIB_NUM_PHASES + 1] = {};
@@ -472,9 +498,12 @@ int run_batch(prib_ctx *c, const Batch &b, bool timed) {
   if (timed) CU(cudaEventRecord(c->evp[3], st));
   k_outside_tile<real><<<tgrid, e.TC, e.tile_smem, st>>>(k, TX, ntiles, scratch);
   if (timed) CU(cudaEventRecord(c->evp[4], st));
-  k_biloop_left<real><<<grid, kThreads, 0, st>>>(k);
+  const unsigned bgrid = (unsigned)((b.NC + e.TXb - 1) / e.TXb);
+  if (c->biloop_v1) k_biloop_left<real><<<grid, kThreads, 0, st>>>(k);
+  else k_biloop_tile<real, true><<<bgrid, e.TXb, e.bi_smem, st>>>(k);
   if (timed) CU(cudaEventRecord(c->evp[5], st));
-  k_biloop_right<real><<<grid, kThreads, 0, st>>>(k);
+  if (c->biloop_v1) k_biloop_right<real><<<grid, kThreads, 0, st>>>(k);
+  else k_biloop_tile<real, false><<<bgrid, e.TXb, e.bi_smem, st>>>(k);
   if (timed) CU(cudaEventRecord(c->evp[6], st));
   k_hairpin_suffix<real><<<grid, kThreads, 0, st>>>(k);
   k_finalize<real><<<grid, kThreads, 0, st>>>(k);
@@ -511,6 +540,8 @@ int setup_engine(prib_ctx *c, const ScaleSpec &spec, size_t smem_max, std::strin
     CU(cudaMalloc(&c->d_log, tab.log_tbl.size() * sizeof(float)));
     CU(cudaMemcpy(c->d_log, tab.log_tbl.data(), tab.log_tbl.size() * sizeof(float), cudaMemcpyHostToDevice));
   }
+  // (function attributes are per device, not per context: always opt in to the device maximum so that
+  //  contexts with different spans can coexist)
   // the widest CTA whose rings fit the opt-in shared memory of this device
   int TC = (int)((smem_max - 64) / (kTileRows * sizeof(real) + 1)) / 32 * 32;
   if (TC > TileMaxThreads<real>::value) TC = TileMaxThreads<real>::value;
@@ -519,8 +550,17 @@ int setup_engine(prib_ctx *c, const ScaleSpec &spec, size_t smem_max, std::strin
   if (TC < c->W + 34) return fail(PRIB_ECUDA, "shared memory too small for the tile kernels at this span");
   e.TC = TC;
   e.tile_smem = (size_t)kTileRows * TC * sizeof(real) + TC + 16;
-  CU(cudaFuncSetAttribute(k_inside_tile<real>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e.tile_smem));
-  CU(cudaFuncSetAttribute(k_outside_tile<real>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e.tile_smem));
+  CU(cudaFuncSetAttribute(k_inside_tile<real>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+  CU(cudaFuncSetAttribute(k_outside_tile<real>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+  // interior-loop tiles: the widest block (<= 512 threads) whose Alpha_stemI tile + span lists fit
+  const int rows = c->W - 5 > 0 ? c->W - 5 : 0;
+  int TXb = 512;
+  while (TXb > 32 && (size_t)rows * (TXb + 32) * sizeof(real) + (size_t)(c->W + 1) * TXb + 64 > smem_max) TXb -= 32;
+  e.TXb = TXb;
+  e.bi_smem = (size_t)rows * (TXb + 32) * sizeof(real) + (size_t)(c->W + 1) * TXb + 64;
+  if (e.bi_smem > smem_max) return fail(PRIB_ECUDA, "shared memory too small for the interior-loop tiles");
+  CU(cudaFuncSetAttribute((k_biloop_tile<real, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+  CU(cudaFuncSetAttribute((k_biloop_tile<real, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
   return PRIB_OK;
 }
 
@@ -566,6 +606,8 @@ int prib_acc_create(prib_ctx **out, const prib_acc_params *params) {
   c->prm = *params;
   c->W = params->maximal_span;
   c->delta = params->min_accessible_length;
+  const char *be = getenv("PRIB_BILOOP");
+  c->biloop_v1 = be && be[0] == '1';
   const char *pe = getenv("PRIB_PRECISION");
   c->use_fp32 = params->mode == 0 && c->W <= kFp32MaxSpan && !(pe && strcmp(pe, "fp64") == 0);
   auto bail = [&](int code) {

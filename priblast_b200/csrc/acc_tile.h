@@ -294,3 +294,160 @@ struct Tile {
 };
 
 }  // namespace prib
+
+// ------------------------------------------------------------------------------------------------
+// Interior-loop strand weights (restructured raccess.cpp:614-771), tile version.
+//
+// ML[u1][i] / MR[u2][j'] are sums over the outer cells (i, j' = i + dp) that close a loop.  Only ~3/8 of
+// the cells can (Beta_stemend != 0 needs a pair), so each thread first lists ITS valid spans and then
+// walks only those: lanes sit at different spans, which is fine because there is no wavefront here and
+// the Alpha_stemI tile in shared memory has a row stride that is a multiple of 32 words (bank = column).
+// The left kernel reads the tile start-indexed, the right kernel end-indexed (element (r, q) = cell with
+// span r ENDING at column q), so that a lane's column never depends on its span.
+// ------------------------------------------------------------------------------------------------
+namespace prib {
+
+template <typename real>
+struct BiTile {
+  typedef Core<real> K;
+  typedef typename K::Ctx Ctx;
+  typedef typename K::SmallTables ST;
+
+  struct Geo {
+    long long g0;  // first owned column
+    int TXb;       // owned columns = threads
+    int cols;      // TXb + 32 (row stride of the tile; multiple of 32)
+    int rows;      // W - 5: spans 5 .. W-1
+  };
+
+  // element of the start-indexed tile: span r, global column g0 + x        (left kernel)
+  static PRIB_HD real load_left(const Ctx &c, const Geo &ge, int r, int x) {
+    const long long col = ge.g0 + x;
+    return col < c.NC ? c.ld(A_STEMI, r, col) : (real)0;
+  }
+  // element of the end-indexed tile: span r, END column g0 - 31 + x        (right kernel)
+  static PRIB_HD real load_right(const Ctx &c, const Geo &ge, int r, int x) {
+    const long long col = ge.g0 - 31 + x - r;
+    return (col >= 0 && col < c.NC) ? c.ld(A_STEMI, r, col) : (real)0;
+  }
+
+  // thread t = left index i (column g0 + t); list: uint8 [W][TXb] scratch in shared memory
+  static PRIB_HD void left(const Ctx &c, const Geo &ge, const real *tile, uint8_t *list, int t) {
+    const long long g = ge.g0 + t;
+    if (g >= c.NC) return;
+    typename K::ColInfo ci;
+    if (!K::col_info(c, g, ci)) return;
+    const ST &T = *c.T;
+    const real *cv = K::conv_tab(T), *bu = K::bulge_tab(T);
+    const int L = ci.L, i = ci.i, W = c.W, delta = c.delta, TXb = ge.TXb, cols = ge.cols;
+    const uint8_t *s = c.S + g;
+    real ml[kMaxLoop + 1];
+#pragma unroll
+    for (int u = 0; u <= kMaxLoop; ++u) ml[u] = 0;
+    int cnt = 0;
+    if (i >= 1) {
+      const int dpmax = imin(W - 1, L - 1 - i);
+      // pass A (all lanes at the same span): list the closing spans, add bulges (u2 = 0) and, for
+      // delta == 2, the 2x1 / 2x2 special loops
+      for (int dp = delta + 5; dp <= dpmax; ++dp) {
+        const real bse = c.ld(B_STEM, dp + 2, g - 1);
+        if (bse == 0) continue;
+        list[cnt * TXb + t] = (uint8_t)dp;
+        ++cnt;
+        const real bseB = c.ld(B_STEMB, dp + 2, g - 1);
+        const int umax = imin(kMaxLoop, dp - 5);
+#pragma unroll
+        for (int u1 = 2; u1 <= kMaxLoop; ++u1)
+          if (u1 >= delta && u1 <= umax) ml[u1] += bseB * bu[u1] * c.ld(A_STEMB, dp - u1, g + u1);
+        if (delta == 2) {
+          const int te = T.bp[s[0]][s[dp + 1]];
+          const real bseO = c.ld(B_STEMO, dp + 2, g - 1);
+          if (dp - 5 >= 3) ml[2] += K::loop_weight(c, T, s, g, dp, te, bse, bseO, bseB, 2, 1);
+          if (dp - 5 >= 4) ml[2] += K::loop_weight(c, T, s, g, dp, te, bse, bseO, bseB, 2, 2);
+        }
+      }
+      // pass B (each lane at its own span): generic interior loops out of the shared-memory tile
+      for (int k = 0; k < cnt; ++k) {
+        const int dp = list[k * TXb + t];
+        const real bseO = c.ld(B_STEMO, dp + 2, g - 1);
+        const int smax = imin(kMaxLoop, dp - 5);
+#pragma unroll
+        for (int u1 = 2; u1 <= kMaxLoop - 1; ++u1) {
+          if (u1 >= delta && u1 <= smax - 1) {
+            real a = 0;
+            const real *p = tile + (dp - u1 - 1 - 5) * cols + t + u1;  // inner cell (i+u1, j'-u2) at u2 = 1
+            const int n2 = smax - u1;
+            for (int u2 = 1; u2 <= n2; ++u2) {
+              a += cv[u1 * 32 + u2] * *p;
+              p -= cols;
+            }
+            ml[u1] += bseO * a;
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int u1 = 2; u1 <= kMaxLoop; ++u1)
+      if (u1 >= delta) c.at(X_ML, u1, g) = ml[u1];
+  }
+
+  // thread t = right end j' of the outer cell (column g0 + t)
+  static PRIB_HD void right(const Ctx &c, const Geo &ge, const real *tile, uint8_t *list, int t) {
+    const long long g2 = ge.g0 + t;
+    if (g2 >= c.NC) return;
+    typename K::ColInfo ci;
+    if (!K::col_info(c, g2, ci)) return;
+    const ST &T = *c.T;
+    const real *cv = K::conv_tab(T), *bu = K::bulge_tab(T);
+    const int L = ci.L, jp = ci.i, W = c.W, delta = c.delta, TXb = ge.TXb, cols = ge.cols;
+    real mr[kMaxLoop + 1];
+#pragma unroll
+    for (int u = 0; u <= kMaxLoop; ++u) mr[u] = 0;
+    int cnt = 0;
+    if (jp <= L - 1) {
+      const int dpmax = imin(W - 1, jp - 1);  // i = jp - dp >= 1
+      for (int dp = delta + 5; dp <= dpmax; ++dp) {
+        const long long g = g2 - dp;  // column of i
+        const real bse = c.ld(B_STEM, dp + 2, g - 1);
+        if (bse == 0) continue;
+        list[cnt * TXb + t] = (uint8_t)dp;
+        ++cnt;
+        const real bseB = c.ld(B_STEMB, dp + 2, g - 1);
+        const int umax = imin(kMaxLoop, dp - 5);
+#pragma unroll
+        for (int u2 = 2; u2 <= kMaxLoop; ++u2)
+          if (u2 >= delta && u2 <= umax) mr[u2] += bseB * bu[u2] * c.ld(A_STEMB, dp - u2, g);
+        if (delta == 2) {
+          const uint8_t *s = c.S + g;
+          const int te = T.bp[s[0]][s[dp + 1]];
+          const real bseO = c.ld(B_STEMO, dp + 2, g - 1);
+          if (dp - 5 >= 3) mr[2] += K::loop_weight(c, T, s, g, dp, te, bse, bseO, bseB, 1, 2);
+          if (dp - 5 >= 4) mr[2] += K::loop_weight(c, T, s, g, dp, te, bse, bseO, bseB, 2, 2);
+        }
+      }
+      for (int k = 0; k < cnt; ++k) {
+        const int dp = list[k * TXb + t];
+        const real bseO = c.ld(B_STEMO, dp + 2, g2 - dp - 1);
+        const int smax = imin(kMaxLoop, dp - 5);
+#pragma unroll
+        for (int u2 = 2; u2 <= kMaxLoop - 1; ++u2) {
+          if (u2 >= delta && u2 <= smax - 1) {
+            real a = 0;
+            const real *p = tile + (dp - u2 - 1 - 5) * cols + t + 31 - u2;  // inner cell ends at j' - u2; u1 = 1
+            const int n1 = smax - u2;
+            for (int u1 = 1; u1 <= n1; ++u1) {
+              a += cv[u1 * 32 + u2] * *p;
+              p -= cols;
+            }
+            mr[u2] += bseO * a;
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int u2 = 2; u2 <= kMaxLoop; ++u2)
+      if (u2 >= delta) c.at(X_MR, u2, g2) = mr[u2];
+  }
+};
+
+}  // namespace prib

@@ -121,12 +121,38 @@ void run_dp_tiled(EmuT<real> &e, int TC) {
 }
 
 template <typename real>
-void run_acc(EmuT<real> &e) {
+void run_biloop_tiled(EmuT<real> &e, int TXb) {
+  typedef BiTile<real> BT;
+  const typename Core<real>::Ctx &c = e.c;
+  typename BT::Geo ge;
+  ge.TXb = TXb;
+  ge.cols = TXb + 32;
+  ge.rows = c.W - 5 > 0 ? c.W - 5 : 0;
+  std::vector<real> tile((size_t)ge.rows * ge.cols + 1);
+  std::vector<uint8_t> list((size_t)(c.W + 1) * TXb);
+  for (int side = 0; side < 2; side++)
+    for (long long g0 = 0; g0 < c.NC; g0 += TXb) {
+      ge.g0 = g0;
+      for (int r = 5; r < 5 + ge.rows; r++)
+        for (int x = 0; x < ge.cols; x++)
+          tile[(size_t)(r - 5) * ge.cols + x] = side == 0 ? BT::load_left(c, ge, r, x) : BT::load_right(c, ge, r, x);
+      for (int t = 0; t < TXb; t++) {
+        if (side == 0) BT::left(c, ge, tile.data(), list.data(), t);
+        else BT::right(c, ge, tile.data(), list.data(), t);
+      }
+    }
+}
+
+template <typename real>
+void run_acc(EmuT<real> &e, int TXb = 0) {
   typedef Core<real> K;
   const typename K::Ctx &c = e.c;
+  if (TXb > 0) run_biloop_tiled(e, TXb);
   for (long long g = 0; g < c.NC; g++) {
-    K::biloop_left(c, g);
-    K::biloop_right(c, g);
+    if (TXb == 0) {
+      K::biloop_left(c, g);
+      K::biloop_right(c, g);
+    }
     K::hairpin_suffix(c, g);
   }
   for (long long g = 0; g < c.NC; g++) K::finalize_position(c, g);
@@ -163,7 +189,7 @@ int run_tiled(int n, const char *const *seqs, const int32_t *lens, int W, int de
   if (!setup(e, n, seqs, lens, W, delta, out, acc_off, cond_off, spec)) return -1;
   if (TC <= W + 2) return -2;
   run_dp_tiled(e, TC);
-  run_acc(e);
+  run_acc(e, TC >= 256 ? 128 : 64);
   if (flags_out) std::memcpy(flags_out, e.flags.data(), sizeof(int32_t) * (size_t)n);
   return 1;
 }

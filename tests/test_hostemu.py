@@ -103,3 +103,14 @@ def test_fp32_engine_emulation_flags_out_of_range_sequences(emu):
             assert np.abs(ref[seg] - got[seg]).max() < 6e-6, k
     assert flags[len(_MIX) - 1] == 1      # perfect 33-bp GC hairpin overflows float: must be flagged
     assert flags[0] == 0 and flags[1] == 0  # random sequences stay in range
+
+
+@pytest.mark.parametrize("name", ["rand_L300_W70_d2", "rand_L300_W70_d10", "rand_L100_W20_d2", "rand_L500_W150_d2",
+                                  "rand_L500_W70_d5", "gcstem_polyA_L576", "mixed_case_N_L300"])
+def test_tiled_formulation_vs_reference(emu, name):
+    """Tile march + tiled interior-loop strand weights (incl. the delta == 2 special loops) vs the fixtures."""
+    case = next(c for c in GOLDEN if c["name"] == name)
+    out, _, lens = _tiled(emu.lib, [case["seq"]], case["W"], case["delta"], 352 if case["W"] > 100 else 256)
+    L = int(lens[0])
+    assert_close_kcal(out[:L], case["acc"], ATOL_VS_REF, RTOL_VS_REF, "acc")
+    assert_close_kcal(out[L:2 * L], case["cond"], ATOL_VS_REF, RTOL_VS_REF, "cond")
