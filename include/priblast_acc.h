@@ -94,6 +94,9 @@ int prib_acc_get_counters(prib_ctx *ctx, prib_acc_counters *out);
  * only copy bandwidth and bf16 GEMM throughput). */
 int prib_peak_probe(int32_t device, double *mufu_gops, double *ffma_gops, double *dfma_gops);
 
+/* Number of CUDA devices visible to the process (0 if none / no driver). */
+int prib_device_count(void);
+
 /* Pinned host memory for `out` (optional). */
 void *prib_host_alloc(size_t bytes);
 void prib_host_free(void *p);

@@ -58,6 +58,7 @@ SIGNATURES = {
     "prib_acc_get_counters": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(AccCounters)]),
     "prib_peak_probe": (ctypes.c_int, [ctypes.c_int32, ctypes.POINTER(ctypes.c_double),
                                        ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]),
+    "prib_device_count": (ctypes.c_int, []),
     "prib_host_alloc": (ctypes.c_void_p, [ctypes.c_size_t]),
     "prib_host_free": (None, [ctypes.c_void_p]),
     "prib_last_error": (ctypes.c_char_p, []),

@@ -830,6 +830,12 @@ int prib_acc_get_counters(prib_ctx *c, prib_acc_counters *out) {
   return PRIB_OK;
 }
 
+int prib_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+
 void *prib_host_alloc(size_t bytes) {
   void *p = nullptr;
   if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) {

@@ -1,0 +1,137 @@
+// `pRIblast db` front-end on top of libpriblast_acc.so: same options and defaults as the reference
+// (main.cpp:43-73, db_construction_parameters.cpp:32-78), same five output files.
+// The per-sequence OpenMP/MPI loop of DbConstruction::CalculateAccessibility (db_construction.cpp:170-229)
+// becomes ONE prib_acc_run call per GPU; the block/heap/dynamic distributors (-a) all map to the
+// length-balanced partitioner over the GPUs of this box (db_format.h lpt_partition); output order is the
+// FASTA order, i.e. what the reference emits with -np 1 and -a heap|block.
+#include <getopt.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../../include/priblast_acc.h"
+#include "db_format.h"
+
+using namespace prib;
+
+static int die(const std::string &msg) {
+  std::fprintf(stderr, "%s\n", msg.c_str());
+  return 1;
+}
+
+static void usage() {
+  std::printf(
+      "pRIblast-b200 db: database construction with GPU accessibility\n"
+      "usage: pRIblast_b200 db -i InputFastaFile -o OutputDbName [-r RepeatMaskingStyle] [-s LookupTableSize]\n"
+      "                        [-w MaximalSpan] [-d MinAccessibleLength] [-c ChunkSize] [-a block|heap|dynamic]\n"
+      "                        [-p TmpPath]\n"
+      "defaults: -r 0 -s 8 -w 70 -d 5 -a heap -c INT_MAX   (reference: main.cpp:43-73)\n"
+      "environment: PRIB_NUM_GPUS=n limits the GPUs used (default: all visible)\n");
+}
+
+int main(int argc, char *argv[]) {
+  if (argc == 1 || std::strcmp(argv[1], "-h") == 0) {
+    usage();
+    return 0;
+  }
+  if (std::strcmp(argv[1], "db") != 0) {
+    std::printf("usage: pRIblast_b200 [-h] db options   (the `ris` step stays the reference binary)\n");
+    return 0;
+  }
+  std::string input, db, tmp_path, alg = "heap";
+  DbParams prm;
+  int c;
+  optind = 1;
+  while ((c = getopt(argc - 1, argv + 1, "i:o:r:s:w:d:t:p:a:c:")) != -1) {
+    switch (c) {
+      case 'i': input = optarg; break;
+      case 'o': db = optarg; break;
+      case 'r': prm.repeat_flag = std::atoi(optarg); break;
+      case 's': prm.hash_size = std::atoi(optarg); break;
+      case 'w': prm.maximal_span = std::atoi(optarg); break;
+      case 'd': prm.min_accessible_length = std::atoi(optarg); break;
+      case 'p': tmp_path = optarg; break;  // accepted; there are no temp files any more
+      case 'a': alg = optarg; break;
+      case 'c': prm.chunk_size = std::atoi(optarg); break;
+      default: return die("Error: invalid argument");  // incl. -t, as in the reference
+    }
+  }
+  if (alg != "block" && alg != "heap" && alg != "dynamic") return die("Error: parallel algorithm not supported");
+
+  std::vector<std::string> names, seqs;
+  std::string err;
+  if (!read_fasta(input, names, seqs, err)) return die(err);
+  if (db.empty()) return die("Error: -o option is required");                                   // raccess.hpp:42-45
+  if (prm.min_accessible_length <= 1) return die("Error: -d option must be greater than 1");   // raccess.hpp:47-50
+  if (prm.repeat_flag < 0 || prm.repeat_flag > 2) return die("Error: -r option must be 0, 1, or 2");
+  const int delta = prm.min_accessible_length;
+  for (size_t k = 0; k < seqs.size(); k++)
+    if ((int)seqs[k].size() < delta)
+      return die("Error: sequence " + names[k] + " is shorter than the minimum accessible length (-d): the "
+                 "reference writes a corrupt record for it (raccess.cpp:449-450); refusing");
+
+  // ---- accessibility on the GPUs ---------------------------------------------------------------
+  const bool formats_only = std::getenv("PRIB_DB_FORMATS_ONLY") != nullptr;  // test switch: no .acc, no GPU
+  std::vector<int64_t> acc_off(seqs.size()), cond_off(seqs.size());
+  int64_t total = 0;
+  for (size_t k = 0; k < seqs.size(); k++) {
+    acc_off[k] = total;
+    cond_off[k] = total + (int64_t)seqs[k].size();
+    total += 2 * (int64_t)seqs[k].size();
+  }
+  float *image = nullptr;
+  if (!formats_only) {
+    int ngpu = prib_device_count();
+    if (const char *e = std::getenv("PRIB_NUM_GPUS")) ngpu = std::min(ngpu, std::max(1, std::atoi(e)));
+    if (ngpu <= 0) return die("Error: no CUDA device available (there is no CPU path)");
+    image = (float *)prib_host_alloc(sizeof(float) * (size_t)std::max<int64_t>(total, 1));
+    if (!image) return die(std::string("Error: ") + prib_last_error());
+    std::vector<std::vector<int>> part;
+    lpt_partition(seqs, ngpu, part);
+    std::vector<std::string> errors(ngpu);
+    std::vector<std::thread> workers;
+    for (int d = 0; d < ngpu; d++) {
+      workers.emplace_back([&, d]() {
+        const std::vector<int> &ids = part[d];
+        if (ids.empty()) return;
+        prib_acc_params ap;
+        std::memset(&ap, 0, sizeof(ap));
+        ap.maximal_span = prm.maximal_span;
+        ap.min_accessible_length = delta;
+        ap.device = d;
+        prib_ctx *ctx = nullptr;
+        if (prib_acc_create(&ctx, &ap) != PRIB_OK) {
+          errors[d] = prib_last_error();
+          return;
+        }
+        std::vector<const char *> sp(ids.size());
+        std::vector<int32_t> sl(ids.size());
+        std::vector<int64_t> ao(ids.size()), co(ids.size());
+        for (size_t k = 0; k < ids.size(); k++) {
+          sp[k] = seqs[ids[k]].data();
+          sl[k] = (int32_t)seqs[ids[k]].size();
+          ao[k] = acc_off[ids[k]];
+          co[k] = cond_off[ids[k]];
+        }
+        if (prib_acc_run(ctx, (int32_t)ids.size(), sp.data(), sl.data(), image, ao.data(), co.data()) != PRIB_OK)
+          errors[d] = prib_last_error();
+        prib_acc_destroy(ctx);
+      });
+    }
+    for (auto &w : workers) w.join();
+    for (int d = 0; d < ngpu; d++)
+      if (!errors[d].empty()) return die("Error: GPU " + std::to_string(d) + ": " + errors[d]);
+  }
+
+  // ---- database files --------------------------------------------------------------------------
+  if (!write_seq_ind(db, seqs, prm, err)) return die(err);
+  if (!formats_only && !write_acc(db, seqs, image, acc_off, cond_off, delta, err)) return die(err);
+  if (!write_nam(db, names, err)) return die(err);
+  if (!write_bas(db, prm, err)) return die(err);
+  if (image) prib_host_free(image);
+  return 0;
+}
