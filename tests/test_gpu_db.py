@@ -40,10 +40,14 @@ def _hits(path):
     rows = []
     for ln in open(path):
         f = ln.rstrip("\n").split(",")
-        if len(f) < 8:
+        # Id, Query name, Query Length, Target name, Target Length, Accessibility E, Hybridization E, Interaction E, BasePair
+        if len(f) < 9:
             continue
-        rows.append((f[0], f[2], f[7].strip(), float(f[4]), float(f[5]), float(f[6])))
-    return rows
+        try:
+            rows.append((f[1], f[3], f[8].strip(), float(f[5]), float(f[6]), float(f[7])))
+        except ValueError:  # header lines of the ris output
+            continue
+    return sorted(rows)  # the reference merges per-thread files: line order varies from run to run
 
 
 def test_gpu_db_then_reference_ris(tmp_path):
