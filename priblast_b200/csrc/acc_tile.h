@@ -128,9 +128,12 @@ struct Tile {
           const int t2 = T.rt[T.bp[s[2]][s[d - 1]]];
           acc += st2[1] * c.e_int11[idx11(te, t2, si1, sj)];
           real bs = 0;
-          for (int u = 2; u <= smax; ++u) {
-            const real *row = sm.stemB + ((d - u) & (kRingIn - 1)) * TC + t;
-            bs += bu[u] * (row[u] + row[0]);
+#pragma unroll
+          for (int u = 2; u <= kMaxLoop; ++u) {
+            if (u <= smax) {
+              const real *row = sm.stemB + ((d - u) & (kRingIn - 1)) * TC + t;
+              bs += bu[u] * (row[u] + row[0]);
+            }
           }
           acc += T.tau[te] * bs;
         }
@@ -143,10 +146,16 @@ struct Tile {
         if (smax >= 4) {
           const int tc = T.rt[T.bp[s[3]][s[d - 2]]];
           acc += st4[2] * c.e_int22[idx22(te, tc, si1, s[2], s[d - 1], sj)];
+          // fully unrolled: every coefficient is a compile-time offset into constant memory, so a
+          // stencil term is exactly one LDS and one FMA
           real gs = 0;
-          for (int sum = 4; sum <= smax; ++sum) {
-            const real *row = sm.stemI + ((d - sum) & (kRingIn - 1)) * TC + t;
-            for (int u1 = 1; u1 < sum; ++u1) gs += cv[u1 * 32 + sum - u1] * row[u1];
+#pragma unroll
+          for (int sum = 4; sum <= kMaxLoop; ++sum) {
+            if (sum <= smax) {
+              const real *row = sm.stemI + ((d - sum) & (kRingIn - 1)) * TC + t;
+#pragma unroll
+              for (int u1 = 1; u1 < sum; ++u1) gs += cv[u1 * 32 + sum - u1] * row[u1];
+            }
           }
           acc += T.e_mmI[te][si1][sj] * gs;
         }
@@ -244,10 +253,13 @@ struct Tile {
           ls += b4[-2] * c.e_int11[idx11(to, t2r, sp, sq1)];
           real bs = 0;
           int slot = wrap_out(slot_d + 4);
-          for (int u = 2; u <= smax; ++u) {
-            const real *row = sm.stemB + slot * TC + t - 1;
-            bs += bu[u] * (row[-u] + row[0]);
-            slot = wrap_out(slot + 1);
+#pragma unroll
+          for (int u = 2; u <= kMaxLoop; ++u) {
+            if (u <= smax) {
+              const real *row = sm.stemB + slot * TC + t - 1;
+              bs += bu[u] * (row[-u] + row[0]);
+              slot = wrap_out(slot + 1);
+            }
           }
           ls += T.tau[t2r] * bs;
         }
@@ -262,10 +274,14 @@ struct Tile {
           ls += b6[-3] * c.e_int22[idx22(tc, t2r, s[-1], sp, sq1, s[d + 2])];
           real gs = 0;
           int slot = wrap_out(slot_d + 6);
-          for (int sum = 4; sum <= smax; ++sum) {
-            const real *row = sm.stemO + slot * TC + t - 1;
-            for (int u1 = 1; u1 < sum; ++u1) gs += cv[u1 * 32 + sum - u1] * row[-u1];
-            slot = wrap_out(slot + 1);
+#pragma unroll
+          for (int sum = 4; sum <= kMaxLoop; ++sum) {
+            if (sum <= smax) {
+              const real *row = sm.stemO + slot * TC + t - 1;
+#pragma unroll
+              for (int u1 = 1; u1 < sum; ++u1) gs += cv[u1 * 32 + sum - u1] * row[-u1];
+              slot = wrap_out(slot + 1);
+            }
           }
           ls += T.e_mmI[t2r][sq1][sp] * gs;
         }
@@ -436,7 +452,7 @@ struct BiTile {
             const real *p = tile + (dp - u2 - 1 - 5) * cols + t + 31 - u2;  // inner cell ends at j' - u2; u1 = 1
             const int n1 = smax - u2;
             for (int u1 = 1; u1 <= n1; ++u1) {
-              a += cv[u1 * 32 + u2] * *p;
+              a += cv[u2 * 32 + u1] * *p;  // conv is symmetric: contiguous walk through constant memory
               p -= cols;
             }
             mr[u2] += bseO * a;
