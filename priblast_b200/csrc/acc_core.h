@@ -71,14 +71,18 @@ static __constant__ double g_conv_d[32 * 32];
 static __constant__ float g_conv_f[32 * 32];
 static __constant__ double g_bulge_d[32];
 static __constant__ float g_bulge_f[32];
+static __constant__ double g_cf_d[32];
+static __constant__ float g_cf_f[32];
 template <typename real> struct ConstTab;
 template <> struct ConstTab<double> {
   static __device__ __forceinline__ const double *conv() { return g_conv_d; }
   static __device__ __forceinline__ const double *bulge() { return g_bulge_d; }
+  static __device__ __forceinline__ const double *cf() { return g_cf_d; }
 };
 template <> struct ConstTab<float> {
   static __device__ __forceinline__ const float *conv() { return g_conv_f; }
   static __device__ __forceinline__ const float *bulge() { return g_bulge_f; }
+  static __device__ __forceinline__ const float *cf() { return g_cf_f; }
 };
 #endif
 
@@ -90,7 +94,9 @@ struct Core {
 struct SmallTables {
   real e_hairpin[kMaxSpan + 8];  // [loop size], incl. the lxc37 extrapolation of raccess.cpp:823
   real e_bulge[32];              // [u]
-  real conv[32][32];             // generic interior loop: exp(internal[u1+u2] + ninio[|u1-u2|]), else 0
+  real conv[32][32];             // generic interior loop: cf[u1+u2] * cg[min(|u1-u2|, 6)], else 0
+  real cf[32];                   // exp(internal[sum]) (x kappa^sum), 0 below 4
+  real cg[8];                    // exp(ninio[k]) for k = 0..6 (ninio saturates at 6: energy_par.hpp:173-174)
   real e_mmH[7][5][5];
   real e_mmI[7][5][5];
   real e_stack[7][7];
@@ -147,6 +153,19 @@ static PRIB_HD const real *conv_tab(const SmallTables &T) {
 #else
   return &T.conv[0][0];
 #endif
+}
+static PRIB_HD const real *cf_tab(const SmallTables &T) {
+#if defined(__CUDA_ARCH__)
+  return ConstTab<real>::cf();
+#else
+  return T.cf;
+#endif
+}
+// ninio step of a generic loop, compile-time after unrolling
+static PRIB_HD int gidx(int u1, int sum) {
+  const int k = 2 * u1 - sum;
+  const int a = k < 0 ? -k : k;
+  return a > 6 ? 6 : a;
 }
 static PRIB_HD const real *bulge_tab(const SmallTables &T) {
 #if defined(__CUDA_ARCH__)
@@ -244,7 +263,10 @@ static PRIB_HD void inside_cell(const Ctx &c, long long g, int d) {
       real gs = 0;  // generic interior loops :808-812 as a fixed stencil over A_STEMI
       for (int sum = 4; sum <= smax; ++sum) {
         const real *row = c.arr[A_STEMI] + (long long)(d - sum) * c.NC + g;
-        for (int u1 = 1; u1 < sum; ++u1) gs += T.conv[u1][sum - u1] * row[u1];
+        real rs = 0;
+        for (int u1 = 1; u1 < sum; ++u1)
+          if (!(sum == 4 && u1 == 2)) rs += T.cg[gidx(u1, sum)] * row[u1];
+        gs += T.cf[sum] * rs;
       }
       acc += T.e_mmI[te][si1][sj] * gs;
     }
@@ -383,7 +405,10 @@ static PRIB_HD void outside_cell(const Ctx &c, long long g, int d) {
       real gs = 0;
       for (int sum = 4; sum <= smax; ++sum) {
         const real *row = c.arr[B_STEMO] + (long long)(d + sum + 2) * c.NC + g - 1;
-        for (int u1 = 1; u1 < sum; ++u1) gs += T.conv[u1][sum - u1] * row[-u1];
+        real rs = 0;
+        for (int u1 = 1; u1 < sum; ++u1)
+          if (!(sum == 4 && u1 == 2)) rs += T.cg[gidx(u1, sum)] * row[-u1];
+        gs += T.cf[sum] * rs;
       }
       ls += T.e_mmI[t2r][sq1][sp] * gs;
     }

@@ -40,12 +40,13 @@ template <typename real> struct TileMaxThreads { static constexpr int value = si
 // ---------------------------------------------------------------------------------------------
 // grid = resident CTAs (one per SM: the rings take ~all shared memory), blockDim = TC, tiles round-robin.
 // dynamic smem: kTileRows * TC reals + (TC + 16) base codes.
-template <typename real>
-__global__ void __launch_bounds__(TileMaxThreads<real>::value, 1)
+template <typename real, int R>
+__global__ void __launch_bounds__(TileMaxThreads<real>::value / R, 1)
 k_inside_tile(typename Core<real>::Ctx c, int TX, long long ntiles, real *scratch) {
   typedef Tile<real> TL;
+  constexpr int TC = TileMaxThreads<real>::value;  // compile-time row stride
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int TC = blockDim.x, t = threadIdx.x, W = c.W;
+  const int nth = blockDim.x, tq = threadIdx.x, W = c.W;  // nth = TC / R threads, R columns each
   real *base = reinterpret_cast<real *>(smem_raw);
   uint8_t *sS = reinterpret_cast<uint8_t *>(base + (size_t)kTileRows * TC);
   real *scrM1 = scratch + (size_t)blockIdx.x * 2 * (W + 4) * TC;
@@ -58,24 +59,26 @@ k_inside_tile(typename Core<real>::Ctx c, int TX, long long ntiles, real *scratc
     ge.TX = TX;
     ge.H = W + 1;
     __syncthreads();  // previous tile fully consumed
-    for (int r = 0; r < kTileRows; r++) base[(size_t)r * TC + t] = 0;
-    for (int k = t; k < TC + 8; k += TC) sS[k] = (ge.g0 + k < c.NC) ? c.S[ge.g0 + k] : 0;
-    typename TL::ColState cs;
-    TL::col_state(c, ge.g0 + t, cs);
+    for (int k = tq; k < kTileRows * TC; k += nth) base[k] = 0;
+    for (int k = tq; k < TC + 8; k += nth) sS[k] = (ge.g0 + k < c.NC) ? c.S[ge.g0 + k] : 0;
+    typename TL::ColState cs[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) TL::col_state(c, ge.g0 + tq * R + r, cs[r]);
     __syncthreads();
     for (int d = kTurn; d <= W + 1; d++) {
-      TL::inside_span(c, ge, sm, scrM1, scrM2, t, cs, d);
+      TL::template inside_span<R, TC>(c, ge, sm, scrM1, scrM2, tq, cs, d);
       __syncthreads();
     }
   }
 }
 
-template <typename real>
-__global__ void __launch_bounds__(TileMaxThreads<real>::value, 1)
+template <typename real, int R>
+__global__ void __launch_bounds__(TileMaxThreads<real>::value / R, 1)
 k_outside_tile(typename Core<real>::Ctx c, int TX, long long ntiles, real *scratch) {
   typedef Tile<real> TL;
+  constexpr int TC = TileMaxThreads<real>::value;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int TC = blockDim.x, t = threadIdx.x, W = c.W;
+  const int nth = blockDim.x, tq = threadIdx.x, W = c.W;
   real *base = reinterpret_cast<real *>(smem_raw);
   real *scrBif = scratch + (size_t)blockIdx.x * 2 * (W + 4) * TC;
   const typename TL::OutSmem sm = TL::carve_out(base, TC);
@@ -86,13 +89,14 @@ k_outside_tile(typename Core<real>::Ctx c, int TX, long long ntiles, real *scrat
     ge.TX = TX;
     ge.H = W + 1;
     __syncthreads();
-    for (int r = 0; r < kTileRows; r++) base[(size_t)r * TC + t] = 0;
-    typename TL::ColState cs;
-    TL::col_state(c, ge.g0 - ge.H + t, cs);
+    for (int k = tq; k < kTileRows * TC; k += nth) base[k] = 0;
+    typename TL::ColState cs[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) TL::col_state(c, ge.g0 - ge.H + tq * R + r, cs[r]);
     __syncthreads();
     int slot = (W + 1) % kRingOut;
     for (int d = W + 1; d >= kTurn; d--) {
-      TL::outside_span(c, ge, sm, scrBif, t, cs, d, slot);
+      TL::template outside_span<R, TC>(c, ge, sm, scrBif, tq, cs, d, slot);
       slot = slot == 0 ? kRingOut - 1 : slot - 1;
       __syncthreads();
     }
@@ -311,6 +315,7 @@ struct prib_ctx {
   int W = 70, delta = 5;
   bool use_fp32 = true;
   bool biloop_v1 = false;
+  int cols_per_thread = 2;  // register tiling of the stencils (PRIB_COLS=1|2|4)
   cudaStream_t own_stream = nullptr, stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk0 = nullptr, evk1 = nullptr;
   cudaEvent_t evp[PRIB_NUM_PHASES + 1] = {};
@@ -492,11 +497,15 @@ int run_batch(prib_ctx *c, const Batch &b, bool timed) {
   const long long ntiles = (b.NC + TX - 1) / TX;
   const int tgrid = (int)std::min<long long>(ntiles, c->grid_tiles);
   real *scratch = reinterpret_cast<real *>(c->d_tile_scratch);
-  k_inside_tile<real><<<tgrid, e.TC, e.tile_smem, st>>>(k, TX, ntiles, scratch);
+  if (c->cols_per_thread == 4) k_inside_tile<real, 4><<<tgrid, e.TC / 4, e.tile_smem, st>>>(k, TX, ntiles, scratch);
+  else if (c->cols_per_thread == 2) k_inside_tile<real, 2><<<tgrid, e.TC / 2, e.tile_smem, st>>>(k, TX, ntiles, scratch);
+  else k_inside_tile<real, 1><<<tgrid, e.TC, e.tile_smem, st>>>(k, TX, ntiles, scratch);
   if (timed) CU(cudaEventRecord(c->evp[2], st));
   k_outer_scans_warp<real><<<(b.n + kScanWarps - 1) / kScanWarps, 32 * kScanWarps, 0, st>>>(k);
   if (timed) CU(cudaEventRecord(c->evp[3], st));
-  k_outside_tile<real><<<tgrid, e.TC, e.tile_smem, st>>>(k, TX, ntiles, scratch);
+  if (c->cols_per_thread == 4) k_outside_tile<real, 4><<<tgrid, e.TC / 4, e.tile_smem, st>>>(k, TX, ntiles, scratch);
+  else if (c->cols_per_thread == 2) k_outside_tile<real, 2><<<tgrid, e.TC / 2, e.tile_smem, st>>>(k, TX, ntiles, scratch);
+  else k_outside_tile<real, 1><<<tgrid, e.TC, e.tile_smem, st>>>(k, TX, ntiles, scratch);
   if (timed) CU(cudaEventRecord(c->evp[4], st));
   const unsigned bgrid = (unsigned)((b.NC + e.TXb - 1) / e.TXb);
   if (c->biloop_v1) k_biloop_left<real><<<grid, kThreads, 0, st>>>(k);
@@ -532,9 +541,11 @@ int setup_engine(prib_ctx *c, const ScaleSpec &spec, size_t smem_max, std::strin
   if (sizeof(real) == 8) {
     CU(cudaMemcpyToSymbol(g_conv_d, &tab.small.conv[0][0], sizeof(real) * 32 * 32));
     CU(cudaMemcpyToSymbol(g_bulge_d, tab.small.e_bulge, sizeof(real) * 32));
+    CU(cudaMemcpyToSymbol(g_cf_d, tab.small.cf, sizeof(real) * 32));
   } else {
     CU(cudaMemcpyToSymbol(g_conv_f, &tab.small.conv[0][0], sizeof(real) * 32 * 32));
     CU(cudaMemcpyToSymbol(g_bulge_f, tab.small.e_bulge, sizeof(real) * 32));
+    CU(cudaMemcpyToSymbol(g_cf_f, tab.small.cf, sizeof(real) * 32));
   }
   if (c->d_log == nullptr) {
     CU(cudaMalloc(&c->d_log, tab.log_tbl.size() * sizeof(float)));
@@ -543,15 +554,20 @@ int setup_engine(prib_ctx *c, const ScaleSpec &spec, size_t smem_max, std::strin
   // (function attributes are per device, not per context: always opt in to the device maximum so that
   //  contexts with different spans can coexist)
   // the widest CTA whose rings fit the opt-in shared memory of this device
-  int TC = (int)((smem_max - 64) / (kTileRows * sizeof(real) + 1)) / 32 * 32;
-  if (TC > TileMaxThreads<real>::value) TC = TileMaxThreads<real>::value;
-  const char *tce = getenv("PRIB_TILE_COLS");
-  if (tce && atoi(tce) >= c->W + 34 && atoi(tce) <= TC) TC = atoi(tce) / 32 * 32;
-  if (TC < c->W + 34) return fail(PRIB_ECUDA, "shared memory too small for the tile kernels at this span");
+  // tile width is a compile-time constant of the kernels (row strides become immediates); it is sized
+  // for the 227 KB opt-in shared memory of sm_100
+  const int TC = TileMaxThreads<real>::value;
+  if ((size_t)kTileRows * TC * sizeof(real) + TC + 16 > smem_max)
+    return fail(PRIB_ECUDA, "this GPU has less opt-in shared memory than the sm_100a tile kernels need");
+  if (TC < c->W + 34) return fail(PRIB_ECUDA, "tile narrower than the span halo");
   e.TC = TC;
   e.tile_smem = (size_t)kTileRows * TC * sizeof(real) + TC + 16;
-  CU(cudaFuncSetAttribute(k_inside_tile<real>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
-  CU(cudaFuncSetAttribute(k_outside_tile<real>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+  CU(cudaFuncSetAttribute((k_inside_tile<real, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+  CU(cudaFuncSetAttribute((k_outside_tile<real, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+  CU(cudaFuncSetAttribute((k_inside_tile<real, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+  CU(cudaFuncSetAttribute((k_outside_tile<real, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+  CU(cudaFuncSetAttribute((k_inside_tile<real, 4>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+  CU(cudaFuncSetAttribute((k_outside_tile<real, 4>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
   // interior-loop tiles: the widest block (<= 512 threads) whose Alpha_stemI tile + span lists fit
   const int rows = c->W - 5 > 0 ? c->W - 5 : 0;
   int TXb = 512;
@@ -606,6 +622,10 @@ int prib_acc_create(prib_ctx **out, const prib_acc_params *params) {
   c->prm = *params;
   c->W = params->maximal_span;
   c->delta = params->min_accessible_length;
+  if (const char *ce = getenv("PRIB_COLS")) {
+    const int v = atoi(ce);
+    if (v == 1 || v == 2 || v == 4) c->cols_per_thread = v;
+  }
   const char *be = getenv("PRIB_BILOOP");
   c->biloop_v1 = be && be[0] == '1';
   const char *pe = getenv("PRIB_PRECISION");

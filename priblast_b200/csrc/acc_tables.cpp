@@ -57,11 +57,13 @@ bool build_tables(int W, int delta, const ScaleSpec &spec, HostTablesT<real> &ou
     if (d + 1 < kMaxSpan + 8) T.hpB[d + 1] = kpow(d + 2) / cB * std::exp(q);  // indexed by dd = loop size + 1
   }
   for (int u = 0; u < 32; u++) T.e_bulge[u] = u <= 30 ? kpow(u) * std::exp(bulge[u]) : 0.0;
+  for (int k = 0; k < 8; k++) T.cg[k] = std::exp(ninio[k < 6 ? k : 6]);
+  for (int sm = 0; sm < 32; sm++) T.cf[sm] = (sm >= 4 && sm <= 30) ? kpow(sm) * std::exp(internal[sm]) : 0.0;
   // generic interior loops (raccess.cpp:808-812): everything except 1x1, 1x2, 2x1, 2x2 and bulges
   for (int u1 = 1; u1 <= 30; u1++)
     for (int u2 = 1; u1 + u2 <= 30; u2++) {
       if (u1 + u2 < 4 || (u1 == 2 && u2 == 2)) continue;
-      T.conv[u1][u2] = kpow(u1 + u2) * std::exp(internal[u1 + u2] + ninio[std::abs(u1 - u2)]);
+      T.conv[u1][u2] = T.cf[u1 + u2] * T.cg[std::abs(u1 - u2) < 6 ? std::abs(u1 - u2) : 6];
     }
   for (int i = 0; i < 7; i++) {
     for (int j = 0; j < 5; j++)

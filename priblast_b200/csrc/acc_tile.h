@@ -55,6 +55,10 @@ struct Tile {
     cs.zcol = c.seq_off[sq] + cs.L;
   }
 
+  static PRIB_HD real gsel(int k, real g0, real g1, real g2, real g3, real g4, real g5, real g6) {
+    return k == 0 ? g0 : k == 1 ? g1 : k == 2 ? g2 : k == 3 ? g3 : k == 4 ? g4 : k == 5 ? g5 : g6;
+  }
+
   // ---- shared-memory carve-up (same 80 rows for both passes) -----------------------------------
   struct InSmem {
     real *stemI, *stemB, *stem, *se, *mu, *m2;
@@ -84,49 +88,107 @@ struct Tile {
     return s;
   }
 
+  // R consecutive reals from shared memory with one vector load (p aligned to R * sizeof(real))
+  template <int R>
+  static PRIB_HD void load_vec(const real *p, real (&v)[R]) {
+#if defined(__CUDA_ARCH__)
+    if (R == 4 && sizeof(real) == 4) {
+      const float4 q = *reinterpret_cast<const float4 *>(p);
+      v[0] = (real)q.x; v[1] = (real)q.y; v[2 % R] = (real)q.z; v[3 % R] = (real)q.w;
+      return;
+    }
+    if (R == 2 && sizeof(real) == 4) {
+      const float2 q = *reinterpret_cast<const float2 *>(p);
+      v[0] = (real)q.x; v[1 % R] = (real)q.y;
+      return;
+    }
+    if (R == 2 && sizeof(real) == 8) {
+      const double2 q = *reinterpret_cast<const double2 *>(p);
+      v[0] = (real)q.x; v[1 % R] = (real)q.y;
+      return;
+    }
+#endif
+#pragma unroll
+    for (int r = 0; r < R; ++r) v[r] = p[r];
+  }
+
   // ---------------------------------------------------------------------------------------------
-  // inside: cell (i, i + d) of local column t.  scrM1/scrM2: per-CTA global scratch, [(W+2)][TC].
+  // inside: thread tq owns the R consecutive local columns tq*R .. tq*R+R-1 (cells (i, i+d)).
+  // scrM1/scrM2: per-CTA global scratch, [(W+4)][TC].  The generic-loop stencil is evaluated jointly for
+  // the R cells: every source element is loaded once (vector LDS) and used by up to R targets, each
+  // target still adds its terms in ascending u1, so the result is bit-identical for every R.
   // ---------------------------------------------------------------------------------------------
+  // TCC: compile-time tile width (0 = take ge.TC at run time, used by the host emulation): with a constant
+  // row stride every ring / scratch row offset becomes an immediate of the load instruction.
+  template <int R, int TCC = 0>
   static PRIB_HD void inside_span(const Ctx &c, const Geo &ge, const InSmem &sm, real *scrM1, real *scrM2,
-                                  int t, const ColState &cs, int d) {
-    const int TC = ge.TC;
+                                  int tq, const ColState (&cs)[R], int d) {
+    const int TC = TCC > 0 ? TCC : ge.TC, c0 = tq * R;
     const ST &T = *c.T;
-    const real *cv = K::conv_tab(T), *bu = K::bulge_tab(T);
-    const int L = cs.L, i = cs.i, j = i + d;
-    real stem = 0, stemI = 0, stemB = 0, stemD = 0, se = 0, mu = 0, m1 = 0, m2 = 0;
-    const bool live = i >= 0 && j <= L && t + d <= TC - 1;
-    if (live) {
+    const real *bu = K::bulge_tab(T), *cf = K::cf_tab(T);
+    const real g0 = T.cg[0], g1 = T.cg[1], g2 = T.cg[2], g3 = T.cg[3], g4 = T.cg[4], g5 = T.cg[5], g6 = T.cg[6];
+    real stem[R], stemI[R], stemB[R], stemD[R], se[R], mu[R], m1[R], m2[R], acc[R], gs[R];
+    int te[R];
+    bool any = false;
+    const int smax = imin(kMaxLoop, d - 5);  // u1 + u2 <= smax keeps the inner span >= 5
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int t = c0 + r;
+      const int L = cs[r].L, i = cs[r].i, j = i + d;
+      stem[r] = stemI[r] = stemB[r] = stemD[r] = se[r] = mu[r] = m1[r] = m2[r] = acc[r] = gs[r] = 0;
+      te[r] = 0;
+      const bool live = i >= 0 && j <= L && t + d <= TC - 1;
+      if (!live) continue;
       const uint8_t *s = sm.S + t;
       const int si = s[0], si1 = s[1], sj = s[d], sj1 = s[d + 1];
       const int tp = T.bp[si1][sj];
       if (tp) {
         const int t2 = T.bp[s[2]][s[d - 1]];
-        stem = T.k2 * (sm.se[((d - 2) & (kRingSE - 1)) * TC + t + 1] +
-                       sm.stem[((d - 2) & (kRingStem - 1)) * TC + t + 1] * T.e_stack[tp][T.rt[t2]]);
+        stem[r] = T.k2 * (sm.se[((d - 2) & (kRingSE - 1)) * TC + t + 1] +
+                          sm.stem[((d - 2) & (kRingStem - 1)) * TC + t + 1] * T.e_stack[tp][T.rt[t2]]);
       }
       real mb = 0;
-      for (int m = 5; m <= d - 5; ++m) mb += scrM1[m * TC + t] * scrM2[(d - m) * TC + t + m];
+      {
+        const real *pa = scrM1 + 5 * TC + t, *pb = scrM2 + (d - 5) * TC + t + 5;
+        int m = 5;
+        for (; m + 3 <= d - 5; m += 4) {  // same order of additions as the plain loop
+          mb += pa[0] * pb[0];
+          mb += pa[TC] * pb[-(TC - 1)];
+          mb += pa[2 * TC] * pb[-2 * (TC - 1)];
+          mb += pa[3 * TC] * pb[-3 * (TC - 1)];
+          pa += 4 * TC;
+          pb -= 4 * (TC - 1);
+        }
+        for (; m <= d - 5; ++m) {
+          mb += pa[0] * pb[0];
+          pa += TC;
+          pb -= TC - 1;
+        }
+      }
       mb *= T.inv_cA;
-      stemD = tp ? stem * K::e_dangle(T, tp, i > 0, si, j < L, sj1) : 0;
-      m2 = stemD * T.e_mlintern + sm.m2[((d - 1) & 1) * TC + t] * T.e_mlbase;
-      m1 = m2 + mb;
-      mu = sm.mu[((d - 1) & 1) * TC + t + 1] * T.e_mlbase + mb;
-
-      const int te = (j != L) ? T.bp[si][sj1] : 0;
-      if (te) {
-        real acc = T.e_hairpin[d] * (d != 3 ? T.e_mmH[te][si1][sj] : T.tau[te]);
-        const int smax = imin(kMaxLoop, d - 5);
+      stemD[r] = tp ? stem[r] * K::e_dangle(T, tp, i > 0, si, j < L, sj1) : 0;
+      m2[r] = stemD[r] * T.e_mlintern + sm.m2[((d - 1) & 1) * TC + t] * T.e_mlbase;
+      m1[r] = m2[r] + mb;
+      mu[r] = sm.mu[((d - 1) & 1) * TC + t + 1] * T.e_mlbase + mb;
+      if (tp) {
+        stemI[r] = stem[r] * T.e_mmI[T.rt[tp]][sj1][si];
+        stemB[r] = stem[r] * T.tau[tp];
+      }
+      te[r] = (j != L) ? T.bp[si][sj1] : 0;
+      if (te[r]) {
+        any = true;
+        real a = T.e_hairpin[d] * (d != 3 ? T.e_mmH[te[r]][si1][sj] : T.tau[te[r]]);
         const real *st1 = sm.stem + ((d - 1) & (kRingStem - 1)) * TC + t;
         const real *st2 = sm.stem + ((d - 2) & (kRingStem - 1)) * TC + t;
         const real *st3 = sm.stem + ((d - 3) & (kRingStem - 1)) * TC + t;
         const real *st4 = sm.stem + ((d - 4) & (kRingStem - 1)) * TC + t;
         if (smax >= 1) {
-          acc += bu[1] * (st1[1] * T.e_stack[te][T.rt[T.bp[s[2]][sj]]] +
-                                 st1[0] * T.e_stack[te][T.rt[T.bp[si1][s[d - 1]]]]);
+          a += bu[1] * (st1[1] * T.e_stack[te[r]][T.rt[T.bp[s[2]][sj]]] +
+                        st1[0] * T.e_stack[te[r]][T.rt[T.bp[si1][s[d - 1]]]]);
         }
         if (smax >= 2) {
           const int t2 = T.rt[T.bp[s[2]][s[d - 1]]];
-          acc += st2[1] * c.e_int11[idx11(te, t2, si1, sj)];
+          a += st2[1] * c.e_int11[idx11(te[r], t2, si1, sj)];
           real bs = 0;
 #pragma unroll
           for (int u = 2; u <= kMaxLoop; ++u) {
@@ -135,82 +197,119 @@ struct Tile {
               bs += bu[u] * (row[u] + row[0]);
             }
           }
-          acc += T.tau[te] * bs;
+          a += T.tau[te[r]] * bs;
         }
         if (smax >= 3) {
           const int ta = T.rt[T.bp[s[2]][s[d - 2]]];
-          acc += st3[1] * c.e_int21[idx21(te, ta, si1, s[d - 1], sj)];
+          a += st3[1] * c.e_int21[idx21(te[r], ta, si1, s[d - 1], sj)];
           const int tb = T.rt[T.bp[s[3]][s[d - 1]]];
-          acc += st3[2] * c.e_int21[idx21(tb, te, sj, si1, s[2])];
+          a += st3[2] * c.e_int21[idx21(tb, te[r], sj, si1, s[2])];
         }
         if (smax >= 4) {
           const int tc = T.rt[T.bp[s[3]][s[d - 2]]];
-          acc += st4[2] * c.e_int22[idx22(te, tc, si1, s[2], s[d - 1], sj)];
-          // fully unrolled: every coefficient is a compile-time offset into constant memory, so a
-          // stencil term is exactly one LDS and one FMA
-          real gs = 0;
-#pragma unroll
-          for (int sum = 4; sum <= kMaxLoop; ++sum) {
-            if (sum <= smax) {
-              const real *row = sm.stemI + ((d - sum) & (kRingIn - 1)) * TC + t;
-#pragma unroll
-              for (int u1 = 1; u1 < sum; ++u1) gs += cv[u1 * 32 + sum - u1] * row[u1];
-            }
-          }
-          acc += T.e_mmI[te][si1][sj] * gs;
+          a += st4[2] * c.e_int22[idx22(te[r], tc, si1, s[2], s[d - 1], sj)];
         }
-        const int tt = T.rt[te];
-        acc += mu * T.e_mlclose * T.e_d3[tt][si1] * T.e_d5[tt][sj];
-        se = acc;
-      }
-      if (tp) {
-        stemI = stem * T.e_mmI[T.rt[tp]][sj1][si];
-        stemB = stem * T.tau[tp];
+        acc[r] = a;
       }
     }
-    // every thread refreshes its ring slots every span (zeros where the cell does not exist)
-    sm.stemI[(d & (kRingIn - 1)) * TC + t] = stemI;
-    sm.stemB[(d & (kRingIn - 1)) * TC + t] = stemB;
-    sm.stem[(d & (kRingStem - 1)) * TC + t] = stem;
-    sm.se[(d & (kRingSE - 1)) * TC + t] = se;
-    sm.mu[(d & 1) * TC + t] = mu;
-    sm.m2[(d & 1) * TC + t] = m2;
-    scrM1[d * TC + t] = m1;
-    scrM2[d * TC + t] = m2;
-    // persistent outputs: owned columns only
-    if (t < ge.TX && i >= 0 && j <= L) {
-      const long long g = ge.g0 + t;
-      c.at(A_STEM, d, g) = stem;
-      c.at(A_STEMI, d, g) = stemI;
-      c.at(A_STEMB, d, g) = stemB;
-      c.at(A_STEMD, d, g) = stemD;
-      c.at(A_STEMDE, d, g + d) = stemD;
-      c.at(A_MULTI, d, g) = mu;
-      c.at(A_MULTI1, d, g) = m1;
-      c.at(A_MULTI2, d, g) = m2;
-      if (!(K::in_safe_range(stem) && K::in_safe_range(se) && K::in_safe_range(mu) && K::in_safe_range(m1) &&
-            K::in_safe_range(m2)))
-        c.flags[cs.sq] = 1;
+    // generic interior loops: joint stencil over A_STEMI, fully unrolled.  Local column c0 + x of row
+    // d - sum is source u1 = x - r of target r; weights depend on |u1 - u2| only (7 register values)
+    // times one factor per loop size, so a term is one FMA and 1/R of a vector LDS.
+    if (any && smax >= 4) {
+#pragma unroll
+      for (int sum = 4; sum <= kMaxLoop; ++sum) {
+        if (sum <= smax) {
+          const real *row = sm.stemI + ((d - sum) & (kRingIn - 1)) * TC + c0;
+          real rs[R];
+#pragma unroll
+          for (int r = 0; r < R; ++r) rs[r] = 0;
+#pragma unroll
+          for (int xb = 0; xb <= sum + R - 2; xb += R) {
+            real v[R];
+            load_vec<R>(row + xb, v);
+#pragma unroll
+            for (int k = 0; k < R; ++k) {
+              const int x = xb + k;
+#pragma unroll
+              for (int r = 0; r < R; ++r) {
+                const int u1 = x - r;
+                if (u1 >= 1 && u1 <= sum - 1 && !(sum == 4 && u1 == 2))
+                  rs[r] += gsel(K::gidx(u1, sum), g0, g1, g2, g3, g4, g5, g6) * v[k];
+              }
+            }
+          }
+#pragma unroll
+          for (int r = 0; r < R; ++r) gs[r] += cf[sum] * rs[r];
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int t = c0 + r;
+      const int L = cs[r].L, i = cs[r].i, j = i + d;
+      if (te[r]) {
+        const uint8_t *s = sm.S + t;
+        const int si1 = s[1], sj = s[d];
+        real a = acc[r];
+        if (smax >= 4) a += T.e_mmI[te[r]][si1][sj] * gs[r];
+        const int tt = T.rt[te[r]];
+        a += mu[r] * T.e_mlclose * T.e_d3[tt][si1] * T.e_d5[tt][sj];
+        se[r] = a;
+      }
+      // every column refreshes its ring slots every span (zeros where the cell does not exist)
+      sm.stemI[(d & (kRingIn - 1)) * TC + t] = stemI[r];
+      sm.stemB[(d & (kRingIn - 1)) * TC + t] = stemB[r];
+      sm.stem[(d & (kRingStem - 1)) * TC + t] = stem[r];
+      sm.se[(d & (kRingSE - 1)) * TC + t] = se[r];
+      sm.mu[(d & 1) * TC + t] = mu[r];
+      sm.m2[(d & 1) * TC + t] = m2[r];
+      scrM1[d * TC + t] = m1[r];
+      scrM2[d * TC + t] = m2[r];
+      // persistent outputs: owned columns only
+      if (t < ge.TX && i >= 0 && j <= L) {
+        const long long g = ge.g0 + t;
+        c.at(A_STEM, d, g) = stem[r];
+        c.at(A_STEMI, d, g) = stemI[r];
+        c.at(A_STEMB, d, g) = stemB[r];
+        c.at(A_STEMD, d, g) = stemD[r];
+        c.at(A_STEMDE, d, g + d) = stemD[r];
+        c.at(A_MULTI, d, g) = mu[r];
+        c.at(A_MULTI1, d, g) = m1[r];
+        c.at(A_MULTI2, d, g) = m2[r];
+        if (!(K::in_safe_range(stem[r]) && K::in_safe_range(se[r]) && K::in_safe_range(mu[r]) &&
+              K::in_safe_range(m1[r]) && K::in_safe_range(m2[r])))
+          c.flags[cs[r].sq] = 1;
+      }
     }
   }
 
   // ---------------------------------------------------------------------------------------------
-  // outside: cell (p, p + d) of local column t; global column g = g0 - H + t.
+  // outside: thread tq owns local columns tq*R .. tq*R+R-1; cell (p, p + d); global column g0 - H + t.
   // scrBif: per-CTA global scratch for Beta_multibif, [(W+4)][TC].
   // ---------------------------------------------------------------------------------------------
   static PRIB_HD int wrap_out(int r) { return r >= kRingOut ? r - kRingOut : r; }
 
-  static PRIB_HD void outside_span(const Ctx &c, const Geo &ge, const OutSmem &sm, real *scrBif, int t,
-                                   const ColState &cs, int d, int slot_d /* = d % kRingOut */) {
-    const int TC = ge.TC, W = c.W;
+  template <int R, int TCC = 0>
+  static PRIB_HD void outside_span(const Ctx &c, const Geo &ge, const OutSmem &sm, real *scrBif, int tq,
+                                   const ColState (&cs)[R], int d, int slot_d /* = d % kRingOut */) {
+    const int TC = TCC > 0 ? TCC : ge.TC, W = c.W, c0 = tq * R;
     const ST &T = *c.T;
-    const real *cv = K::conv_tab(T), *bu = K::bulge_tab(T);
-    const long long g = ge.g0 - ge.H + t;
-    const int L = cs.L, p = cs.i, q = p + d;
-    real bstem = 0, bstemO = 0, bstemB = 0, bmulti = 0, bmulti2 = 0, bmbif = 0;
-    // a halo cell is exact iff its end reaches the owned region (all its super-intervals are in the tile)
-    const bool live = p >= 0 && q <= L && t + d >= ge.H;
-    if (live) {
+    const real *bu = K::bulge_tab(T), *cf = K::cf_tab(T);
+    const real g0 = T.cg[0], g1 = T.cg[1], g2 = T.cg[2], g3 = T.cg[3], g4 = T.cg[4], g5 = T.cg[5], g6 = T.cg[6];
+    real bstem[R], bstemO[R], bstemB[R], bmulti[R], bmulti2[R], bmbif[R], base[R], ls[R], gs[R], dang[R];
+    int t2v[R];
+    bool any = false;
+    const int smax = imin(kMaxLoop, W - 1 - d);  // source row d + sum + 2 <= W + 1
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int t = c0 + r;
+      const long long g = ge.g0 - ge.H + t;
+      const int L = cs[r].L, p = cs[r].i, q = p + d;
+      bstem[r] = bstemO[r] = bstemB[r] = bmulti[r] = bmulti2[r] = bmbif[r] = base[r] = ls[r] = gs[r] = dang[r] = 0;
+      t2v[r] = 0;
+      // a halo cell is exact iff its end reaches the owned region (all its super-intervals are in the tile)
+      const bool live = p >= 0 && q <= L && t + d >= ge.H;
+      if (!live) continue;
       const uint8_t *s = c.S + g;  // the right end q = p + d can lie beyond the tile: bases come from global
       const int sp = s[0], sp1 = s[1], sq_ = s[d], sq1 = s[d + 1];
       const bool inner = (p != 0 && q != L);
@@ -219,26 +318,43 @@ struct Tile {
       const real bse = (inner && d + 2 <= W + 1) ? b2[-1] : 0;  // Beta_stemend(p,q), :277-279
       if (inner) {
         const int tt = T.rt[te];
-        bmulti = (d + 1 <= W + 1 ? sm.mu[((d + 1) & 1) * TC + t - 1] * T.e_mlbase : (real)0) +
-                 T.k2 * bse * T.e_mlclose * T.e_d3[tt][sp1] * T.e_d5[tt][sq_];
+        bmulti[r] = (d + 1 <= W + 1 ? sm.mu[((d + 1) & 1) * TC + t - 1] * T.e_mlbase : (real)0) +
+                    T.k2 * bse * T.e_mlclose * T.e_d3[tt][sp1] * T.e_d5[tt][sq_];
         real bm1 = 0;
         const int m1max = imin(L - q, W - d);
-        for (int m = 5; m <= m1max; ++m) bm1 += scrBif[(d + m) * TC + t] * c.ld(A_MULTI2, m, g + d);
+        {
+          const real *pa = scrBif + (d + 5) * TC + t;
+          const real *pb = c.arr[A_MULTI2] + 5 * c.NC + g + d;
+          for (int m = 5; m <= m1max; ++m) {
+            bm1 += pa[0] * pb[0];
+            pa += TC;
+            pb += c.NC;
+          }
+        }
         bm1 *= T.inv_cA;
         real ks = 0;
         const int m2max = imin(p, W - d);
-        for (int m = 5; m <= m2max; ++m) ks += scrBif[(d + m) * TC + t - m] * c.ld(A_MULTI1, m, g - m);
-        bmulti2 = bm1 + sm.m2[((d + 1) & 1) * TC + t] * T.e_mlbase + ks * T.inv_cA;
-        bmbif = bm1 + bmulti;
+        {
+          const real *pa = scrBif + (d + 5) * TC + t - 5;
+          const real *pb = c.arr[A_MULTI1] + 5 * c.NC + g - 5;
+          for (int m = 5; m <= m2max; ++m) {
+            ks += pa[0] * pb[0];
+            pa += TC - 1;
+            pb += c.NC - 1;
+          }
+        }
+        bmulti2[r] = bm1 + sm.m2[((d + 1) & 1) * TC + t] * T.e_mlbase + ks * T.inv_cA;
+        bmbif[r] = bm1 + bmulti[r];
       }
       const int t2 = T.bp[sp1][sq_];
+      t2v[r] = t2;
       if (t2) {
+        any = true;
         const int t2r = T.rt[t2];
-        const real dang = K::e_dangle(T, t2, p > 0, sp, q < L, sq1);
-        const real base = (real)exp(c.lao[g] + c.lbo[g + d] - c.lao[cs.zcol]) * dang * T.sB[d];
-        real ls = 0;
-        const int smax = imin(kMaxLoop, W - 1 - d);
-        if (smax >= 0) ls += bse * T.e_stack[te][t2r];
+        dang[r] = K::e_dangle(T, t2, p > 0, sp, q < L, sq1);
+        base[r] = (real)exp(c.lao[g] + c.lbo[g + d] - c.lao[cs[r].zcol]) * dang[r] * T.sB[d];
+        real l = 0;
+        if (smax >= 0) l += bse * T.e_stack[te][t2r];
         const real *b3 = sm.stem + ((d + 3) & (kRingStem - 1)) * TC + t;
         const real *b4 = sm.stem + ((d + 4) & (kRingStem - 1)) * TC + t;
         const real *b5 = sm.stem + ((d + 5) & (kRingStem - 1)) * TC + t;
@@ -246,11 +362,11 @@ struct Tile {
         if (smax >= 1) {
           const int ta = T.bp[s[-1]][sq1];
           const int tb = T.bp[sp][s[d + 2]];
-          ls += bu[1] * (b3[-2] * T.e_stack[ta][t2r] + b3[-1] * T.e_stack[tb][t2r]);
+          l += bu[1] * (b3[-2] * T.e_stack[ta][t2r] + b3[-1] * T.e_stack[tb][t2r]);
         }
         if (smax >= 2) {
           const int to = T.bp[s[-1]][s[d + 2]];
-          ls += b4[-2] * c.e_int11[idx11(to, t2r, sp, sq1)];
+          l += b4[-2] * c.e_int11[idx11(to, t2r, sp, sq1)];
           real bs = 0;
           int slot = wrap_out(slot_d + 4);
 #pragma unroll
@@ -261,50 +377,90 @@ struct Tile {
               slot = wrap_out(slot + 1);
             }
           }
-          ls += T.tau[t2r] * bs;
+          l += T.tau[t2r] * bs;
         }
         if (smax >= 3) {
           const int ta = T.bp[s[-1]][s[d + 3]];
-          ls += b5[-2] * c.e_int21[idx21(ta, t2r, sp, sq1, s[d + 2])];
+          l += b5[-2] * c.e_int21[idx21(ta, t2r, sp, sq1, s[d + 2])];
           const int tb = T.bp[s[-2]][s[d + 2]];
-          ls += b5[-3] * c.e_int21[idx21(t2r, tb, sq1, s[-1], sp)];
+          l += b5[-3] * c.e_int21[idx21(t2r, tb, sq1, s[-1], sp)];
         }
         if (smax >= 4) {
           const int tc = T.bp[s[-2]][s[d + 3]];
-          ls += b6[-3] * c.e_int22[idx22(tc, t2r, s[-1], sp, sq1, s[d + 2])];
-          real gs = 0;
-          int slot = wrap_out(slot_d + 6);
-#pragma unroll
-          for (int sum = 4; sum <= kMaxLoop; ++sum) {
-            if (sum <= smax) {
-              const real *row = sm.stemO + slot * TC + t - 1;
-#pragma unroll
-              for (int u1 = 1; u1 < sum; ++u1) gs += cv[u1 * 32 + sum - u1] * row[-u1];
-              slot = wrap_out(slot + 1);
-            }
-          }
-          ls += T.e_mmI[t2r][sq1][sp] * gs;
+          l += b6[-3] * c.e_int22[idx22(tc, t2r, s[-1], sp, sq1, s[d + 2])];
         }
-        bstem = base + T.k2 * ls + bmulti2 * T.e_mlintern * dang;
-        bstemO = bstem * T.e_mmI[t2][s[2]][s[d - 1]];
-        bstemB = bstem * T.tau[t2];
+        ls[r] = l;
       }
     }
-    sm.stemO[slot_d * TC + t] = bstemO;
-    sm.stemB[slot_d * TC + t] = bstemB;
-    sm.stem[(d & (kRingStem - 1)) * TC + t] = bstem;
-    sm.mu[(d & 1) * TC + t] = bmulti;
-    sm.m2[(d & 1) * TC + t] = bmulti2;
-    scrBif[d * TC + t] = bmbif;
-    if (t >= ge.H && p >= 0 && q <= L) {
-      c.at(B_STEM, d, g) = bstem;
-      c.at(B_STEMO, d, g) = bstemO;
-      c.at(B_STEMB, d, g) = bstemB;
-      c.at(B_MULTI, d, g) = bmulti;
-      c.at(B_MULTI2, d, g) = bmulti2;
-      if (!(K::in_safe_range(bstem) && K::in_safe_range(bmulti) && K::in_safe_range(bmulti2) &&
-            K::in_safe_range(bmbif)))
-        c.flags[cs.sq] = 1;
+    // generic loops: joint stencil over B_STEMO.  Target r (column c0 + r) takes source u1 from local
+    // column c0 + r - 1 - u1; the elements are read as aligned vectors going left from c0 + R - 1.
+    if (any && smax >= 4) {
+      int slot = wrap_out(slot_d + 6);
+#pragma unroll
+      for (int sum = 4; sum <= kMaxLoop; ++sum) {
+        if (sum <= smax) {
+          const real *row = sm.stemO + slot * TC + c0;
+          real rs[R];
+#pragma unroll
+          for (int r = 0; r < R; ++r) rs[r] = 0;
+          // aligned blocks [c0 - yb - R, c0 - yb - 1], yb = 0, R, ...; for ascending u1 per target the
+          // blocks are visited right to left and their elements right to left
+#pragma unroll
+          for (int yb = -R; yb <= sum - 1; yb += R) {
+            real v[R];
+            if (c0 - yb - R >= 0) {
+              load_vec<R>(row - yb - R, v);
+            } else {  // left of the tile: only columns that are not live could ask for it
+#pragma unroll
+              for (int k = 0; k < R; ++k) v[k] = 0;
+            }
+#pragma unroll
+            for (int k = R - 1; k >= 0; --k) {
+              const int e = -yb - R + k;  // column offset from c0
+#pragma unroll
+              for (int r = 0; r < R; ++r) {
+                const int u1 = r - 1 - e;
+                if (u1 >= 1 && u1 <= sum - 1 && !(sum == 4 && u1 == 2))
+                  rs[r] += gsel(K::gidx(u1, sum), g0, g1, g2, g3, g4, g5, g6) * v[k];
+              }
+            }
+          }
+#pragma unroll
+          for (int r = 0; r < R; ++r) gs[r] += cf[sum] * rs[r];
+          slot = wrap_out(slot + 1);
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int t = c0 + r;
+      const long long g = ge.g0 - ge.H + t;
+      const int L = cs[r].L, p = cs[r].i, q = p + d;
+      if (t2v[r]) {
+        const uint8_t *s = c.S + g;
+        const int t2 = t2v[r], t2r = T.rt[t2];
+        real l = ls[r];
+        if (smax >= 4) l += T.e_mmI[t2r][s[d + 1]][s[0]] * gs[r];
+        bstem[r] = base[r] + T.k2 * l + bmulti2[r] * T.e_mlintern * dang[r];
+        bstemO[r] = bstem[r] * T.e_mmI[t2][s[2]][s[d - 1]];
+        bstemB[r] = bstem[r] * T.tau[t2];
+      }
+      sm.stemO[slot_d * TC + t] = bstemO[r];
+      sm.stemB[slot_d * TC + t] = bstemB[r];
+      sm.stem[(d & (kRingStem - 1)) * TC + t] = bstem[r];
+      sm.mu[(d & 1) * TC + t] = bmulti[r];
+      sm.m2[(d & 1) * TC + t] = bmulti2[r];
+      scrBif[d * TC + t] = bmbif[r];
+      if (t >= ge.H && p >= 0 && q <= L) {
+        c.at(B_STEM, d, g) = bstem[r];
+        c.at(B_STEMO, d, g) = bstemO[r];
+        c.at(B_STEMB, d, g) = bstemB[r];
+        c.at(B_MULTI, d, g) = bmulti[r];
+        c.at(B_MULTI2, d, g) = bmulti2[r];
+        if (!(K::in_safe_range(bstem[r]) && K::in_safe_range(bmulti[r]) && K::in_safe_range(bmulti2[r]) &&
+              K::in_safe_range(bmbif[r])))
+          c.flags[cs[r].sq] = 1;
+      }
     }
   }
 };

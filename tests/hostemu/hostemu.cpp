@@ -86,7 +86,7 @@ void run_dp(EmuT<real> &e) {
 
 // Emulation of the tile-persistent kernels (acc_tile.h): one "CTA" per tile, TC "threads", a barrier
 // (= end of the inner loop over t) after every span.
-template <typename real>
+template <typename real, int R>
 void run_dp_tiled(EmuT<real> &e, int TC) {
   typedef Tile<real> TL;
   typedef Core<real> K;
@@ -103,7 +103,11 @@ void run_dp_tiled(EmuT<real> &e, int TC) {
     for (int t = 0; t < TC; t++) TL::col_state(c, ge.g0 + t, cs[t]);
     typename TL::InSmem sm = TL::carve_in(smem.data(), TC, sS.data());
     for (int d = kTurn; d <= W + 1; d++)
-      for (int t = 0; t < TC; t++) TL::inside_span(c, ge, sm, scr.data(), scr.data() + (size_t)(W + 4) * TC, t, cs[t], d);
+      for (int tq = 0; tq < TC / R; tq++) {
+        typename TL::ColState csr[R];
+        for (int r = 0; r < R; r++) csr[r] = cs[tq * R + r];
+        TL::template inside_span<R>(c, ge, sm, scr.data(), scr.data() + (size_t)(W + 4) * TC, tq, csr, d);
+      }
   }
   double ring[256];
   for (int k = 0; k < c.nseq; k++) {
@@ -116,7 +120,11 @@ void run_dp_tiled(EmuT<real> &e, int TC) {
     for (int t = 0; t < TC; t++) TL::col_state(c, ge.g0 - H + t, cs[t]);
     typename TL::OutSmem sm = TL::carve_out(smem.data(), TC);
     for (int d = W + 1; d >= kTurn; d--)
-      for (int t = 0; t < TC; t++) TL::outside_span(c, ge, sm, scr.data(), t, cs[t], d, d % kRingOut);
+      for (int tq = 0; tq < TC / R; tq++) {
+        typename TL::ColState csr[R];
+        for (int r = 0; r < R; r++) csr[r] = cs[tq * R + r];
+        TL::template outside_span<R>(c, ge, sm, scr.data(), tq, csr, d, d % kRingOut);
+      }
   }
 }
 
@@ -180,22 +188,30 @@ int hostemu_run_batch(int n, const char *const *seqs, const int32_t *lens, int W
 namespace {
 template <typename real>
 int run_tiled(int n, const char *const *seqs, const int32_t *lens, int W, int delta, float *out,
-              const int64_t *acc_off, const int64_t *cond_off, int TC, const ScaleSpec &spec, int32_t *flags_out) {
+              const int64_t *acc_off, const int64_t *cond_off, int TC, const ScaleSpec &spec, int32_t *flags_out,
+              int R = 1) {
   EmuT<real> e;
   for (int k = 0; k < n; k++) {
     std::memset(out + acc_off[k], 0, sizeof(float) * (size_t)lens[k]);
     std::memset(out + cond_off[k], 0, sizeof(float) * (size_t)lens[k]);
   }
   if (!setup(e, n, seqs, lens, W, delta, out, acc_off, cond_off, spec)) return -1;
-  if (TC <= W + 2) return -2;
-  run_dp_tiled(e, TC);
+  if (TC <= W + 2 || TC % 4 != 0) return -2;
+  if (R == 4) run_dp_tiled<real, 4>(e, TC);
+  else if (R == 2) run_dp_tiled<real, 2>(e, TC);
+  else run_dp_tiled<real, 1>(e, TC);
   run_acc(e, TC >= 256 ? 128 : 64);
   if (flags_out) std::memcpy(flags_out, e.flags.data(), sizeof(int32_t) * (size_t)n);
   return 1;
 }
 }  // namespace
 
+static int g_cols_per_thread = 1;
+
 extern "C" {
+
+// columns per emulated thread (register tiling of the stencils): 1, 2 or 4
+void hostemu_set_cols_per_thread(int R) { g_cols_per_thread = R; }
 
 // FP32 band arithmetic with span scaling; flags_out[k] != 0 marks sequences whose stored values left
 // the safe range (the product re-runs those in FP64).
@@ -206,7 +222,7 @@ int hostemu_run_batch_tiled_f32(int n, const char *const *seqs, const int32_t *l
   spec.klog2 = klog2;
   spec.alog2 = alog2;
   spec.blog2 = blog2;
-  return run_tiled<float>(n, seqs, lens, W, delta, out, acc_off, cond_off, TC, spec, flags_out);
+  return run_tiled<float>(n, seqs, lens, W, delta, out, acc_off, cond_off, TC, spec, flags_out, g_cols_per_thread);
 }
 
 // Same batch through the tile-persistent formulation; TC = emulated CTA width.
@@ -217,7 +233,7 @@ int hostemu_run_batch_tiled(int n, const char *const *seqs, const int32_t *lens,
   spec.klog2 = klog2;
   spec.alog2 = alog2;
   spec.blog2 = blog2;
-  return run_tiled<double>(n, seqs, lens, W, delta, out, acc_off, cond_off, TC, spec, nullptr);
+  return run_tiled<double>(n, seqs, lens, W, delta, out, acc_off, cond_off, TC, spec, nullptr, g_cols_per_thread);
 }
 
 int hostemu_run(const char *seq, int L, int W, int delta, float *acc, float *cond) {
