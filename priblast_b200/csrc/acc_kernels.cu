@@ -183,7 +183,7 @@ __global__ void __launch_bounds__(kThreads) k_biloop_right(typename Core<real>::
 }
 // Interior-loop strand weights, tile version (acc_tile.h BiTile): blockDim = TXb owned columns; dynamic smem =
 // (W-5) x (TXb+32) reals (Alpha_stemI tile) + W x TXb bytes (per-thread lists of closing spans).
-template <typename real, bool LEFT>
+template <typename real, bool LEFT, int ULO, int TXB>
 __global__ void __launch_bounds__(512) k_biloop_tile(typename Core<real>::Ctx c) {
   typedef BiTile<real> BT;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -200,8 +200,24 @@ __global__ void __launch_bounds__(512) k_biloop_tile(typename Core<real>::Ctx c)
     tile[idx] = LEFT ? BT::load_left(c, ge, r, x) : BT::load_right(c, ge, r, x);
   }
   __syncthreads();
-  if (LEFT) BT::left(c, ge, tile, list, threadIdx.x);
-  else BT::right(c, ge, tile, list, threadIdx.x);
+  // TXB > 0: block width (hence the tile row stride) known at compile time
+  if (LEFT) BT::template left<(TXB > 0 ? TXB + 32 : 0), ULO>(c, ge, tile, list, threadIdx.x);
+  else BT::template right<(TXB > 0 ? TXB + 32 : 0), ULO>(c, ge, tile, list, threadIdx.x);
+}
+
+template <typename real, bool LEFT>
+void launch_biloop(const typename Core<real>::Ctx &k, unsigned grid, int TXb, size_t smem, cudaStream_t st) {
+  const bool d5 = k.delta >= 5;
+  if (TXb == 512) {
+    if (d5) k_biloop_tile<real, LEFT, 5, 512><<<grid, TXb, smem, st>>>(k);
+    else k_biloop_tile<real, LEFT, 2, 512><<<grid, TXb, smem, st>>>(k);
+  } else if (TXb == 256) {
+    if (d5) k_biloop_tile<real, LEFT, 5, 256><<<grid, TXb, smem, st>>>(k);
+    else k_biloop_tile<real, LEFT, 2, 256><<<grid, TXb, smem, st>>>(k);
+  } else {
+    if (d5) k_biloop_tile<real, LEFT, 5, 0><<<grid, TXb, smem, st>>>(k);
+    else k_biloop_tile<real, LEFT, 2, 0><<<grid, TXb, smem, st>>>(k);
+  }
 }
 
 template <typename real>
@@ -315,7 +331,7 @@ struct prib_ctx {
   int W = 70, delta = 5;
   bool use_fp32 = true;
   bool biloop_v1 = false;
-  int cols_per_thread = 2;  // register tiling of the stencils (PRIB_COLS=1|2|4)
+  int cols_per_thread = 1;  // register tiling of the stencils (PRIB_COLS=1|2|4); measured: 1 is fastest (latency-bound)
   cudaStream_t own_stream = nullptr, stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk0 = nullptr, evk1 = nullptr;
   cudaEvent_t evp[PRIB_NUM_PHASES + 1] = {};
@@ -509,10 +525,10 @@ int run_batch(prib_ctx *c, const Batch &b, bool timed) {
   if (timed) CU(cudaEventRecord(c->evp[4], st));
   const unsigned bgrid = (unsigned)((b.NC + e.TXb - 1) / e.TXb);
   if (c->biloop_v1) k_biloop_left<real><<<grid, kThreads, 0, st>>>(k);
-  else k_biloop_tile<real, true><<<bgrid, e.TXb, e.bi_smem, st>>>(k);
+  else launch_biloop<real, true>(k, bgrid, e.TXb, e.bi_smem, st);
   if (timed) CU(cudaEventRecord(c->evp[5], st));
   if (c->biloop_v1) k_biloop_right<real><<<grid, kThreads, 0, st>>>(k);
-  else k_biloop_tile<real, false><<<bgrid, e.TXb, e.bi_smem, st>>>(k);
+  else launch_biloop<real, false>(k, bgrid, e.TXb, e.bi_smem, st);
   if (timed) CU(cudaEventRecord(c->evp[6], st));
   k_hairpin_suffix<real><<<grid, kThreads, 0, st>>>(k);
   k_finalize<real><<<grid, kThreads, 0, st>>>(k);
@@ -575,8 +591,12 @@ int setup_engine(prib_ctx *c, const ScaleSpec &spec, size_t smem_max, std::strin
   e.TXb = TXb;
   e.bi_smem = (size_t)rows * (TXb + 32) * sizeof(real) + (size_t)(c->W + 1) * TXb + 64;
   if (e.bi_smem > smem_max) return fail(PRIB_ECUDA, "shared memory too small for the interior-loop tiles");
-  CU(cudaFuncSetAttribute((k_biloop_tile<real, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
-  CU(cudaFuncSetAttribute((k_biloop_tile<real, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+#define PRIB_BI_ATTR(L, U, X) \
+  CU(cudaFuncSetAttribute((k_biloop_tile<real, L, U, X>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max))
+  PRIB_BI_ATTR(true, 5, 512); PRIB_BI_ATTR(true, 2, 512); PRIB_BI_ATTR(false, 5, 512); PRIB_BI_ATTR(false, 2, 512);
+  PRIB_BI_ATTR(true, 5, 256); PRIB_BI_ATTR(true, 2, 256); PRIB_BI_ATTR(false, 5, 256); PRIB_BI_ATTR(false, 2, 256);
+  PRIB_BI_ATTR(true, 5, 0); PRIB_BI_ATTR(true, 2, 0); PRIB_BI_ATTR(false, 5, 0); PRIB_BI_ATTR(false, 2, 0);
+#undef PRIB_BI_ATTR
   return PRIB_OK;
 }
 

@@ -503,7 +503,10 @@ struct BiTile {
     return (col >= 0 && col < c.NC) ? c.ld(A_STEMI, r, col) : (real)0;
   }
 
-  // thread t = left index i (column g0 + t); list: uint8 [W][TXb] scratch in shared memory
+  // thread t = left index i (column g0 + t); list: uint8 [W][TXb] scratch in shared memory.
+  // COLS: compile-time row stride of the tile (0 = ge.cols at run time, host emulation); ULO: smallest strand
+  // length that is accumulated (min(delta, 5): strands shorter than delta are never read).
+  template <int COLS, int ULO>
   static PRIB_HD void left(const Ctx &c, const Geo &ge, const real *tile, uint8_t *list, int t) {
     const long long g = ge.g0 + t;
     if (g >= c.NC) return;
@@ -511,7 +514,7 @@ struct BiTile {
     if (!K::col_info(c, g, ci)) return;
     const ST &T = *c.T;
     const real *cv = K::conv_tab(T), *bu = K::bulge_tab(T);
-    const int L = ci.L, i = ci.i, W = c.W, delta = c.delta, TXb = ge.TXb, cols = ge.cols;
+    const int L = ci.L, i = ci.i, W = c.W, delta = c.delta, TXb = ge.TXb, cols = COLS > 0 ? COLS : ge.cols;
     const uint8_t *s = c.S + g;
     real ml[kMaxLoop + 1];
 #pragma unroll
@@ -538,24 +541,26 @@ struct BiTile {
           if (dp - 5 >= 4) ml[2] += K::loop_weight(c, T, s, g, dp, te, bse, bseO, bseB, 2, 2);
         }
       }
-      // pass B (each lane at its own span): generic interior loops out of the shared-memory tile
+      // pass B (each lane at its own span): generic interior loops out of the shared-memory tile, walked by
+      // loop size: all terms of one size share a tile row, every offset and coefficient is compile-time
       for (int k = 0; k < cnt; ++k) {
         const int dp = list[k * TXb + t];
         const real bseO = c.ld(B_STEMO, dp + 2, g - 1);
         const int smax = imin(kMaxLoop, dp - 5);
+        const real *base = tile + (dp - 5) * cols + t;
+        real a[kMaxLoop];
 #pragma unroll
-        for (int u1 = 2; u1 <= kMaxLoop - 1; ++u1) {
-          if (u1 >= delta && u1 <= smax - 1) {
-            real a = 0;
-            const real *p = tile + (dp - u1 - 1 - 5) * cols + t + u1;  // inner cell (i+u1, j'-u2) at u2 = 1
-            const int n2 = smax - u1;
-            for (int u2 = 1; u2 <= n2; ++u2) {
-              a += cv[u1 * 32 + u2] * *p;
-              p -= cols;
-            }
-            ml[u1] += bseO * a;
+        for (int u1 = 0; u1 < kMaxLoop; ++u1) a[u1] = 0;
+#pragma unroll
+        for (int sum = ULO + 1; sum <= kMaxLoop; ++sum) {
+          if (sum <= smax) {
+            const real *row = base - sum * cols;  // span dp - sum
+#pragma unroll
+            for (int u1 = ULO; u1 < sum; ++u1) a[u1] += cv[u1 * 32 + sum - u1] * row[u1];
           }
         }
+#pragma unroll
+        for (int u1 = ULO; u1 < kMaxLoop; ++u1) ml[u1] += bseO * a[u1];
       }
     }
 #pragma unroll
@@ -564,6 +569,7 @@ struct BiTile {
   }
 
   // thread t = right end j' of the outer cell (column g0 + t)
+  template <int COLS, int ULO>
   static PRIB_HD void right(const Ctx &c, const Geo &ge, const real *tile, uint8_t *list, int t) {
     const long long g2 = ge.g0 + t;
     if (g2 >= c.NC) return;
@@ -571,7 +577,7 @@ struct BiTile {
     if (!K::col_info(c, g2, ci)) return;
     const ST &T = *c.T;
     const real *cv = K::conv_tab(T), *bu = K::bulge_tab(T);
-    const int L = ci.L, jp = ci.i, W = c.W, delta = c.delta, TXb = ge.TXb, cols = ge.cols;
+    const int L = ci.L, jp = ci.i, W = c.W, delta = c.delta, TXb = ge.TXb, cols = COLS > 0 ? COLS : ge.cols;
     real mr[kMaxLoop + 1];
 #pragma unroll
     for (int u = 0; u <= kMaxLoop; ++u) mr[u] = 0;
@@ -601,19 +607,20 @@ struct BiTile {
         const int dp = list[k * TXb + t];
         const real bseO = c.ld(B_STEMO, dp + 2, g2 - dp - 1);
         const int smax = imin(kMaxLoop, dp - 5);
+        const real *base = tile + (dp - 5) * cols + t + 31;
+        real a[kMaxLoop];
 #pragma unroll
-        for (int u2 = 2; u2 <= kMaxLoop - 1; ++u2) {
-          if (u2 >= delta && u2 <= smax - 1) {
-            real a = 0;
-            const real *p = tile + (dp - u2 - 1 - 5) * cols + t + 31 - u2;  // inner cell ends at j' - u2; u1 = 1
-            const int n1 = smax - u2;
-            for (int u1 = 1; u1 <= n1; ++u1) {
-              a += cv[u2 * 32 + u1] * *p;  // conv is symmetric: contiguous walk through constant memory
-              p -= cols;
-            }
-            mr[u2] += bseO * a;
+        for (int u2 = 0; u2 < kMaxLoop; ++u2) a[u2] = 0;
+#pragma unroll
+        for (int sum = ULO + 1; sum <= kMaxLoop; ++sum) {
+          if (sum <= smax) {
+            const real *row = base - sum * cols;  // span dp - sum, end-indexed: the inner cell ends at j' - u2
+#pragma unroll
+            for (int u2 = ULO; u2 < sum; ++u2) a[u2] += cv[u2 * 32 + sum - u2] * row[-u2];
           }
         }
+#pragma unroll
+        for (int u2 = ULO; u2 < kMaxLoop; ++u2) mr[u2] += bseO * a[u2];
       }
     }
 #pragma unroll

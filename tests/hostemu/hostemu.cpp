@@ -145,8 +145,13 @@ void run_biloop_tiled(EmuT<real> &e, int TXb) {
         for (int x = 0; x < ge.cols; x++)
           tile[(size_t)(r - 5) * ge.cols + x] = side == 0 ? BT::load_left(c, ge, r, x) : BT::load_right(c, ge, r, x);
       for (int t = 0; t < TXb; t++) {
-        if (side == 0) BT::left(c, ge, tile.data(), list.data(), t);
-        else BT::right(c, ge, tile.data(), list.data(), t);
+        if (side == 0) {
+          if (c.delta >= 5) BT::template left<0, 5>(c, ge, tile.data(), list.data(), t);
+          else BT::template left<0, 2>(c, ge, tile.data(), list.data(), t);
+        } else {
+          if (c.delta >= 5) BT::template right<0, 5>(c, ge, tile.data(), list.data(), t);
+          else BT::template right<0, 2>(c, ge, tile.data(), list.data(), t);
+        }
       }
     }
 }
