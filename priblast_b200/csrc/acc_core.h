@@ -19,6 +19,7 @@
 // all out-of-range neighbours read as 0 and removes the boundary tests of the reference loops.
 #pragma once
 #include <math.h>
+#include <stddef.h>
 #include <stdint.h>
 
 #if defined(__CUDACC__)
@@ -92,34 +93,39 @@ template <typename real>
 struct Core {
 // Boltzmann factors exp(-E/kT) of the scaled tables of raccess.hpp:105-158 (built on the host).
 struct SmallTables {
-  real e_hairpin[kMaxSpan + 8];  // [loop size], incl. the lxc37 extrapolation of raccess.cpp:823
-  real e_bulge[32];              // [u]
-  real conv[32][32];             // generic interior loop: cf[u1+u2] * cg[min(|u1-u2|, 6)], else 0
-  real cf[32];                   // exp(internal[sum]) (x kappa^sum), 0 below 4
-  real cg[8];                    // exp(ninio[k]) for k = 0..6 (ninio saturates at 6: energy_par.hpp:173-174)
+  // ---- hot part: everything the tile kernels index per cell; the kernels keep a copy of this prefix
+  // (kHotBytes) in shared memory so that a lookup is a 30-cycle LDS instead of a trip through L1/L2 ----
+  real e_hairpin[kMaxSpan + 8];  // [loop size], incl. the lxc37 extrapolation of raccess.cpp:823 (x cA kappa^d)
+  real sB[kMaxSpan + 8];         // cB * kappa^-d
   real e_mmH[7][5][5];
   real e_mmI[7][5][5];
   real e_stack[7][7];
   real e_d5[8][5];
   real e_d3[8][5];               // includes TermAU for types > 2 (raccess.hpp:132-134)
   real tau[8];                   // exp(TermAU) for types > 2, else 1
+  real cg[8];                    // exp(ninio[k]) for k = 0..6 (ninio saturates at 6: energy_par.hpp:173-174)
   real e_mlbase, e_mlintern, e_mlclose;  // e_mlclose = exp(MLclosing + MLintern)
-  // Span scaling (DESIGN.md §2.3): stored Alpha-type values are cA * kappa^d * (true value), stored
+  // Span scaling (DESIGN.md §2.6): stored Alpha-type values are cA * kappa^d * (true value), stored
   // Beta-type values are cB * kappa^-d * (true value / Z).  kappa = cA = cB = 1 in the FP64 build; the
   // FP32 build uses them to centre the dynamic range.  kappa^(u1+u2) is folded into conv / e_bulge /
   // e_int11 / e_int21 / e_int22, kappa into e_mlbase, cA * kappa^d into e_hairpin[d].
   real k2;                       // kappa^2
   real inv_cA;                   // 1 / cA
+  int8_t bp[5][5];
+  int8_t rt[8];
+  int8_t hot_end[7];             // marks the end of the hot prefix
+  // ---- cold part ----
+  real e_bulge[32];              // [u] (device copy in __constant__)
+  real conv[32][32];             // generic interior loop: cf[u1+u2] * cg[min(|u1-u2|, 6)], else 0
+  real cf[32];                   // exp(internal[sum]) (x kappa^sum), 0 below 4
   real kacc;                     // kappa^2 / (cA cB): un-scales Beta_stemend * loop * Alpha_stem products
   real kmul[2];                  // kappa^w / (cA cB) for w = delta, delta + 1 (CalcMultiProbability)
-  real sB[kMaxSpan + 8];         // cB * kappa^-d
   real hpB[kMaxSpan + 8];        // [dd]: kappa^(dd+1) / cB * exp(hairpin length term of loop size dd-1)
   double us[kMaxSpan + 8];       // kappa^-d / cA (outer-array scans run un-scaled in double)
   double kT;
   float log_c_log2;              // fmath LogVar::c_log2
-  int8_t bp[5][5];
-  int8_t rt[8];
 };
+static constexpr int kHotBytes = (int)((offsetof(SmallTables, hot_end) + 15) / 16 * 16);
 
 struct Ctx {
   long long NC;            // padded number of columns of this batch

@@ -33,7 +33,7 @@ constexpr int kThreads = 128;
 constexpr int kScanWarps = 4;
 constexpr int kFp32MaxSpan = 100;
 // widest CTA of the tile kernels per precision (227 KB of rings / 80 rows): bounds the register budget
-template <typename real> struct TileMaxThreads { static constexpr int value = sizeof(real) == 4 ? 704 : 352; };
+template <typename real> struct TileMaxThreads { static constexpr int value = sizeof(real) == 4 ? 704 : 320; };
 
 // ---------------------------------------------------------------------------------------------
 // kernels
@@ -48,7 +48,11 @@ k_inside_tile(typename Core<real>::Ctx c, int TX, long long ntiles, real *scratc
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int nth = blockDim.x, tq = threadIdx.x, W = c.W;  // nth = TC / R threads, R columns each
   real *base = reinterpret_cast<real *>(smem_raw);
-  uint8_t *sS = reinterpret_cast<uint8_t *>(base + (size_t)kTileRows * TC);
+  unsigned char *stab = smem_raw + (size_t)kTileRows * TC * sizeof(real);  // hot tables (16-byte aligned)
+  uint8_t *sS = stab + Core<real>::kHotBytes;
+  for (int k = tq; k < Core<real>::kHotBytes / 4; k += nth)
+    reinterpret_cast<uint32_t *>(stab)[k] = reinterpret_cast<const uint32_t *>(c.T)[k];
+  const typename Core<real>::SmallTables &T = *reinterpret_cast<const typename Core<real>::SmallTables *>(stab);
   real *scrM1 = scratch + (size_t)blockIdx.x * 2 * (W + 4) * TC;
   real *scrM2 = scrM1 + (size_t)(W + 4) * TC;
   const typename TL::InSmem sm = TL::carve_in(base, TC, sS);
@@ -66,7 +70,7 @@ k_inside_tile(typename Core<real>::Ctx c, int TX, long long ntiles, real *scratc
     for (int r = 0; r < R; ++r) TL::col_state(c, ge.g0 + tq * R + r, cs[r]);
     __syncthreads();
     for (int d = kTurn; d <= W + 1; d++) {
-      TL::template inside_span<R, TC>(c, ge, sm, scrM1, scrM2, tq, cs, d);
+      TL::template inside_span<R, TC>(c, T, ge, sm, scrM1, scrM2, tq, cs, d);
       __syncthreads();
     }
   }
@@ -80,6 +84,10 @@ k_outside_tile(typename Core<real>::Ctx c, int TX, long long ntiles, real *scrat
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int nth = blockDim.x, tq = threadIdx.x, W = c.W;
   real *base = reinterpret_cast<real *>(smem_raw);
+  unsigned char *stab = smem_raw + (size_t)kTileRows * TC * sizeof(real);
+  for (int k = tq; k < Core<real>::kHotBytes / 4; k += nth)
+    reinterpret_cast<uint32_t *>(stab)[k] = reinterpret_cast<const uint32_t *>(c.T)[k];
+  const typename Core<real>::SmallTables &T = *reinterpret_cast<const typename Core<real>::SmallTables *>(stab);
   real *scrBif = scratch + (size_t)blockIdx.x * 2 * (W + 4) * TC;
   const typename TL::OutSmem sm = TL::carve_out(base, TC);
   for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -96,7 +104,7 @@ k_outside_tile(typename Core<real>::Ctx c, int TX, long long ntiles, real *scrat
     __syncthreads();
     int slot = (W + 1) % kRingOut;
     for (int d = W + 1; d >= kTurn; d--) {
-      TL::template outside_span<R, TC>(c, ge, sm, scrBif, tq, cs, d, slot);
+      TL::template outside_span<R, TC>(c, T, ge, sm, scrBif, tq, cs, d, slot);
       slot = slot == 0 ? kRingOut - 1 : slot - 1;
       __syncthreads();
     }
@@ -195,14 +203,25 @@ __global__ void __launch_bounds__(512) k_biloop_tile(typename Core<real>::Ctx c)
   real *tile = reinterpret_cast<real *>(smem_raw);
   uint8_t *list = reinterpret_cast<uint8_t *>(tile + (size_t)ge.rows * ge.cols);
   const int total = ge.rows * ge.cols;
+  constexpr int COLS = TXB > 0 ? TXB + 32 : 0;  // TXB > 0: block width (hence the tile row stride) known at compile time
+  typename BT::Strand st;
+  // generic loops out of the Alpha_stemI tile
   for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
     const int r = idx / ge.cols + 5, x = idx - (r - 5) * ge.cols;
-    tile[idx] = LEFT ? BT::load_left(c, ge, r, x) : BT::load_right(c, ge, r, x);
+    tile[idx] = LEFT ? BT::load_left(c, ge, r, x, A_STEMI) : BT::load_right(c, ge, r, x, A_STEMI);
   }
   __syncthreads();
-  // TXB > 0: block width (hence the tile row stride) known at compile time
-  if (LEFT) BT::template left<(TXB > 0 ? TXB + 32 : 0), ULO>(c, ge, tile, list, threadIdx.x);
-  else BT::template right<(TXB > 0 ? TXB + 32 : 0), ULO>(c, ge, tile, list, threadIdx.x);
+  if (LEFT) BT::template left<COLS, ULO>(c, ge, tile, list, threadIdx.x, st);
+  else BT::template right<COLS, ULO>(c, ge, tile, list, threadIdx.x, st);
+  __syncthreads();
+  // bulges out of the Alpha_stemB tile (same buffer)
+  for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+    const int r = idx / ge.cols + 5, x = idx - (r - 5) * ge.cols;
+    tile[idx] = LEFT ? BT::load_left(c, ge, r, x, A_STEMB) : BT::load_right(c, ge, r, x, A_STEMB);
+  }
+  __syncthreads();
+  if (LEFT) BT::template left_bulge<COLS, ULO>(c, ge, tile, list, threadIdx.x, st);
+  else BT::template right_bulge<COLS, ULO>(c, ge, tile, list, threadIdx.x, st);
 }
 
 template <typename real, bool LEFT>
@@ -573,11 +592,11 @@ int setup_engine(prib_ctx *c, const ScaleSpec &spec, size_t smem_max, std::strin
   // tile width is a compile-time constant of the kernels (row strides become immediates); it is sized
   // for the 227 KB opt-in shared memory of sm_100
   const int TC = TileMaxThreads<real>::value;
-  if ((size_t)kTileRows * TC * sizeof(real) + TC + 16 > smem_max)
+  if ((size_t)kTileRows * TC * sizeof(real) + Core<real>::kHotBytes + TC + 16 > smem_max)
     return fail(PRIB_ECUDA, "this GPU has less opt-in shared memory than the sm_100a tile kernels need");
   if (TC < c->W + 34) return fail(PRIB_ECUDA, "tile narrower than the span halo");
   e.TC = TC;
-  e.tile_smem = (size_t)kTileRows * TC * sizeof(real) + TC + 16;
+  e.tile_smem = (size_t)kTileRows * TC * sizeof(real) + Core<real>::kHotBytes + TC + 16;
   CU(cudaFuncSetAttribute((k_inside_tile<real, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
   CU(cudaFuncSetAttribute((k_outside_tile<real, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
   CU(cudaFuncSetAttribute((k_inside_tile<real, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));

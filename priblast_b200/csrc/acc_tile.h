@@ -121,10 +121,9 @@ struct Tile {
   // TCC: compile-time tile width (0 = take ge.TC at run time, used by the host emulation): with a constant
   // row stride every ring / scratch row offset becomes an immediate of the load instruction.
   template <int R, int TCC = 0>
-  static PRIB_HD void inside_span(const Ctx &c, const Geo &ge, const InSmem &sm, real *scrM1, real *scrM2,
-                                  int tq, const ColState (&cs)[R], int d) {
+  static PRIB_HD void inside_span(const Ctx &c, const ST &T, const Geo &ge, const InSmem &sm, real *scrM1,
+                                  real *scrM2, int tq, const ColState (&cs)[R], int d) {
     const int TC = TCC > 0 ? TCC : ge.TC, c0 = tq * R;
-    const ST &T = *c.T;
     const real *bu = K::bulge_tab(T), *cf = K::cf_tab(T);
     const real g0 = T.cg[0], g1 = T.cg[1], g2 = T.cg[2], g3 = T.cg[3], g4 = T.cg[4], g5 = T.cg[5], g6 = T.cg[6];
     real stem[R], stemI[R], stemB[R], stemD[R], se[R], mu[R], m1[R], m2[R], acc[R], gs[R];
@@ -151,13 +150,17 @@ struct Tile {
       {
         const real *pa = scrM1 + 5 * TC + t, *pb = scrM2 + (d - 5) * TC + t + 5;
         int m = 5;
-        for (; m + 3 <= d - 5; m += 4) {  // same order of additions as the plain loop
-          mb += pa[0] * pb[0];
-          mb += pa[TC] * pb[-(TC - 1)];
-          mb += pa[2 * TC] * pb[-2 * (TC - 1)];
-          mb += pa[3 * TC] * pb[-3 * (TC - 1)];
-          pa += 4 * TC;
-          pb -= 4 * (TC - 1);
+        for (; m + 7 <= d - 5; m += 8) {  // 16 loads in flight; same order of additions as the plain loop
+          real av[8], bv[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            av[k] = pa[k * TC];
+            bv[k] = pb[-k * (TC - 1)];
+          }
+#pragma unroll
+          for (int k = 0; k < 8; ++k) mb += av[k] * bv[k];
+          pa += 8 * TC;
+          pb -= 8 * (TC - 1);
         }
         for (; m <= d - 5; ++m) {
           mb += pa[0] * pb[0];
@@ -290,10 +293,9 @@ struct Tile {
   static PRIB_HD int wrap_out(int r) { return r >= kRingOut ? r - kRingOut : r; }
 
   template <int R, int TCC = 0>
-  static PRIB_HD void outside_span(const Ctx &c, const Geo &ge, const OutSmem &sm, real *scrBif, int tq,
-                                   const ColState (&cs)[R], int d, int slot_d /* = d % kRingOut */) {
+  static PRIB_HD void outside_span(const Ctx &c, const ST &T, const Geo &ge, const OutSmem &sm, real *scrBif,
+                                   int tq, const ColState (&cs)[R], int d, int slot_d /* = d % kRingOut */) {
     const int TC = TCC > 0 ? TCC : ge.TC, W = c.W, c0 = tq * R;
-    const ST &T = *c.T;
     const real *bu = K::bulge_tab(T), *cf = K::cf_tab(T);
     const real g0 = T.cg[0], g1 = T.cg[1], g2 = T.cg[2], g3 = T.cg[3], g4 = T.cg[4], g5 = T.cg[5], g6 = T.cg[6];
     real bstem[R], bstemO[R], bstemB[R], bmulti[R], bmulti2[R], bmbif[R], base[R], ls[R], gs[R], dang[R];
@@ -493,30 +495,40 @@ struct BiTile {
   };
 
   // element of the start-indexed tile: span r, global column g0 + x        (left kernel)
-  static PRIB_HD real load_left(const Ctx &c, const Geo &ge, int r, int x) {
+  static PRIB_HD real load_left(const Ctx &c, const Geo &ge, int r, int x, int arr = A_STEMI) {
     const long long col = ge.g0 + x;
-    return col < c.NC ? c.ld(A_STEMI, r, col) : (real)0;
+    return col < c.NC ? c.ld(arr, r, col) : (real)0;
   }
   // element of the end-indexed tile: span r, END column g0 - 31 + x        (right kernel)
-  static PRIB_HD real load_right(const Ctx &c, const Geo &ge, int r, int x) {
+  static PRIB_HD real load_right(const Ctx &c, const Geo &ge, int r, int x, int arr = A_STEMI) {
     const long long col = ge.g0 - 31 + x - r;
-    return (col >= 0 && col < c.NC) ? c.ld(A_STEMI, r, col) : (real)0;
+    return (col >= 0 && col < c.NC) ? c.ld(arr, r, col) : (real)0;
   }
+
+  // Per-thread state carried from the generic pass (Alpha_stemI tile) to the bulge pass (Alpha_stemB tile).
+  struct Strand {
+    real w[kMaxLoop + 1];  // strand weights by strand length
+    int cnt;               // number of closing spans listed by this thread
+    bool active;
+  };
 
   // thread t = left index i (column g0 + t); list: uint8 [W][TXb] scratch in shared memory.
   // COLS: compile-time row stride of the tile (0 = ge.cols at run time, host emulation); ULO: smallest strand
   // length that is accumulated (min(delta, 5): strands shorter than delta are never read).
   template <int COLS, int ULO>
-  static PRIB_HD void left(const Ctx &c, const Geo &ge, const real *tile, uint8_t *list, int t) {
+  static PRIB_HD void left(const Ctx &c, const Geo &ge, const real *tile, uint8_t *list, int t, Strand &st) {
     const long long g = ge.g0 + t;
+    st.cnt = 0;
+    st.active = false;
     if (g >= c.NC) return;
     typename K::ColInfo ci;
     if (!K::col_info(c, g, ci)) return;
+    st.active = true;
     const ST &T = *c.T;
     const real *cv = K::conv_tab(T), *bu = K::bulge_tab(T);
     const int L = ci.L, i = ci.i, W = c.W, delta = c.delta, TXb = ge.TXb, cols = COLS > 0 ? COLS : ge.cols;
     const uint8_t *s = c.S + g;
-    real ml[kMaxLoop + 1];
+    real (&ml)[kMaxLoop + 1] = st.w;
 #pragma unroll
     for (int u = 0; u <= kMaxLoop; ++u) ml[u] = 0;
     int cnt = 0;
@@ -529,14 +541,9 @@ struct BiTile {
         if (bse == 0) continue;
         list[cnt * TXb + t] = (uint8_t)dp;
         ++cnt;
-        const real bseB = c.ld(B_STEMB, dp + 2, g - 1);
-        const int umax = imin(kMaxLoop, dp - 5);
-#pragma unroll
-        for (int u1 = 2; u1 <= kMaxLoop; ++u1)
-          if (u1 >= delta && u1 <= umax) ml[u1] += bseB * bu[u1] * c.ld(A_STEMB, dp - u1, g + u1);
         if (delta == 2) {
           const int te = T.bp[s[0]][s[dp + 1]];
-          const real bseO = c.ld(B_STEMO, dp + 2, g - 1);
+          const real bseO = c.ld(B_STEMO, dp + 2, g - 1), bseB = c.ld(B_STEMB, dp + 2, g - 1);
           if (dp - 5 >= 3) ml[2] += K::loop_weight(c, T, s, g, dp, te, bse, bseO, bseB, 2, 1);
           if (dp - 5 >= 4) ml[2] += K::loop_weight(c, T, s, g, dp, te, bse, bseO, bseB, 2, 2);
         }
@@ -563,6 +570,26 @@ struct BiTile {
         for (int u1 = ULO; u1 < kMaxLoop; ++u1) ml[u1] += bseO * a[u1];
       }
     }
+    st.cnt = cnt;
+  }
+
+  // bulges (u2 = 0) of the left strand out of the Alpha_stemB tile, then the store of ML
+  template <int COLS, int ULO>
+  static PRIB_HD void left_bulge(const Ctx &c, const Geo &ge, const real *tile, const uint8_t *list, int t, Strand &st) {
+    if (!st.active) return;
+    const long long g = ge.g0 + t;
+    const real *bu = K::bulge_tab(*c.T);
+    const int delta = c.delta, TXb = ge.TXb, cols = COLS > 0 ? COLS : ge.cols;
+    real (&ml)[kMaxLoop + 1] = st.w;
+    for (int k = 0; k < st.cnt; ++k) {
+      const int dp = list[k * TXb + t];
+      const real bseB = c.ld(B_STEMB, dp + 2, g - 1);
+      const int umax = imin(kMaxLoop, dp - 5);
+      const real *base = tile + (dp - 5) * cols + t;
+#pragma unroll
+      for (int u1 = ULO; u1 <= kMaxLoop; ++u1)
+        if (u1 >= delta && u1 <= umax) ml[u1] += bseB * bu[u1] * base[u1 - u1 * cols];  // cell (i+u1, j'), span dp-u1
+    }
 #pragma unroll
     for (int u1 = 2; u1 <= kMaxLoop; ++u1)
       if (u1 >= delta) c.at(X_ML, u1, g) = ml[u1];
@@ -570,15 +597,18 @@ struct BiTile {
 
   // thread t = right end j' of the outer cell (column g0 + t)
   template <int COLS, int ULO>
-  static PRIB_HD void right(const Ctx &c, const Geo &ge, const real *tile, uint8_t *list, int t) {
+  static PRIB_HD void right(const Ctx &c, const Geo &ge, const real *tile, uint8_t *list, int t, Strand &st) {
     const long long g2 = ge.g0 + t;
+    st.cnt = 0;
+    st.active = false;
     if (g2 >= c.NC) return;
     typename K::ColInfo ci;
     if (!K::col_info(c, g2, ci)) return;
+    st.active = true;
     const ST &T = *c.T;
     const real *cv = K::conv_tab(T), *bu = K::bulge_tab(T);
     const int L = ci.L, jp = ci.i, W = c.W, delta = c.delta, TXb = ge.TXb, cols = COLS > 0 ? COLS : ge.cols;
-    real mr[kMaxLoop + 1];
+    real (&mr)[kMaxLoop + 1] = st.w;
 #pragma unroll
     for (int u = 0; u <= kMaxLoop; ++u) mr[u] = 0;
     int cnt = 0;
@@ -590,15 +620,10 @@ struct BiTile {
         if (bse == 0) continue;
         list[cnt * TXb + t] = (uint8_t)dp;
         ++cnt;
-        const real bseB = c.ld(B_STEMB, dp + 2, g - 1);
-        const int umax = imin(kMaxLoop, dp - 5);
-#pragma unroll
-        for (int u2 = 2; u2 <= kMaxLoop; ++u2)
-          if (u2 >= delta && u2 <= umax) mr[u2] += bseB * bu[u2] * c.ld(A_STEMB, dp - u2, g);
         if (delta == 2) {
           const uint8_t *s = c.S + g;
           const int te = T.bp[s[0]][s[dp + 1]];
-          const real bseO = c.ld(B_STEMO, dp + 2, g - 1);
+          const real bseO = c.ld(B_STEMO, dp + 2, g - 1), bseB = c.ld(B_STEMB, dp + 2, g - 1);
           if (dp - 5 >= 3) mr[2] += K::loop_weight(c, T, s, g, dp, te, bse, bseO, bseB, 1, 2);
           if (dp - 5 >= 4) mr[2] += K::loop_weight(c, T, s, g, dp, te, bse, bseO, bseB, 2, 2);
         }
@@ -622,6 +647,26 @@ struct BiTile {
 #pragma unroll
         for (int u2 = ULO; u2 < kMaxLoop; ++u2) mr[u2] += bseO * a[u2];
       }
+    }
+    st.cnt = cnt;
+  }
+
+  // bulges (u1 = 0) of the right strand out of the end-indexed Alpha_stemB tile, then the store of MR
+  template <int COLS, int ULO>
+  static PRIB_HD void right_bulge(const Ctx &c, const Geo &ge, const real *tile, const uint8_t *list, int t, Strand &st) {
+    if (!st.active) return;
+    const long long g2 = ge.g0 + t;
+    const real *bu = K::bulge_tab(*c.T);
+    const int delta = c.delta, TXb = ge.TXb, cols = COLS > 0 ? COLS : ge.cols;
+    real (&mr)[kMaxLoop + 1] = st.w;
+    for (int k = 0; k < st.cnt; ++k) {
+      const int dp = list[k * TXb + t];
+      const real bseB = c.ld(B_STEMB, dp + 2, g2 - dp - 1);
+      const int umax = imin(kMaxLoop, dp - 5);
+      const real *base = tile + (dp - 5) * cols + t + 31;
+#pragma unroll
+      for (int u2 = ULO; u2 <= kMaxLoop; ++u2)
+        if (u2 >= delta && u2 <= umax) mr[u2] += bseB * bu[u2] * base[-u2 - u2 * cols];  // cell (i, j'-u2), span dp-u2
     }
 #pragma unroll
     for (int u2 = 2; u2 <= kMaxLoop; ++u2)

@@ -106,7 +106,7 @@ void run_dp_tiled(EmuT<real> &e, int TC) {
       for (int tq = 0; tq < TC / R; tq++) {
         typename TL::ColState csr[R];
         for (int r = 0; r < R; r++) csr[r] = cs[tq * R + r];
-        TL::template inside_span<R>(c, ge, sm, scr.data(), scr.data() + (size_t)(W + 4) * TC, tq, csr, d);
+        TL::template inside_span<R>(c, *c.T, ge, sm, scr.data(), scr.data() + (size_t)(W + 4) * TC, tq, csr, d);
       }
   }
   double ring[256];
@@ -123,7 +123,7 @@ void run_dp_tiled(EmuT<real> &e, int TC) {
       for (int tq = 0; tq < TC / R; tq++) {
         typename TL::ColState csr[R];
         for (int r = 0; r < R; r++) csr[r] = cs[tq * R + r];
-        TL::template outside_span<R>(c, ge, sm, scr.data(), tq, csr, d, d % kRingOut);
+        TL::template outside_span<R>(c, *c.T, ge, sm, scr.data(), tq, csr, d, d % kRingOut);
       }
   }
 }
@@ -138,19 +138,33 @@ void run_biloop_tiled(EmuT<real> &e, int TXb) {
   ge.rows = c.W - 5 > 0 ? c.W - 5 : 0;
   std::vector<real> tile((size_t)ge.rows * ge.cols + 1);
   std::vector<uint8_t> list((size_t)(c.W + 1) * TXb);
+  std::vector<typename BT::Strand> st(TXb);
   for (int side = 0; side < 2; side++)
     for (long long g0 = 0; g0 < c.NC; g0 += TXb) {
       ge.g0 = g0;
-      for (int r = 5; r < 5 + ge.rows; r++)
-        for (int x = 0; x < ge.cols; x++)
-          tile[(size_t)(r - 5) * ge.cols + x] = side == 0 ? BT::load_left(c, ge, r, x) : BT::load_right(c, ge, r, x);
+      auto fill = [&](int arr) {
+        for (int r = 5; r < 5 + ge.rows; r++)
+          for (int x = 0; x < ge.cols; x++)
+            tile[(size_t)(r - 5) * ge.cols + x] = side == 0 ? BT::load_left(c, ge, r, x, arr) : BT::load_right(c, ge, r, x, arr);
+      };
+      fill(A_STEMI);
       for (int t = 0; t < TXb; t++) {
         if (side == 0) {
-          if (c.delta >= 5) BT::template left<0, 5>(c, ge, tile.data(), list.data(), t);
-          else BT::template left<0, 2>(c, ge, tile.data(), list.data(), t);
+          if (c.delta >= 5) BT::template left<0, 5>(c, ge, tile.data(), list.data(), t, st[t]);
+          else BT::template left<0, 2>(c, ge, tile.data(), list.data(), t, st[t]);
         } else {
-          if (c.delta >= 5) BT::template right<0, 5>(c, ge, tile.data(), list.data(), t);
-          else BT::template right<0, 2>(c, ge, tile.data(), list.data(), t);
+          if (c.delta >= 5) BT::template right<0, 5>(c, ge, tile.data(), list.data(), t, st[t]);
+          else BT::template right<0, 2>(c, ge, tile.data(), list.data(), t, st[t]);
+        }
+      }
+      fill(A_STEMB);
+      for (int t = 0; t < TXb; t++) {
+        if (side == 0) {
+          if (c.delta >= 5) BT::template left_bulge<0, 5>(c, ge, tile.data(), list.data(), t, st[t]);
+          else BT::template left_bulge<0, 2>(c, ge, tile.data(), list.data(), t, st[t]);
+        } else {
+          if (c.delta >= 5) BT::template right_bulge<0, 5>(c, ge, tile.data(), list.data(), t, st[t]);
+          else BT::template right_bulge<0, 2>(c, ge, tile.data(), list.data(), t, st[t]);
         }
       }
     }
