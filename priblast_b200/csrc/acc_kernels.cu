@@ -120,50 +120,65 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
+// Blocked scan: 32 consecutive positions per round, lane = position.  In "step" coordinates (step = i for
+// Alpha_outer, L - i for Beta_outer) both recurrences read  v[st] = v[st-1] + sum_d w(st,d) v[st-d].
+//  (1) partners before the block: every lane sums its own <= W terms, no communication;
+//  (2) partners inside the block: 32 sequential sub-steps, each = one 64-bit broadcast + one FMA on the
+//      lanes at distance >= 5; the critical chain is  v[s] = v[s-1] + ext[s]  (ext[s] is final 5 sub-steps
+//      earlier), i.e. one shuffle + one add per position.
+// wbuf: per-warp [W + 2][32] weights (each lane only touches its own column), usm: us[] in shared memory.
 template <typename real, bool ALPHA>
-__device__ void warp_scan(const typename Core<real>::Ctx &c, int sq, double *ring, int lane) {
+__device__ void warp_scan(const typename Core<real>::Ctx &c, int sq, double *ring, real *wbuf, const double *usm,
+                          int lane) {
   const int L = c.seq_len[sq], W = c.W;
   const long long off = c.seq_off[sq];
   const double kBig = 1.3407807929942597e154, kLn2 = 0.6931471805599453094;
   double *dst = ALPHA ? c.lao : c.lbo;
   const real *src = c.arr[ALPHA ? A_STEMDE : A_STEMD];
-  const double *us = c.T->us;
   long long e2 = 0;
-  const int start = ALPHA ? 0 : L;
   if (lane == 0) {
-    ring[start & 255] = 1.0;
-    dst[off + start] = 0.0;
+    ring[0] = 1.0;
+    dst[off + (ALPHA ? 0 : L)] = 0.0;
   }
   __syncwarp();
-  double keep_v = 1.0;  // value of the position this lane will take the log of
-  long long keep_e = 0;
-  int keep_pos = -1;
-  for (int step = 1; step <= L; ++step) {
-    const int i = ALPHA ? step : L - step;
-    const long long col = off + i;
-    const int dmax = ALPHA ? imin(W + 1, i) : imin(W + 1, L - i);
-    double part = 0;
-    for (int d = 5 + lane; d <= dmax; d += 32) {
-      const int j = ALPHA ? i - d : i + d;
-      part += (double)src[(long long)d * c.NC + col] * us[d] * ring[j & 255];
+  for (int st0 = 1; st0 <= L; st0 += 32) {
+    const int st = st0 + lane;
+    const bool ok = st <= L;
+    const int i = ALPHA ? st : L - st;
+    const int dhi = ok ? imin(W + 1, st) : 0;  // partner step st - d >= 0
+    // stage this position's weights, 8 independent loads in flight at a time
+    const real *col = src + off + i;
+    for (int d0 = 5; d0 <= W + 1; d0 += 8) {
+      real tmp[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) tmp[k] = (d0 + k <= dhi) ? col[(long long)(d0 + k) * c.NC] : (real)0;
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        if (d0 + k <= W + 1) wbuf[(d0 + k - 5) * 32 + lane] = tmp[k];
     }
-    double v = warp_sum(part) + ring[(ALPHA ? i - 1 : i + 1) & 255];
-    if (v > kBig) {  // uniform: every lane holds the same v
-      const int lo = ALPHA ? imax(0, i - W - 2) : i + 1, hi = ALPHA ? i - 1 : imin(L, i + W + 2);
-      for (int k = lo + lane; k <= hi; k += 32) ring[k & 255] *= 1.0 / kBig;
-      v *= 1.0 / kBig;
-      e2 += 512;
+    double ext = 0;
+    for (int d = imax(5, lane + 1); d <= dhi; ++d)  // partners before the block
+      ext += (double)wbuf[(d - 5) * 32 + lane] * usm[d] * ring[(st - d) & 255];
+    double vprev = ring[(st0 - 1) & 255];
+    double myv = 0;
+    const int nsub = imin(32, L - st0 + 1);
+    for (int s = 0; s < nsub; ++s) {
+      const double vs = __shfl_sync(0xffffffffu, vprev + ext, s);  // lane s holds v[s-1] + ext[s]
+      if (lane == s) myv = vs;
+      vprev = vs;
+      const int dd = lane - s;
+      if (dd >= 5 && dd <= dhi) ext += (double)wbuf[(dd - 5) * 32 + lane] * usm[dd] * vs;
     }
-    if (lane == 0) ring[i & 255] = v;
-    if ((step & 31) == lane) {
-      keep_v = v;
-      keep_e = e2;
-      keep_pos = i;
+    if (ok) {
+      ring[st & 255] = myv;
+      dst[off + i] = log(myv) + (double)e2 * kLn2;
     }
     __syncwarp();
-    if ((step & 31) == 31 || step == L) {
-      if (keep_pos >= 0) dst[off + keep_pos] = log(keep_v) + (double)keep_e * kLn2;
-      keep_pos = -1;
+    if (vprev > kBig) {  // uniform (vprev was broadcast): exact power-of-two rescale of the live window
+      const int hi = imin(L, st0 + 31), lo = imax(0, hi - W - 2);
+      for (int k = lo + lane; k <= hi; k += 32) ring[k & 255] *= 1.0 / kBig;
+      e2 += 512;
+      __syncwarp();
     }
   }
 }
@@ -171,26 +186,19 @@ __device__ void warp_scan(const typename Core<real>::Ctx &c, int sq, double *rin
 template <typename real>
 __global__ void __launch_bounds__(32 * kScanWarps) k_outer_scans_warp(typename Core<real>::Ctx c) {
   __shared__ double rings[kScanWarps][256];
+  __shared__ double usm[kMaxSpan + 8];
+  extern __shared__ __align__(16) unsigned char scan_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int k = threadIdx.x; k < kMaxSpan + 8; k += blockDim.x) usm[k] = c.T->us[k];
+  __syncthreads();
   const int sq = blockIdx.x * kScanWarps + warp;
   if (sq >= c.nseq) return;
-  warp_scan<real, true>(c, sq, rings[warp], lane);
+  real *wbuf = reinterpret_cast<real *>(scan_smem) + (size_t)warp * (c.W + 2) * 32;
+  warp_scan<real, true>(c, sq, rings[warp], wbuf, usm, lane);
   __syncwarp();
-  warp_scan<real, false>(c, sq, rings[warp], lane);
+  warp_scan<real, false>(c, sq, rings[warp], wbuf, usm, lane);
 }
 
-template <typename real>
-__global__ void __launch_bounds__(kThreads) k_biloop_left(typename Core<real>::Ctx c) {
-  const long long g = (long long)blockIdx.x * kThreads + threadIdx.x;
-  if (g < c.NC) Core<real>::biloop_left(c, g);
-}
-template <typename real>
-__global__ void __launch_bounds__(kThreads) k_biloop_right(typename Core<real>::Ctx c) {
-  const long long g = (long long)blockIdx.x * kThreads + threadIdx.x;
-  if (g < c.NC) Core<real>::biloop_right(c, g);
-}
-// Interior-loop strand weights, tile version (acc_tile.h BiTile): blockDim = TXb owned columns; dynamic smem =
-// (W-5) x (TXb+32) reals (Alpha_stemI tile) + W x TXb bytes (per-thread lists of closing spans).
 template <typename real, bool LEFT, int ULO, int TXB>
 __global__ void __launch_bounds__(512) k_biloop_tile(typename Core<real>::Ctx c) {
   typedef BiTile<real> BT;
@@ -349,7 +357,6 @@ struct prib_ctx {
   prib_acc_params prm{};
   int W = 70, delta = 5;
   bool use_fp32 = true;
-  bool biloop_v1 = false;
   int cols_per_thread = 1;  // register tiling of the stencils (PRIB_COLS=1|2|4); measured: 1 is fastest (latency-bound)
   cudaStream_t own_stream = nullptr, stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk0 = nullptr, evk1 = nullptr;
@@ -536,18 +543,17 @@ int run_batch(prib_ctx *c, const Batch &b, bool timed) {
   else if (c->cols_per_thread == 2) k_inside_tile<real, 2><<<tgrid, e.TC / 2, e.tile_smem, st>>>(k, TX, ntiles, scratch);
   else k_inside_tile<real, 1><<<tgrid, e.TC, e.tile_smem, st>>>(k, TX, ntiles, scratch);
   if (timed) CU(cudaEventRecord(c->evp[2], st));
-  k_outer_scans_warp<real><<<(b.n + kScanWarps - 1) / kScanWarps, 32 * kScanWarps, 0, st>>>(k);
+  k_outer_scans_warp<real><<<(b.n + kScanWarps - 1) / kScanWarps, 32 * kScanWarps,
+                             (size_t)kScanWarps * (c->W + 2) * 32 * sizeof(real), st>>>(k);
   if (timed) CU(cudaEventRecord(c->evp[3], st));
   if (c->cols_per_thread == 4) k_outside_tile<real, 4><<<tgrid, e.TC / 4, e.tile_smem, st>>>(k, TX, ntiles, scratch);
   else if (c->cols_per_thread == 2) k_outside_tile<real, 2><<<tgrid, e.TC / 2, e.tile_smem, st>>>(k, TX, ntiles, scratch);
   else k_outside_tile<real, 1><<<tgrid, e.TC, e.tile_smem, st>>>(k, TX, ntiles, scratch);
   if (timed) CU(cudaEventRecord(c->evp[4], st));
   const unsigned bgrid = (unsigned)((b.NC + e.TXb - 1) / e.TXb);
-  if (c->biloop_v1) k_biloop_left<real><<<grid, kThreads, 0, st>>>(k);
-  else launch_biloop<real, true>(k, bgrid, e.TXb, e.bi_smem, st);
+  launch_biloop<real, true>(k, bgrid, e.TXb, e.bi_smem, st);
   if (timed) CU(cudaEventRecord(c->evp[5], st));
-  if (c->biloop_v1) k_biloop_right<real><<<grid, kThreads, 0, st>>>(k);
-  else launch_biloop<real, false>(k, bgrid, e.TXb, e.bi_smem, st);
+  launch_biloop<real, false>(k, bgrid, e.TXb, e.bi_smem, st);
   if (timed) CU(cudaEventRecord(c->evp[6], st));
   k_hairpin_suffix<real><<<grid, kThreads, 0, st>>>(k);
   k_finalize<real><<<grid, kThreads, 0, st>>>(k);
@@ -610,6 +616,8 @@ int setup_engine(prib_ctx *c, const ScaleSpec &spec, size_t smem_max, std::strin
   e.TXb = TXb;
   e.bi_smem = (size_t)rows * (TXb + 32) * sizeof(real) + (size_t)(c->W + 1) * TXb + 64;
   if (e.bi_smem > smem_max) return fail(PRIB_ECUDA, "shared memory too small for the interior-loop tiles");
+  CU(cudaFuncSetAttribute(k_outer_scans_warp<real>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                          (int)(smem_max - 16 * 1024)));
 #define PRIB_BI_ATTR(L, U, X) \
   CU(cudaFuncSetAttribute((k_biloop_tile<real, L, U, X>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max))
   PRIB_BI_ATTR(true, 5, 512); PRIB_BI_ATTR(true, 2, 512); PRIB_BI_ATTR(false, 5, 512); PRIB_BI_ATTR(false, 2, 512);
@@ -665,8 +673,6 @@ int prib_acc_create(prib_ctx **out, const prib_acc_params *params) {
     const int v = atoi(ce);
     if (v == 1 || v == 2 || v == 4) c->cols_per_thread = v;
   }
-  const char *be = getenv("PRIB_BILOOP");
-  c->biloop_v1 = be && be[0] == '1';
   const char *pe = getenv("PRIB_PRECISION");
   c->use_fp32 = params->mode == 0 && c->W <= kFp32MaxSpan && !(pe && strcmp(pe, "fp64") == 0);
   auto bail = [&](int code) {

@@ -327,10 +327,24 @@ struct Tile {
         {
           const real *pa = scrBif + (d + 5) * TC + t;
           const real *pb = c.arr[A_MULTI2] + 5 * c.NC + g + d;
-          for (int m = 5; m <= m1max; ++m) {
+          const long long nc = c.NC;
+          int m = 5;
+          for (; m + 7 <= m1max; m += 8) {  // 16 loads in flight; additions in the plain order
+            real av[8], bv[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              av[k] = pa[k * TC];
+              bv[k] = pb[k * nc];
+            }
+#pragma unroll
+            for (int k = 0; k < 8; ++k) bm1 += av[k] * bv[k];
+            pa += 8 * TC;
+            pb += 8 * nc;
+          }
+          for (; m <= m1max; ++m) {
             bm1 += pa[0] * pb[0];
             pa += TC;
-            pb += c.NC;
+            pb += nc;
           }
         }
         bm1 *= T.inv_cA;
@@ -339,10 +353,24 @@ struct Tile {
         {
           const real *pa = scrBif + (d + 5) * TC + t - 5;
           const real *pb = c.arr[A_MULTI1] + 5 * c.NC + g - 5;
-          for (int m = 5; m <= m2max; ++m) {
+          const long long nc1 = c.NC - 1;
+          int m = 5;
+          for (; m + 7 <= m2max; m += 8) {
+            real av[8], bv[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              av[k] = pa[k * (TC - 1)];
+              bv[k] = pb[k * nc1];
+            }
+#pragma unroll
+            for (int k = 0; k < 8; ++k) ks += av[k] * bv[k];
+            pa += 8 * (TC - 1);
+            pb += 8 * nc1;
+          }
+          for (; m <= m2max; ++m) {
             ks += pa[0] * pb[0];
             pa += TC - 1;
-            pb += c.NC - 1;
+            pb += nc1;
           }
         }
         bmulti2[r] = bm1 + sm.m2[((d + 1) & 1) * TC + t] * T.e_mlbase + ks * T.inv_cA;
