@@ -170,6 +170,7 @@ def ours(args, rank: int, local_rank: int, world: int) -> None:
         raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     if world > 1:
+        os.environ["NCCL_DEBUG"] = "WARN"  # stdout must carry exactly one JSON line (no "NCCL version" banner)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     def barrier():
@@ -288,8 +289,10 @@ def ours(args, rank: int, local_rank: int, world: int) -> None:
         line = {
             "metric": "db-step accessibility throughput", "value": value, "unit": "nt/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step_max,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "transcripts_per_gpu_per_step": SEQS_PER_STEP,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "arithmetic": "band DP in f32 (span-scaled, range-guarded, f64 re-run of flagged sequences: "
+                       + str(int(c1["fp64_rerun_sequences"] - c0["fp64_rerun_sequences"])) + " in the timed region); outer arrays and final sums in f64",
+                       "transcripts_per_gpu_per_step": SEQS_PER_STEP,
                        "nt_per_gpu_per_step": nt_rank, "span": W_SPAN, "delta": DELTA,
                        "l2_policy": f"no flush needed: each step rewrites {used_state / 2**30:.1f} GiB of DP state "
                                     "(>> 126 MB L2)",

@@ -328,6 +328,7 @@ struct Batch {
   uint8_t *d_S = nullptr;
   int32_t *d_col_seq = nullptr, *d_seq_len = nullptr, *d_flags = nullptr;
   long long *d_seq_off = nullptr, *d_acc_off = nullptr, *d_cond_off = nullptr;
+  long long cap_cols = 0, cap_seqs = 0;  // device buffers are grow-only and reused from stage to stage
 };
 
 template <typename real>
@@ -372,8 +373,9 @@ struct prib_ctx {
   // staged work
   std::vector<Batch> batches;
   std::vector<std::string> seqs;  // host copies (needed to re-run flagged sequences in double)
+  size_t n_batches = 0;           // batches[0..n_batches) are live; the rest keep their buffers for reuse
   float *d_out = nullptr;
-  long long out_floats = 0;
+  long long out_floats = 0, out_cap = 0;
   bool staged = false, computed = false;
   float *h_stage = nullptr;
   long long h_stage_floats = 0;
@@ -385,6 +387,10 @@ struct prib_ctx {
 namespace {
 
 void free_batch(Batch &b) {
+  if (!b.d_S && !b.d_seq_len) {
+    b = Batch();
+    return;
+  }
   cudaFree(b.d_S);
   cudaFree(b.d_col_seq);
   cudaFree(b.d_seq_len);
@@ -398,8 +404,10 @@ void free_batch(Batch &b) {
 void free_batches(prib_ctx *c) {
   for (auto &b : c->batches) free_batch(b);
   c->batches.clear();
+  c->n_batches = 0;
   if (c->d_out) cudaFree(c->d_out);
   c->d_out = nullptr;
+  c->out_cap = 0;
   c->out_floats = 0;
   c->seqs.clear();
   c->staged = c->computed = false;
@@ -474,13 +482,32 @@ int make_batch(prib_ctx *c, const std::vector<int> &ids, const std::vector<long 
   build_layout(b.n, sp.data(), sl.data(), lay);
   b.NC = lay.NC;
   const size_t n1 = (size_t)std::max(b.n, 1);
-  CU(cudaMalloc(&b.d_S, (size_t)b.NC));
-  CU(cudaMalloc(&b.d_col_seq, (size_t)b.NC * sizeof(int32_t)));
-  CU(cudaMalloc(&b.d_seq_len, n1 * sizeof(int32_t)));
-  CU(cudaMalloc(&b.d_flags, n1 * sizeof(int32_t)));
-  CU(cudaMalloc(&b.d_seq_off, n1 * sizeof(long long)));
-  CU(cudaMalloc(&b.d_acc_off, n1 * sizeof(long long)));
-  CU(cudaMalloc(&b.d_cond_off, n1 * sizeof(long long)));
+  if (b.NC > b.cap_cols) {
+    cudaFree(b.d_S);
+    cudaFree(b.d_col_seq);
+    b.d_S = nullptr;
+    b.d_col_seq = nullptr;
+    b.cap_cols = 0;
+    CU(cudaMalloc(&b.d_S, (size_t)b.NC));
+    CU(cudaMalloc(&b.d_col_seq, (size_t)b.NC * sizeof(int32_t)));
+    b.cap_cols = b.NC;
+  }
+  if ((long long)n1 > b.cap_seqs) {
+    cudaFree(b.d_seq_len);
+    cudaFree(b.d_flags);
+    cudaFree(b.d_seq_off);
+    cudaFree(b.d_acc_off);
+    cudaFree(b.d_cond_off);
+    b.d_seq_len = b.d_flags = nullptr;
+    b.d_seq_off = b.d_acc_off = b.d_cond_off = nullptr;
+    b.cap_seqs = 0;
+    CU(cudaMalloc(&b.d_seq_len, n1 * sizeof(int32_t)));
+    CU(cudaMalloc(&b.d_flags, n1 * sizeof(int32_t)));
+    CU(cudaMalloc(&b.d_seq_off, n1 * sizeof(long long)));
+    CU(cudaMalloc(&b.d_acc_off, n1 * sizeof(long long)));
+    CU(cudaMalloc(&b.d_cond_off, n1 * sizeof(long long)));
+    b.cap_seqs = (long long)n1;
+  }
   CU(cudaEventRecord(c->ev0, c->stream));
   CU(cudaMemcpyAsync(b.d_S, lay.S.data(), (size_t)b.NC, cudaMemcpyHostToDevice, c->stream));
   CU(cudaMemcpyAsync(b.d_col_seq, lay.col_seq.data(), (size_t)b.NC * 4, cudaMemcpyHostToDevice, c->stream));
@@ -499,8 +526,8 @@ int make_batch(prib_ctx *c, const std::vector<int> &ids, const std::vector<long 
 
 // Greedy partition of `order` (already longest-first) into batches that fit `max_cols` columns.
 int partition(prib_ctx *c, const std::vector<int> &order, long long max_cols, const std::vector<long long> &acc_abs,
-              const std::vector<long long> &cond_abs, std::vector<Batch> &out) {
-  size_t pos = 0;
+              const std::vector<long long> &cond_abs, std::vector<Batch> &out, size_t *n_live) {
+  size_t pos = 0, used = 0;
   while (pos < order.size()) {
     std::vector<int> ids;
     std::vector<long long> ao, co;
@@ -514,10 +541,12 @@ int partition(prib_ctx *c, const std::vector<int> &order, long long max_cols, co
     }
     if (ids.empty())
       return fail(PRIB_ECUDA, "sequence " + std::to_string(order[pos]) + " does not fit the device DP budget");
-    out.emplace_back();
-    int rc = make_batch(c, ids, ao, co, out.back());
+    if (used == out.size()) out.emplace_back();
+    int rc = make_batch(c, ids, ao, co, out[used]);
     if (rc != PRIB_OK) return rc;
+    ++used;
   }
+  *n_live = used;
   return PRIB_OK;
 }
 
@@ -753,7 +782,8 @@ int prib_acc_set_stream(prib_ctx *c, void *cuda_stream) {
 int prib_acc_stage(prib_ctx *c, int32_t n, const char *const *seq, const int32_t *len) {
   if (!c || n < 0 || (n > 0 && (!seq || !len))) return fail(PRIB_EINVAL, "bad argument");
   CU(cudaSetDevice(c->prm.device));
-  free_batches(c);
+  c->staged = c->computed = false;
+  c->n_batches = 0;
   const long long max_cols = c->use_fp32 ? c->e32.max_cols : c->e64.max_cols;
   for (int k = 0; k < n; k++) {
     if (len[k] < 0) return fail(PRIB_EINVAL, "negative sequence length");
@@ -776,9 +806,15 @@ int prib_acc_stage(prib_ctx *c, int32_t n, const char *const *seq, const int32_t
   std::vector<int> order(n);
   std::iota(order.begin(), order.end(), 0);
   std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return len[a] > len[b]; });
-  int rc = partition(c, order, max_cols, acc_abs, cond_abs, c->batches);
+  int rc = partition(c, order, max_cols, acc_abs, cond_abs, c->batches, &c->n_batches);
   if (rc != PRIB_OK) return rc;
-  CU(cudaMalloc(&c->d_out, (size_t)std::max<long long>(o, 1) * sizeof(float)));
+  if (o > c->out_cap || !c->d_out) {
+    if (c->d_out) cudaFree(c->d_out);
+    c->d_out = nullptr;
+    c->out_cap = 0;
+    CU(cudaMalloc(&c->d_out, (size_t)std::max<long long>(o, 1) * sizeof(float)));
+    c->out_cap = std::max<long long>(o, 1);
+  }
   c->staged = true;
   return PRIB_OK;
 }
@@ -792,7 +828,8 @@ int prib_acc_compute(prib_ctx *c) {
   // entries the kernels never write (acc tail, cond head) must read 0: raccess.cpp:487-488
   CU(cudaMemsetAsync(c->d_out, 0, (size_t)std::max<long long>(c->out_floats, 1) * sizeof(float), c->stream));
   std::vector<int> flagged;
-  for (const Batch &b : c->batches) {
+  for (size_t bi = 0; bi < c->n_batches; ++bi) {
+    const Batch &b = c->batches[bi];
     if (b.n == 0) continue;
     int rc = c->use_fp32 ? run_batch<float>(c, b, true) : run_batch<double>(c, b, true);
     if (rc != PRIB_OK) return rc;
@@ -824,7 +861,8 @@ int prib_acc_compute(prib_ctx *c) {
     std::stable_sort(flagged.begin(), flagged.end(),
                      [&](int a, int b) { return c->seqs[a].size() > c->seqs[b].size(); });
     std::vector<Batch> fb;
-    int rc = partition(c, flagged, c->e64.max_cols, acc_abs, cond_abs, fb);
+    size_t nfb = 0;
+    int rc = partition(c, flagged, c->e64.max_cols, acc_abs, cond_abs, fb, &nfb);
     for (Batch &b : fb) {
       if (rc == PRIB_OK) rc = run_batch<double>(c, b, false);
       if (rc == PRIB_OK && cudaStreamSynchronize(c->stream) != cudaSuccess) rc = fail(PRIB_ECUDA, "fp64 re-run failed");
