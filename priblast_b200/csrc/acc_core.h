@@ -52,6 +52,8 @@ enum Arr {
   X_ML,        // rows 0..30: left-strand loop weight  ML[u1][i]    (restructured :644-650)
   X_MR,        // rows 0..30: right-strand loop weight MR[u2][j']   (restructured :652-658)
   X_SUFH,      // suffix sums over span of hairpin-loop weights     (restructured :546-561)
+  X_MLS,       // X_MLS[m][i] = sum over u1 >= m of ML[u1][i] (strands LONGER than the window)
+  X_MRS,       // same for MR
   kNumArr
 };
 
@@ -487,6 +489,11 @@ static PRIB_HD void biloop_left(const Ctx &c, long long g) {
     }
     c.at(X_ML, u1, g) = acc;
   }
+  real suf = 0;
+  for (int u1 = kMaxLoop; u1 >= c.delta; --u1) {
+    suf += c.ld(X_ML, u1, g);
+    c.at(X_MLS, u1, g) = suf;
+  }
 }
 
 // thread = right end j' of the outer cell; writes MR[u2][g'] for u2 in [delta, 30]
@@ -511,6 +518,11 @@ static PRIB_HD void biloop_right(const Ctx &c, long long g2) {
       }
     }
     c.at(X_MR, u2, g2) = acc;
+  }
+  real suf = 0;
+  for (int u2 = kMaxLoop; u2 >= c.delta; --u2) {
+    suf += c.ld(X_MR, u2, g2);
+    c.at(X_MRS, u2, g2) = suf;
   }
 }
 
@@ -589,15 +601,12 @@ static PRIB_HD void biloop_gather(const Ctx &c, long long off, int L, int k, dou
   for (int i = imax(1, k + w - 1 - kMaxLoop); i <= k - 1; ++i) {
     const int ub = k + w - 1 - i;  // strand length whose last base is the window end
     b += c.ld(X_ML, ub, off + i);
-    for (int u1 = ub + 1; u1 <= kMaxLoop; ++u1) cc += c.ld(X_ML, u1, off + i);
+    if (ub + 1 <= kMaxLoop) cc += c.ld(X_MLS, ub + 1, off + i);
   }
   for (int jp = k + w - 1; jp <= imin(L - 1, k + kMaxLoop - 1); ++jp) {
     const int umin = jp - k + 1;  // strand must start before k
-    if (jp == k + w - 1) {
-      for (int u2 = umin; u2 <= kMaxLoop; ++u2) b += c.ld(X_MR, u2, off + jp);
-    } else {
-      for (int u2 = umin; u2 <= kMaxLoop; ++u2) cc += c.ld(X_MR, u2, off + jp);
-    }
+    if (jp == k + w - 1) b += c.ld(X_MRS, umin, off + jp);
+    else cc += c.ld(X_MRS, umin, off + jp);
   }
   b *= (double)c.T->kacc;
   cc *= (double)c.T->kacc;

@@ -312,7 +312,7 @@ int fail(int code, const std::string &msg) {
       return fail(PRIB_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_));            \
   } while (0)
 
-int rows_of(int a, int W) { return (a == X_ML || a == X_MR) ? 32 : W + 4; }
+int rows_of(int a, int W) { return (a == X_ML || a == X_MR || a == X_MLS || a == X_MRS) ? 32 : W + 4; }
 
 long long state_bytes_per_column(int W, size_t real_size) {
   long long r = 0;

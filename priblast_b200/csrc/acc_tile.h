@@ -618,9 +618,15 @@ struct BiTile {
       for (int u1 = ULO; u1 <= kMaxLoop; ++u1)
         if (u1 >= delta && u1 <= umax) ml[u1] += bseB * bu[u1] * base[u1 - u1 * cols];  // cell (i+u1, j'), span dp-u1
     }
+    real suf = 0;
 #pragma unroll
-    for (int u1 = 2; u1 <= kMaxLoop; ++u1)
-      if (u1 >= delta) c.at(X_ML, u1, g) = ml[u1];
+    for (int u1 = kMaxLoop; u1 >= 2; --u1) {
+      if (u1 >= delta) {
+        c.at(X_ML, u1, g) = ml[u1];
+        suf += ml[u1];
+        c.at(X_MLS, u1, g) = suf;
+      }
+    }
   }
 
   // thread t = right end j' of the outer cell (column g0 + t)
@@ -696,9 +702,15 @@ struct BiTile {
       for (int u2 = ULO; u2 <= kMaxLoop; ++u2)
         if (u2 >= delta && u2 <= umax) mr[u2] += bseB * bu[u2] * base[-u2 - u2 * cols];  // cell (i, j'-u2), span dp-u2
     }
+    real suf = 0;
 #pragma unroll
-    for (int u2 = 2; u2 <= kMaxLoop; ++u2)
-      if (u2 >= delta) c.at(X_MR, u2, g2) = mr[u2];
+    for (int u2 = kMaxLoop; u2 >= 2; --u2) {
+      if (u2 >= delta) {
+        c.at(X_MR, u2, g2) = mr[u2];
+        suf += mr[u2];
+        c.at(X_MRS, u2, g2) = suf;
+      }
+    }
   }
 };
 

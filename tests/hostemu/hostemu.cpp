@@ -53,7 +53,7 @@ bool setup(EmuT<real> &e, int n, const char *const *seqs, const int32_t *lens, i
   c.log_tbl = e.tab.log_tbl.data();
   e.arr.resize(kNumArr);
   for (int a = 0; a < kNumArr; a++) {
-    int rows = (a == X_ML || a == X_MR) ? 32 : c.rows;
+    int rows = (a == X_ML || a == X_MR || a == X_MLS || a == X_MRS) ? 32 : c.rows;
     e.arr[a].assign((size_t)rows * (size_t)c.NC, (real)0);
     c.arr[a] = e.arr[a].data();
   }
