@@ -560,7 +560,8 @@ int run_batch(prib_ctx *c, const Batch &b, bool timed) {
   cudaStream_t st = c->stream;
   if (used > c->cnt.dp_state_bytes_used) c->cnt.dp_state_bytes_used = used;
   if (timed) CU(cudaEventRecord(c->evp[0], st));
-  CU(cudaMemsetAsync(c->d_state, 0, (size_t)used, st));
+  // the DP state is NOT cleared: every kernel only reads cells written earlier in the same batch
+  // (tests/test_hostemu.py::test_no_kernel_reads_a_cell_it_did_not_write poisons the state with NaN)
   CU(cudaMemsetAsync(b.d_flags, 0, sizeof(int32_t) * (size_t)std::max(b.n, 1), st));
   const unsigned grid = (unsigned)((b.NC + kThreads - 1) / kThreads);
   if (timed) CU(cudaEventRecord(c->evp[1], st));

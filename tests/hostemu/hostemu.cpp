@@ -8,6 +8,7 @@
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
+#include <limits>
 #include <string>
 #include <vector>
 
@@ -16,6 +17,7 @@
 #include "../../priblast_b200/csrc/acc_tile.h"
 
 using namespace prib;
+static int g_poison = 0;
 
 namespace {
 
@@ -216,6 +218,11 @@ int run_tiled(int n, const char *const *seqs, const int32_t *lens, int W, int de
   }
   if (!setup(e, n, seqs, lens, W, delta, out, acc_off, cond_off, spec)) return -1;
   if (TC <= W + 2 || TC % 4 != 0) return -2;
+  if (g_poison) {
+    for (auto &a : e.arr) std::fill(a.begin(), a.end(), std::numeric_limits<real>::quiet_NaN());
+    std::fill(e.lao.begin(), e.lao.end(), std::numeric_limits<double>::quiet_NaN());
+    std::fill(e.lbo.begin(), e.lbo.end(), std::numeric_limits<double>::quiet_NaN());
+  }
   if (R == 4) run_dp_tiled<real, 4>(e, TC);
   else if (R == 2) run_dp_tiled<real, 2>(e, TC);
   else run_dp_tiled<real, 1>(e, TC);
@@ -228,6 +235,10 @@ int run_tiled(int n, const char *const *seqs, const int32_t *lens, int W, int de
 static int g_cols_per_thread = 1;
 
 extern "C" {
+
+// poison = 1: fill every DP array with NaN before the run (emulates a device that does not zero its state):
+// any read of a never-written cell then shows up in the output
+void hostemu_set_poison(int on) { g_poison = on; }
 
 // columns per emulated thread (register tiling of the stencils): 1, 2 or 4
 void hostemu_set_cols_per_thread(int R) { g_cols_per_thread = R; }

@@ -129,3 +129,19 @@ def test_register_tiled_stencil_is_bit_identical(emu, R, W, TC):
     finally:
         emu.lib.hostemu_set_cols_per_thread(1)
     assert np.array_equal(ref.view(np.uint32), got.view(np.uint32))
+
+
+@pytest.mark.parametrize("W,TC,delta", [(70, 352, 5), (20, 64, 2), (150, 352, 10)])
+def test_no_kernel_reads_a_cell_it_did_not_write(emu, W, TC, delta):
+    """The device does not clear its DP state between batches: with every array poisoned with NaN the tile
+    path must still give the same bits (every read is of a cell written earlier in the same batch)."""
+    ref, _, _ = _tiled(emu.lib, _MIX, W, delta, TC)
+    emu.lib.hostemu_set_poison(1)
+    try:
+        got, _, _ = _tiled(emu.lib, _MIX, W, delta, TC)
+        got32, flags, _ = _tiled(emu.lib, _MIX, W, delta, TC, scale=(0.3, 4.0, 16.0), f32=True)
+    finally:
+        emu.lib.hostemu_set_poison(0)
+    assert np.all(np.isfinite(got))
+    assert np.array_equal(ref.view(np.uint32), got.view(np.uint32))
+    assert np.all(np.isfinite(got32))
