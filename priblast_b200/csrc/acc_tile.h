@@ -578,9 +578,11 @@ struct BiTile {
       }
       // pass B (each lane at its own span): generic interior loops out of the shared-memory tile, walked by
       // loop size: all terms of one size share a tile row, every offset and coefficient is compile-time
+      real bseO_next = cnt > 0 ? c.ld(B_STEMO, list[t] + 2, g - 1) : (real)0;
       for (int k = 0; k < cnt; ++k) {
         const int dp = list[k * TXb + t];
-        const real bseO = c.ld(B_STEMO, dp + 2, g - 1);
+        const real bseO = bseO_next;  // fetched one iteration ahead: the gather latency hides behind the stencil
+        if (k + 1 < cnt) bseO_next = c.ld(B_STEMO, list[(k + 1) * TXb + t] + 2, g - 1);
         const int smax = imin(kMaxLoop, dp - 5);
         const real *base = tile + (dp - 5) * cols + t;
         real a[kMaxLoop];
@@ -609,9 +611,11 @@ struct BiTile {
     const real *bu = K::bulge_tab(*c.T);
     const int delta = c.delta, TXb = ge.TXb, cols = COLS > 0 ? COLS : ge.cols;
     real (&ml)[kMaxLoop + 1] = st.w;
+    real bseB_next = st.cnt > 0 ? c.ld(B_STEMB, list[t] + 2, g - 1) : (real)0;
     for (int k = 0; k < st.cnt; ++k) {
       const int dp = list[k * TXb + t];
-      const real bseB = c.ld(B_STEMB, dp + 2, g - 1);
+      const real bseB = bseB_next;
+      if (k + 1 < st.cnt) bseB_next = c.ld(B_STEMB, list[(k + 1) * TXb + t] + 2, g - 1);
       const int umax = imin(kMaxLoop, dp - 5);
       const real *base = tile + (dp - 5) * cols + t;
 #pragma unroll
@@ -662,9 +666,14 @@ struct BiTile {
           if (dp - 5 >= 4) mr[2] += K::loop_weight(c, T, s, g, dp, te, bse, bseO, bseB, 2, 2);
         }
       }
+      real bseO_next = cnt > 0 ? c.ld(B_STEMO, list[t] + 2, g2 - list[t] - 1) : (real)0;
       for (int k = 0; k < cnt; ++k) {
         const int dp = list[k * TXb + t];
-        const real bseO = c.ld(B_STEMO, dp + 2, g2 - dp - 1);
+        const real bseO = bseO_next;
+        if (k + 1 < cnt) {
+          const int dn = list[(k + 1) * TXb + t];
+          bseO_next = c.ld(B_STEMO, dn + 2, g2 - dn - 1);
+        }
         const int smax = imin(kMaxLoop, dp - 5);
         const real *base = tile + (dp - 5) * cols + t + 31;
         real a[kMaxLoop];
@@ -693,9 +702,14 @@ struct BiTile {
     const real *bu = K::bulge_tab(*c.T);
     const int delta = c.delta, TXb = ge.TXb, cols = COLS > 0 ? COLS : ge.cols;
     real (&mr)[kMaxLoop + 1] = st.w;
+    real bseB_next = st.cnt > 0 ? c.ld(B_STEMB, list[t] + 2, g2 - list[t] - 1) : (real)0;
     for (int k = 0; k < st.cnt; ++k) {
       const int dp = list[k * TXb + t];
-      const real bseB = c.ld(B_STEMB, dp + 2, g2 - dp - 1);
+      const real bseB = bseB_next;
+      if (k + 1 < st.cnt) {
+        const int dn = list[(k + 1) * TXb + t];
+        bseB_next = c.ld(B_STEMB, dn + 2, g2 - dn - 1);
+      }
       const int umax = imin(kMaxLoop, dp - 5);
       const real *base = tile + (dp - 5) * cols + t + 31;
 #pragma unroll
