@@ -265,9 +265,29 @@ def ours(args, rank: int, local_rank: int, world: int) -> None:
             pass
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
         used_state = c1["dp_state_bytes_used"]
+        # the dominant kernel on its own: its share of the algorithmic terms over its own device time
+        phase_terms = {"inside": wk.get("terms_inside_per_nt"), "outside": wk.get("terms_outside_per_nt"),
+                       "biloop_left": None, "biloop_right": None}
+        dom_kernel = {"inside": "k_inside_tile", "outside": "k_outside_tile", "biloop_left": "k_biloop_tile<LEFT>",
+                      "biloop_right": "k_biloop_tile<RIGHT>"}.get(dom, dom)
+        dom_obj = {"phase": dom, "kernel": dom_kernel, "ms_per_launch": phases[dom]}
+        if phase_terms.get(dom):
+            # 6 band variables of this pass = 6 (W-1) reduction outputs per nt
+            ops = (phase_terms[dom] + 6 * (W_SPAN - 1)) * nt_rank
+            dom_obj.update({"sfu_ops_per_nt": phase_terms[dom] + 6 * (W_SPAN - 1),
+                            "achieved": ops / (phases[dom] * 1e-3) / 1e9,
+                            "frac": ops / (phases[dom] * 1e-3) / 1e9 / mufu.value})
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "r1", "traffic.json")) as f:
+                tj = json.load(f)
+            if tj["kernel"].startswith(dom_kernel) and tj["nt_per_launch"] == nt_rank:
+                traffic = tj["dram_bytes_read_per_launch"] + tj["dram_bytes_write_per_launch"]
+        except Exception:
+            pass
         roofline = {
             "bound": "sfu", "achieved": achieved, "peak": mufu.value, "unit": "Gop/s", "frac": achieved / mufu.value,
-            "traffic": None,
+            "traffic": traffic, "dominant_kernel": dom_obj,
             "definition": "algorithmic terms x 1 EX2 + reduction outputs x 1 LG2 per second (SURVEY 8d) over the "
                           "measured MUFU ex2.approx issue peak of this GPU (prib_peak_probe, same run)",
             "sfu_ops_per_nt": wk["sfu_ops_per_nt"], "terms_per_nt": wk["terms_per_nt"],

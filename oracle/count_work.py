@@ -19,18 +19,22 @@ from priblast_b200 import workloads  # noqa: E402
 
 
 def measure(o, seqs, W, delta=5):
-    tot = dict(nt=0, terms=0, loop_energy=0, cells=0, logs=0)
+    tot = dict(nt=0, terms=0, loop_energy=0, cells=0, logs=0, inside=0, outside=0, access=0)
     for s in seqs:
         c = o.count_terms(s.decode(), W, delta)
         tot["nt"] += len(s)
         tot["terms"] += c["lse_inside"] + c["lse_outside"] + c["lse_access"] + c["expd_access"]
+        tot["inside"] += c["lse_inside"]
+        tot["outside"] += c["lse_outside"]
+        tot["access"] += c["lse_access"] + c["expd_access"]
         tot["loop_energy"] += c["loop_energy"]
         tot["cells"] += c["cells"]
         tot["logs"] += c["final_logs"]
     nt = tot["nt"]
     red = 14 * (W - 1) + tot["logs"] / nt
     return dict(sample_nt=nt, sample_seqs=len(seqs), terms_per_nt=tot["terms"] / nt,
-                reductions_per_nt=red, loop_energy_calls_per_nt=tot["loop_energy"] / nt,
+                reductions_per_nt=red, terms_inside_per_nt=tot["inside"] / nt, terms_outside_per_nt=tot["outside"] / nt,
+                terms_access_per_nt=tot["access"] / nt, loop_energy_calls_per_nt=tot["loop_energy"] / nt,
                 cells_per_nt=tot["cells"] / nt,
                 sfu_ops_per_nt=tot["terms"] / nt + red, fp32_instr_per_nt=6 * tot["terms"] / nt)
 

@@ -564,16 +564,23 @@ struct BiTile {
       const int dpmax = imin(W - 1, L - 1 - i);
       // pass A (all lanes at the same span): list the closing spans, add bulges (u2 = 0) and, for
       // delta == 2, the 2x1 / 2x2 special loops
-      for (int dp = delta + 5; dp <= dpmax; ++dp) {
-        const real bse = c.ld(B_STEM, dp + 2, g - 1);
-        if (bse == 0) continue;
-        list[cnt * TXb + t] = (uint8_t)dp;
-        ++cnt;
-        if (delta == 2) {
-          const int te = T.bp[s[0]][s[dp + 1]];
-          const real bseO = c.ld(B_STEMO, dp + 2, g - 1), bseB = c.ld(B_STEMB, dp + 2, g - 1);
-          if (dp - 5 >= 3) ml[2] += K::loop_weight(c, T, s, g, dp, te, bse, bseO, bseB, 2, 1);
-          if (dp - 5 >= 4) ml[2] += K::loop_weight(c, T, s, g, dp, te, bse, bseO, bseB, 2, 2);
+      for (int dp0 = delta + 5; dp0 <= dpmax; dp0 += 8) {
+        real bv[8];  // 8 independent loads in flight (the list update is a serial chain on the loaded values)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) bv[k] = (dp0 + k <= dpmax) ? c.ld(B_STEM, dp0 + k + 2, g - 1) : (real)0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int dp = dp0 + k;
+          const real bse = bv[k];
+          if (bse == 0) continue;
+          list[cnt * TXb + t] = (uint8_t)dp;
+          ++cnt;
+          if (delta == 2) {
+            const int te = T.bp[s[0]][s[dp + 1]];
+            const real bseO = c.ld(B_STEMO, dp + 2, g - 1), bseB = c.ld(B_STEMB, dp + 2, g - 1);
+            if (dp - 5 >= 3) ml[2] += K::loop_weight(c, T, s, g, dp, te, bse, bseO, bseB, 2, 1);
+            if (dp - 5 >= 4) ml[2] += K::loop_weight(c, T, s, g, dp, te, bse, bseO, bseB, 2, 2);
+          }
         }
       }
       // pass B (each lane at its own span): generic interior loops out of the shared-memory tile, walked by
@@ -652,18 +659,25 @@ struct BiTile {
     int cnt = 0;
     if (jp <= L - 1) {
       const int dpmax = imin(W - 1, jp - 1);  // i = jp - dp >= 1
-      for (int dp = delta + 5; dp <= dpmax; ++dp) {
-        const long long g = g2 - dp;  // column of i
-        const real bse = c.ld(B_STEM, dp + 2, g - 1);
-        if (bse == 0) continue;
-        list[cnt * TXb + t] = (uint8_t)dp;
-        ++cnt;
-        if (delta == 2) {
-          const uint8_t *s = c.S + g;
-          const int te = T.bp[s[0]][s[dp + 1]];
-          const real bseO = c.ld(B_STEMO, dp + 2, g - 1), bseB = c.ld(B_STEMB, dp + 2, g - 1);
-          if (dp - 5 >= 3) mr[2] += K::loop_weight(c, T, s, g, dp, te, bse, bseO, bseB, 1, 2);
-          if (dp - 5 >= 4) mr[2] += K::loop_weight(c, T, s, g, dp, te, bse, bseO, bseB, 2, 2);
+      for (int dp0 = delta + 5; dp0 <= dpmax; dp0 += 8) {
+        real bv[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) bv[k] = (dp0 + k <= dpmax) ? c.ld(B_STEM, dp0 + k + 2, g2 - dp0 - k - 1) : (real)0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int dp = dp0 + k;
+          const long long g = g2 - dp;  // column of i
+          const real bse = bv[k];
+          if (bse == 0) continue;
+          list[cnt * TXb + t] = (uint8_t)dp;
+          ++cnt;
+          if (delta == 2) {
+            const uint8_t *s = c.S + g;
+            const int te = T.bp[s[0]][s[dp + 1]];
+            const real bseO = c.ld(B_STEMO, dp + 2, g - 1), bseB = c.ld(B_STEMB, dp + 2, g - 1);
+            if (dp - 5 >= 3) mr[2] += K::loop_weight(c, T, s, g, dp, te, bse, bseO, bseB, 1, 2);
+            if (dp - 5 >= 4) mr[2] += K::loop_weight(c, T, s, g, dp, te, bse, bseO, bseB, 2, 2);
+          }
         }
       }
       real bseO_next = cnt > 0 ? c.ld(B_STEMO, list[t] + 2, g2 - list[t] - 1) : (real)0;
