@@ -1,8 +1,9 @@
 // CUDA kernels (sm_100a) and the C ABI of libpriblast_acc.so.
 //
 // Kernel set:
-//   k_inside_tile / k_outside_tile   tile-persistent span march (acc_tile.h): one CTA per column tile,
-//                                    stencil source rows in shared-memory rings, halo recomputed
+//   k_inside_tile / k_outside_tile   tile-persistent, time-tiled span march (acc_tile.h): one CTA per column
+//                                    tile, stencil source rows in shared-memory rings, halo recomputed,
+//                                    one deep step (kTT spans' long-range sums) per kTT shallow steps
 //   k_outer_scans_warp               the two outer arrays, one warp per sequence
 //   k_biloop_left/right, k_hairpin_suffix, k_finalize   accessibility, one thread per column
 // Every kernel exists for float and double band arithmetic.  The float engine (span-scaled, range
@@ -39,23 +40,30 @@ template <typename real> struct TileMaxThreads { static constexpr int value = si
 // kernels
 // ---------------------------------------------------------------------------------------------
 // grid = resident CTAs (one per SM: the rings take ~all shared memory), blockDim = TC, tiles round-robin.
-// dynamic smem: kTileRows * TC reals + (TC + 16) base codes.
-template <typename real, int R>
-__global__ void __launch_bounds__(TileMaxThreads<real>::value / R, 1)
+// dynamic smem: (kTilePad + kTileRows * TC) reals + hot tables + (TC + 16) base codes.
+template <typename real>
+constexpr size_t tile_smem_bytes() {
+  return ((size_t)kTilePad + (size_t)kTileRows * TileMaxThreads<real>::value) * sizeof(real) +
+         Core<real>::kHotBytes + TileMaxThreads<real>::value + 16;
+}
+
+template <typename real>
+__global__ void __launch_bounds__(TileMaxThreads<real>::value, 1)
 k_inside_tile(typename Core<real>::Ctx c, int TX, long long ntiles, real *scratch) {
   typedef Tile<real> TL;
   constexpr int TC = TileMaxThreads<real>::value;  // compile-time row stride
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int nth = blockDim.x, tq = threadIdx.x, W = c.W;  // nth = TC / R threads, R columns each
-  real *base = reinterpret_cast<real *>(smem_raw);
-  unsigned char *stab = smem_raw + (size_t)kTileRows * TC * sizeof(real);  // hot tables (16-byte aligned)
+  const int t = threadIdx.x, W = c.W;
+  real *base = reinterpret_cast<real *>(smem_raw) + kTilePad;
+  unsigned char *stab = smem_raw + ((size_t)kTilePad + (size_t)kTileRows * TC) * sizeof(real);  // 16-byte aligned
   uint8_t *sS = stab + Core<real>::kHotBytes;
-  for (int k = tq; k < Core<real>::kHotBytes / 4; k += nth)
+  for (int k = t; k < Core<real>::kHotBytes / 4; k += TC)
     reinterpret_cast<uint32_t *>(stab)[k] = reinterpret_cast<const uint32_t *>(c.T)[k];
   const typename Core<real>::SmallTables &T = *reinterpret_cast<const typename Core<real>::SmallTables *>(stab);
   real *scrM1 = scratch + (size_t)blockIdx.x * 2 * (W + 4) * TC;
   real *scrM2 = scrM1 + (size_t)(W + 4) * TC;
   const typename TL::InSmem sm = TL::carve_in(base, TC, sS);
+  const int dfirst = TL::first_group(W);
   for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     typename TL::Geo ge;
     ge.g0 = tile * TX;
@@ -63,33 +71,41 @@ k_inside_tile(typename Core<real>::Ctx c, int TX, long long ntiles, real *scratc
     ge.TX = TX;
     ge.H = W + 1;
     __syncthreads();  // previous tile fully consumed
-    for (int k = tq; k < kTileRows * TC; k += nth) base[k] = 0;
-    for (int k = tq; k < TC + 8; k += nth) sS[k] = (ge.g0 + k < c.NC) ? c.S[ge.g0 + k] : 0;
-    typename TL::ColState cs[R];
-#pragma unroll
-    for (int r = 0; r < R; ++r) TL::col_state(c, ge.g0 + tq * R + r, cs[r]);
+    for (int k = t; k < kTileRows * TC; k += TC) base[k] = 0;
+    for (int k = t; k < TC + 8; k += TC) sS[k] = (ge.g0 + k < c.NC) ? c.S[ge.g0 + k] : 0;
+    typename TL::ColState cs;
+    TL::col_state(c, ge.g0 + t, cs);
     __syncthreads();
-    for (int d = kTurn; d <= W + 1; d++) {
-      TL::template inside_span<R, TC>(c, T, ge, sm, scrM1, scrM2, tq, cs, d);
-      __syncthreads();
+    for (int d0 = dfirst; d0 <= W + 1; d0 += kTT) {
+      real gs[kTT], mb[kTT];
+      TL::template inside_deep<TC>(T, ge, sm, scrM1, scrM2, t, d0, gs, mb);
+#pragma unroll
+      for (int k = 0; k < kTT; ++k) {
+        if (d0 + k >= kTurn) {  // uniform
+          TL::template inside_shallow<TC>(c, T, ge, sm, scrM1, scrM2, t, cs, d0 + k, gs[k], mb[k]);
+          __syncthreads();
+        }
+      }
     }
   }
 }
 
-template <typename real, int R>
-__global__ void __launch_bounds__(TileMaxThreads<real>::value / R, 1)
+template <typename real>
+__global__ void __launch_bounds__(TileMaxThreads<real>::value, 1)
 k_outside_tile(typename Core<real>::Ctx c, int TX, long long ntiles, real *scratch) {
   typedef Tile<real> TL;
   constexpr int TC = TileMaxThreads<real>::value;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int nth = blockDim.x, tq = threadIdx.x, W = c.W;
-  real *base = reinterpret_cast<real *>(smem_raw);
-  unsigned char *stab = smem_raw + (size_t)kTileRows * TC * sizeof(real);
-  for (int k = tq; k < Core<real>::kHotBytes / 4; k += nth)
+  const int t = threadIdx.x, W = c.W;
+  real *pad = reinterpret_cast<real *>(smem_raw);
+  real *base = pad + kTilePad;
+  unsigned char *stab = smem_raw + ((size_t)kTilePad + (size_t)kTileRows * TC) * sizeof(real);
+  for (int k = t; k < Core<real>::kHotBytes / 4; k += TC)
     reinterpret_cast<uint32_t *>(stab)[k] = reinterpret_cast<const uint32_t *>(c.T)[k];
   const typename Core<real>::SmallTables &T = *reinterpret_cast<const typename Core<real>::SmallTables *>(stab);
   real *scrBif = scratch + (size_t)blockIdx.x * 2 * (W + 4) * TC;
   const typename TL::OutSmem sm = TL::carve_out(base, TC);
+  const int dlast = TL::first_group(W);  // the groups of the inside pass, walked downwards
   for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     typename TL::Geo ge;
     ge.g0 = tile * TX;
@@ -97,16 +113,23 @@ k_outside_tile(typename Core<real>::Ctx c, int TX, long long ntiles, real *scrat
     ge.TX = TX;
     ge.H = W + 1;
     __syncthreads();
-    for (int k = tq; k < kTileRows * TC; k += nth) base[k] = 0;
-    typename TL::ColState cs[R];
-#pragma unroll
-    for (int r = 0; r < R; ++r) TL::col_state(c, ge.g0 - ge.H + tq * R + r, cs[r]);
+    for (int k = t; k < kTilePad + kTileRows * TC; k += TC) pad[k] = 0;
+    typename TL::ColState cs;
+    TL::col_state(c, ge.g0 - ge.H + t, cs);
     __syncthreads();
     int slot = (W + 1) % kRingOut;
-    for (int d = W + 1; d >= kTurn; d--) {
-      TL::template outside_span<R, TC>(c, T, ge, sm, scrBif, tq, cs, d, slot);
-      slot = slot == 0 ? kRingOut - 1 : slot - 1;
-      __syncthreads();
+    for (int d0 = W + 1; d0 >= dlast + kTT - 1; d0 -= kTT) {
+      typename TL::OutDeep o;
+      TL::template outside_deep<TC>(c, T, ge, sm, scrBif, t, cs, d0, slot, o);
+#pragma unroll
+      for (int k = 0; k < kTT; ++k) {
+        if (d0 - k >= kTurn) {  // uniform
+          TL::template outside_shallow<TC>(c, T, ge, sm, scrBif, t, cs, d0 - k, slot, o.gs[k], o.bs[k], o.bm1[k],
+                                           o.ks[k]);
+          __syncthreads();
+        }
+        slot = slot == 0 ? kRingOut - 1 : slot - 1;
+      }
     }
   }
 }
@@ -358,7 +381,6 @@ struct prib_ctx {
   prib_acc_params prm{};
   int W = 70, delta = 5;
   bool use_fp32 = true;
-  int cols_per_thread = 1;  // register tiling of the stencils (PRIB_COLS=1|2|4); measured: 1 is fastest (latency-bound)
   cudaStream_t own_stream = nullptr, stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk0 = nullptr, evk1 = nullptr;
   cudaEvent_t evp[PRIB_NUM_PHASES + 1] = {};
@@ -569,16 +591,12 @@ int run_batch(prib_ctx *c, const Batch &b, bool timed) {
   const long long ntiles = (b.NC + TX - 1) / TX;
   const int tgrid = (int)std::min<long long>(ntiles, c->grid_tiles);
   real *scratch = reinterpret_cast<real *>(c->d_tile_scratch);
-  if (c->cols_per_thread == 4) k_inside_tile<real, 4><<<tgrid, e.TC / 4, e.tile_smem, st>>>(k, TX, ntiles, scratch);
-  else if (c->cols_per_thread == 2) k_inside_tile<real, 2><<<tgrid, e.TC / 2, e.tile_smem, st>>>(k, TX, ntiles, scratch);
-  else k_inside_tile<real, 1><<<tgrid, e.TC, e.tile_smem, st>>>(k, TX, ntiles, scratch);
+  k_inside_tile<real><<<tgrid, e.TC, e.tile_smem, st>>>(k, TX, ntiles, scratch);
   if (timed) CU(cudaEventRecord(c->evp[2], st));
   k_outer_scans_warp<real><<<(b.n + kScanWarps - 1) / kScanWarps, 32 * kScanWarps,
                              (size_t)kScanWarps * (c->W + 2) * 32 * sizeof(real), st>>>(k);
   if (timed) CU(cudaEventRecord(c->evp[3], st));
-  if (c->cols_per_thread == 4) k_outside_tile<real, 4><<<tgrid, e.TC / 4, e.tile_smem, st>>>(k, TX, ntiles, scratch);
-  else if (c->cols_per_thread == 2) k_outside_tile<real, 2><<<tgrid, e.TC / 2, e.tile_smem, st>>>(k, TX, ntiles, scratch);
-  else k_outside_tile<real, 1><<<tgrid, e.TC, e.tile_smem, st>>>(k, TX, ntiles, scratch);
+  k_outside_tile<real><<<tgrid, e.TC, e.tile_smem, st>>>(k, TX, ntiles, scratch);
   if (timed) CU(cudaEventRecord(c->evp[4], st));
   const unsigned bgrid = (unsigned)((b.NC + e.TXb - 1) / e.TXb);
   launch_biloop<real, true>(k, bgrid, e.TXb, e.bi_smem, st);
@@ -628,17 +646,13 @@ int setup_engine(prib_ctx *c, const ScaleSpec &spec, size_t smem_max, std::strin
   // tile width is a compile-time constant of the kernels (row strides become immediates); it is sized
   // for the 227 KB opt-in shared memory of sm_100
   const int TC = TileMaxThreads<real>::value;
-  if ((size_t)kTileRows * TC * sizeof(real) + Core<real>::kHotBytes + TC + 16 > smem_max)
+  if (tile_smem_bytes<real>() > smem_max)
     return fail(PRIB_ECUDA, "this GPU has less opt-in shared memory than the sm_100a tile kernels need");
   if (TC < c->W + 34) return fail(PRIB_ECUDA, "tile narrower than the span halo");
   e.TC = TC;
-  e.tile_smem = (size_t)kTileRows * TC * sizeof(real) + Core<real>::kHotBytes + TC + 16;
-  CU(cudaFuncSetAttribute((k_inside_tile<real, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
-  CU(cudaFuncSetAttribute((k_outside_tile<real, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
-  CU(cudaFuncSetAttribute((k_inside_tile<real, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
-  CU(cudaFuncSetAttribute((k_outside_tile<real, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
-  CU(cudaFuncSetAttribute((k_inside_tile<real, 4>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
-  CU(cudaFuncSetAttribute((k_outside_tile<real, 4>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+  e.tile_smem = tile_smem_bytes<real>();
+  CU(cudaFuncSetAttribute(k_inside_tile<real>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+  CU(cudaFuncSetAttribute(k_outside_tile<real>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
   // interior-loop tiles: the widest block (<= 512 threads) whose Alpha_stemI tile + span lists fit
   const int rows = c->W - 5 > 0 ? c->W - 5 : 0;
   int TXb = 512;
@@ -699,10 +713,6 @@ int prib_acc_create(prib_ctx **out, const prib_acc_params *params) {
   c->prm = *params;
   c->W = params->maximal_span;
   c->delta = params->min_accessible_length;
-  if (const char *ce = getenv("PRIB_COLS")) {
-    const int v = atoi(ce);
-    if (v == 1 || v == 2 || v == 4) c->cols_per_thread = v;
-  }
   const char *pe = getenv("PRIB_PRECISION");
   c->use_fp32 = params->mode == 0 && c->W <= kFp32MaxSpan && !(pe && strcmp(pe, "fp64") == 0);
   auto bail = [&](int code) {

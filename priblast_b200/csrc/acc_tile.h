@@ -1,27 +1,35 @@
-// Tile-persistent span march (kernel set v2).
+// Tile-persistent span march (kernel set v3).
 //
 // One CTA owns TX consecutive columns of the batch and walks ALL spans for them, keeping the source rows
-// of the 2-D stencils in shared-memory ring buffers, so a stencil term is one LDS + one FMA and nothing
-// is re-read from HBM.  Because a cell (i, d) only depends on sub-intervals of [i, i+d] (inside) or on
-// super-intervals within the band (outside), a CTA that also carries a halo of W+1 columns on the right
-// (inside) or on the left (outside) can recompute everything its owned cells need without talking to
-// its neighbours: no grid-wide synchronisation, one __syncthreads per span.
+// of the 2-D stencils in shared-memory ring buffers, so nothing is re-read from HBM.  Because a cell (i, d)
+// only depends on sub-intervals of [i, i+d] (inside) or on super-intervals within the band (outside), a CTA
+// that also carries a halo of W+1 columns on the right (inside) or on the left (outside) can recompute
+// everything its owned cells need without talking to its neighbours: no grid-wide synchronisation.
 //
-// The functions below are the per-thread, per-span bodies (thread t = local column t of the tile); the
-// CUDA kernels and the host emulation both call them span by span with a barrier in between.
-// Summation order inside a cell is identical to acc_core.h's v1 cell functions, so both give the same
-// bits in the same precision (checked by tests/test_hostemu.py).
+// Time tiling.  The long-range sums of a cell (generic interior loops: ~435 terms, multibranch splits,
+// long bulges) only read rows that are at least kTT spans away from the cell, so the sums of kTT
+// consecutive spans can be evaluated TOGETHER from the rows that exist before the first of them is
+// produced: one "deep" step loads every source element once and feeds kTT accumulators (kTT FMAs per
+// shared-memory load instead of one), then kTT "shallow" steps finish the cells span by span (stack,
+// 1-nt bulges, 1x1/1x2/2x1/2x2 loops, multiloop bookkeeping) with a __syncthreads in between.
+//
+// The functions below are the per-thread bodies (thread t = local column t of the tile); the CUDA kernels
+// and the host emulation (tests/hostemu) both call them.  The order of additions inside a cell is
+// identical to acc_core.h's one-cell-at-a-time functions, so both give the same bits in the same
+// precision (checked by tests/test_hostemu.py).
 #pragma once
 #include "acc_core.h"
 
 namespace prib {
 
 enum {
+  kTT = 4,         // spans per deep step
   kRingIn = 32,    // inside: source rows d-30..d-1 plus the row being written
   kRingOut = 34,   // outside: source rows d+1..d+32 plus the row being written
   kRingStem = 8,
   kRingSE = 4,
   kTileRows = 80,  // shared-memory rows of TC reals per CTA (both passes)
+  kTilePad = 64,   // zeroed reals in front of the rings: the outside stencils look up to 33 columns to the left
 };
 
 template <typename real>
@@ -59,7 +67,11 @@ struct Tile {
     return k == 0 ? g0 : k == 1 ? g1 : k == 2 ? g2 : k == 3 ? g3 : k == 4 ? g4 : k == 5 ? g5 : g6;
   }
 
-  // ---- shared-memory carve-up (same 80 rows for both passes) -----------------------------------
+  // first span of the first deep step: groups of kTT spans that END exactly at W + 1 (spans below kTurn
+  // are skipped by the callers)
+  static PRIB_HD int first_group(int W) { return W + 2 - ((W + 2 - kTurn + kTT - 1) / kTT) * kTT; }
+
+  // ---- shared-memory carve-up (same kTileRows rows for both passes; base points past the zero pad) ----
   struct InSmem {
     real *stemI, *stemB, *stem, *se, *mu, *m2;
     const uint8_t *S;  // bases of local columns 0 .. TC+3
@@ -88,110 +100,128 @@ struct Tile {
     return s;
   }
 
-  // R consecutive reals from shared memory with one vector load (p aligned to R * sizeof(real))
-  template <int R>
-  static PRIB_HD void load_vec(const real *p, real (&v)[R]) {
-#if defined(__CUDA_ARCH__)
-    if (R == 4 && sizeof(real) == 4) {
-      const float4 q = *reinterpret_cast<const float4 *>(p);
-      v[0] = (real)q.x; v[1] = (real)q.y; v[2 % R] = (real)q.z; v[3 % R] = (real)q.w;
-      return;
-    }
-    if (R == 2 && sizeof(real) == 4) {
-      const float2 q = *reinterpret_cast<const float2 *>(p);
-      v[0] = (real)q.x; v[1 % R] = (real)q.y;
-      return;
-    }
-    if (R == 2 && sizeof(real) == 8) {
-      const double2 q = *reinterpret_cast<const double2 *>(p);
-      v[0] = (real)q.x; v[1 % R] = (real)q.y;
-      return;
-    }
-#endif
+  // One source row of the inside generic stencil (row d0 - S of the Alpha_stemI ring) for all kTT targets;
+  // S is a template parameter so that every coefficient choice and column offset is resolved at compile
+  // time (a plain `#pragma unroll` nest of this size is not unrolled by nvcc).
+  template <int S, int TCC>
+  static PRIB_HD void in_rows(const InSmem &sm, int TC, int t, int d0, const real *cf, real g0, real g1, real g2,
+                              real g3, real g4, real g5, real g6, real (&gs)[kTT]) {
+    if (d0 - S >= 5) {  // rows below span 5 hold no stems; same cut as `sum <= min(30, d - 5)` per target
+      const real *row = sm.stemI + ((d0 - S) & (kRingIn - 1)) * (TCC > 0 ? TCC : TC) + t;
+      real rs[kTT];
 #pragma unroll
-    for (int r = 0; r < R; ++r) v[r] = p[r];
+      for (int k = 0; k < kTT; ++k) rs[k] = 0;
+#pragma unroll
+      for (int x = 1; x <= S + kTT - 2; ++x) {  // x = u1; target k takes it while x <= (S + k) - 1
+        const real v = row[x];
+#pragma unroll
+        for (int k = 0; k < kTT; ++k) {
+          const int sum = S + k;
+          if (sum >= 4 && sum <= kMaxLoop && x <= sum - 1 && !(sum == 4 && x == 2))
+            rs[k] += gsel(K::gidx(x, sum), g0, g1, g2, g3, g4, g5, g6) * v;
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < kTT; ++k)
+        if (S + k >= 4 && S + k <= kMaxLoop) gs[k] += cf[S + k] * rs[k];
+    }
+    if constexpr (S < kMaxLoop) in_rows<S + 1, TCC>(sm, TC, t, d0, cf, g0, g1, g2, g3, g4, g5, g6, gs);
   }
 
   // ---------------------------------------------------------------------------------------------
-  // inside: thread tq owns the R consecutive local columns tq*R .. tq*R+R-1 (cells (i, i+d)).
-  // scrM1/scrM2: per-CTA global scratch, [(W+4)][TC].  The generic-loop stencil is evaluated jointly for
-  // the R cells: every source element is loaded once (vector LDS) and used by up to R targets, each
-  // target still adds its terms in ascending u1, so the result is bit-identical for every R.
+  // inside, deep step: thread t = local column t; targets are the cells (i, i + d0 + k), k = 0..kTT-1.
+  //   gs[k] = generic interior loops of Alpha_stemend (raccess.cpp:201-215, 808-812) as a stencil over the
+  //           Alpha_stemI ring: source row d0 - s serves target k with loop size s + k;
+  //   mb[k] = Alpha_multibif (:131-143) from the per-CTA scratch rows scrM1 / scrM2 ([(W+4)][TC]).
+  // Only rows <= d0 - 1 are read, so all kTT targets are legal at once.  TCC: compile-time tile width
+  // (0 = ge.TC at run time, host emulation): every ring row offset becomes an immediate.
   // ---------------------------------------------------------------------------------------------
-  // TCC: compile-time tile width (0 = take ge.TC at run time, used by the host emulation): with a constant
-  // row stride every ring / scratch row offset becomes an immediate of the load instruction.
-  template <int R, int TCC = 0>
-  static PRIB_HD void inside_span(const Ctx &c, const ST &T, const Geo &ge, const InSmem &sm, real *scrM1,
-                                  real *scrM2, int tq, const ColState (&cs)[R], int d) {
-    const int TC = TCC > 0 ? TCC : ge.TC, c0 = tq * R;
-    const real *bu = K::bulge_tab(T), *cf = K::cf_tab(T);
+  template <int TCC = 0>
+  static PRIB_HD void inside_deep(const ST &T, const Geo &ge, const InSmem &sm, const real *scrM1, const real *scrM2,
+                                  int t, int d0, real (&gs)[kTT], real (&mb)[kTT]) {
+    const int TC = TCC > 0 ? TCC : ge.TC;
+    const real *cf = K::cf_tab(T);
     const real g0 = T.cg[0], g1 = T.cg[1], g2 = T.cg[2], g3 = T.cg[3], g4 = T.cg[4], g5 = T.cg[5], g6 = T.cg[6];
-    real stem[R], stemI[R], stemB[R], stemD[R], se[R], mu[R], m1[R], m2[R], acc[R], gs[R];
-    int te[R];
-    bool any = false;
-    const int smax = imin(kMaxLoop, d - 5);  // u1 + u2 <= smax keeps the inner span >= 5
 #pragma unroll
-    for (int r = 0; r < R; ++r) {
-      const int t = c0 + r;
-      const int L = cs[r].L, i = cs[r].i, j = i + d;
-      stem[r] = stemI[r] = stemB[r] = stemD[r] = se[r] = mu[r] = m1[r] = m2[r] = acc[r] = gs[r] = 0;
-      te[r] = 0;
-      const bool live = i >= 0 && j <= L && t + d <= TC - 1;
-      if (!live) continue;
+    for (int k = 0; k < kTT; ++k) gs[k] = mb[k] = 0;
+    in_rows<1, TCC>(sm, TC, t, d0, cf, g0, g1, g2, g3, g4, g5, g6, gs);
+    // multibif: mb[k] = sum over m = 5 .. d0+k-5 of multi1[m][t] * multi2[d0+k-m][t+m]; a multi1 element
+    // serves all kTT targets.  Two running pointers, every other offset is an immediate.
+    {
+      const real *pa = scrM1 + 5 * TC + t;                       // multi1[m][t]
+      const real *pb = scrM2 + (long long)(d0 - 5) * TC + t + 5;  // multi2[d0 - m][t + m]; target k: pb[k * TC]
+      int m = 5;
+      for (; m + 1 <= d0 - 5; m += 2) {  // two m per round, 10 independent loads in flight
+        const real a0 = pa[0], a1 = pa[TC];
+        real b0[kTT], b1[kTT];
+#pragma unroll
+        for (int k = 0; k < kTT; ++k) {
+          b0[k] = pb[k * TC];
+          b1[k] = pb[k * TC - (TC - 1)];
+        }
+#pragma unroll
+        for (int k = 0; k < kTT; ++k) {
+          mb[k] += a0 * b0[k];
+          mb[k] += a1 * b1[k];
+        }
+        pa += 2 * TC;
+        pb -= 2 * (TC - 1);
+      }
+      for (; m <= d0 + kTT - 1 - 5; ++m) {  // tail: targets drop out one by one (rows below 5 do not exist)
+        const real a = pa[0];
+#pragma unroll
+        for (int k = 0; k < kTT; ++k)
+          if (m <= d0 + k - 5) mb[k] += a * pb[k * TC];
+        pa += TC;
+        pb -= TC - 1;
+      }
+    }
+  }
+
+  // ---------------------------------------------------------------------------------------------
+  // inside, shallow step: finishes cell (i, i + d) of column t given its deep sums gs / mb.
+  // ---------------------------------------------------------------------------------------------
+  template <int TCC = 0>
+  static PRIB_HD void inside_shallow(const Ctx &c, const ST &T, const Geo &ge, const InSmem &sm, real *scrM1,
+                                     real *scrM2, int t, const ColState &cs, int d, real gs, real mb) {
+    const int TC = TCC > 0 ? TCC : ge.TC;
+    const real *bu = K::bulge_tab(T);
+    real stem = 0, stemI = 0, stemB = 0, stemD = 0, se = 0, mu = 0, m1 = 0, m2 = 0;
+    const int smax = imin(kMaxLoop, d - 5);  // u1 + u2 <= smax keeps the inner span >= 5
+    const int L = cs.L, i = cs.i, j = i + d;
+    const bool live = i >= 0 && j <= L && t + d <= TC - 1;
+    if (live) {
       const uint8_t *s = sm.S + t;
       const int si = s[0], si1 = s[1], sj = s[d], sj1 = s[d + 1];
       const int tp = T.bp[si1][sj];
       if (tp) {
         const int t2 = T.bp[s[2]][s[d - 1]];
-        stem[r] = T.k2 * (sm.se[((d - 2) & (kRingSE - 1)) * TC + t + 1] +
-                          sm.stem[((d - 2) & (kRingStem - 1)) * TC + t + 1] * T.e_stack[tp][T.rt[t2]]);
-      }
-      real mb = 0;
-      {
-        const real *pa = scrM1 + 5 * TC + t, *pb = scrM2 + (d - 5) * TC + t + 5;
-        int m = 5;
-        for (; m + 7 <= d - 5; m += 8) {  // 16 loads in flight; same order of additions as the plain loop
-          real av[8], bv[8];
-#pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            av[k] = pa[k * TC];
-            bv[k] = pb[-k * (TC - 1)];
-          }
-#pragma unroll
-          for (int k = 0; k < 8; ++k) mb += av[k] * bv[k];
-          pa += 8 * TC;
-          pb -= 8 * (TC - 1);
-        }
-        for (; m <= d - 5; ++m) {
-          mb += pa[0] * pb[0];
-          pa += TC;
-          pb -= TC - 1;
-        }
+        stem = T.k2 * (sm.se[((d - 2) & (kRingSE - 1)) * TC + t + 1] +
+                       sm.stem[((d - 2) & (kRingStem - 1)) * TC + t + 1] * T.e_stack[tp][T.rt[t2]]);
       }
       mb *= T.inv_cA;
-      stemD[r] = tp ? stem[r] * K::e_dangle(T, tp, i > 0, si, j < L, sj1) : 0;
-      m2[r] = stemD[r] * T.e_mlintern + sm.m2[((d - 1) & 1) * TC + t] * T.e_mlbase;
-      m1[r] = m2[r] + mb;
-      mu[r] = sm.mu[((d - 1) & 1) * TC + t + 1] * T.e_mlbase + mb;
+      stemD = tp ? stem * K::e_dangle(T, tp, i > 0, si, j < L, sj1) : 0;
+      m2 = stemD * T.e_mlintern + sm.m2[((d - 1) & 1) * TC + t] * T.e_mlbase;
+      m1 = m2 + mb;
+      mu = sm.mu[((d - 1) & 1) * TC + t + 1] * T.e_mlbase + mb;
       if (tp) {
-        stemI[r] = stem[r] * T.e_mmI[T.rt[tp]][sj1][si];
-        stemB[r] = stem[r] * T.tau[tp];
+        stemI = stem * T.e_mmI[T.rt[tp]][sj1][si];
+        stemB = stem * T.tau[tp];
       }
-      te[r] = (j != L) ? T.bp[si][sj1] : 0;
-      if (te[r]) {
-        any = true;
-        real a = T.e_hairpin[d] * (d != 3 ? T.e_mmH[te[r]][si1][sj] : T.tau[te[r]]);
+      const int te = (j != L) ? T.bp[si][sj1] : 0;
+      if (te) {
+        real a = T.e_hairpin[d] * (d != 3 ? T.e_mmH[te][si1][sj] : T.tau[te]);
         const real *st1 = sm.stem + ((d - 1) & (kRingStem - 1)) * TC + t;
         const real *st2 = sm.stem + ((d - 2) & (kRingStem - 1)) * TC + t;
         const real *st3 = sm.stem + ((d - 3) & (kRingStem - 1)) * TC + t;
         const real *st4 = sm.stem + ((d - 4) & (kRingStem - 1)) * TC + t;
         if (smax >= 1) {
-          a += bu[1] * (st1[1] * T.e_stack[te[r]][T.rt[T.bp[s[2]][sj]]] +
-                        st1[0] * T.e_stack[te[r]][T.rt[T.bp[si1][s[d - 1]]]]);
+          a += bu[1] * (st1[1] * T.e_stack[te][T.rt[T.bp[s[2]][sj]]] +
+                        st1[0] * T.e_stack[te][T.rt[T.bp[si1][s[d - 1]]]]);
         }
         if (smax >= 2) {
           const int t2 = T.rt[T.bp[s[2]][s[d - 1]]];
-          a += st2[1] * c.e_int11[idx11(te[r], t2, si1, sj)];
+          a += st2[1] * c.e_int11[idx11(te, t2, si1, sj)];
           real bs = 0;
 #pragma unroll
           for (int u = 2; u <= kMaxLoop; ++u) {
@@ -200,118 +230,214 @@ struct Tile {
               bs += bu[u] * (row[u] + row[0]);
             }
           }
-          a += T.tau[te[r]] * bs;
+          a += T.tau[te] * bs;
         }
         if (smax >= 3) {
           const int ta = T.rt[T.bp[s[2]][s[d - 2]]];
-          a += st3[1] * c.e_int21[idx21(te[r], ta, si1, s[d - 1], sj)];
+          a += st3[1] * c.e_int21[idx21(te, ta, si1, s[d - 1], sj)];
           const int tb = T.rt[T.bp[s[3]][s[d - 1]]];
-          a += st3[2] * c.e_int21[idx21(tb, te[r], sj, si1, s[2])];
+          a += st3[2] * c.e_int21[idx21(tb, te, sj, si1, s[2])];
         }
         if (smax >= 4) {
           const int tc = T.rt[T.bp[s[3]][s[d - 2]]];
-          a += st4[2] * c.e_int22[idx22(te[r], tc, si1, s[2], s[d - 1], sj)];
+          a += st4[2] * c.e_int22[idx22(te, tc, si1, s[2], s[d - 1], sj)];
+          a += T.e_mmI[te][si1][sj] * gs;
         }
-        acc[r] = a;
+        const int tt = T.rt[te];
+        a += mu * T.e_mlclose * T.e_d3[tt][si1] * T.e_d5[tt][sj];
+        se = a;
       }
     }
-    // generic interior loops: joint stencil over A_STEMI, fully unrolled.  Local column c0 + x of row
-    // d - sum is source u1 = x - r of target r; weights depend on |u1 - u2| only (7 register values)
-    // times one factor per loop size, so a term is one FMA and 1/R of a vector LDS.
-    if (any && smax >= 4) {
-#pragma unroll
-      for (int sum = 4; sum <= kMaxLoop; ++sum) {
-        if (sum <= smax) {
-          const real *row = sm.stemI + ((d - sum) & (kRingIn - 1)) * TC + c0;
-          real rs[R];
-#pragma unroll
-          for (int r = 0; r < R; ++r) rs[r] = 0;
-#pragma unroll
-          for (int xb = 0; xb <= sum + R - 2; xb += R) {
-            real v[R];
-            load_vec<R>(row + xb, v);
-#pragma unroll
-            for (int k = 0; k < R; ++k) {
-              const int x = xb + k;
-#pragma unroll
-              for (int r = 0; r < R; ++r) {
-                const int u1 = x - r;
-                if (u1 >= 1 && u1 <= sum - 1 && !(sum == 4 && u1 == 2))
-                  rs[r] += gsel(K::gidx(u1, sum), g0, g1, g2, g3, g4, g5, g6) * v[k];
-              }
-            }
-          }
-#pragma unroll
-          for (int r = 0; r < R; ++r) gs[r] += cf[sum] * rs[r];
-        }
-      }
-    }
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-      const int t = c0 + r;
-      const int L = cs[r].L, i = cs[r].i, j = i + d;
-      if (te[r]) {
-        const uint8_t *s = sm.S + t;
-        const int si1 = s[1], sj = s[d];
-        real a = acc[r];
-        if (smax >= 4) a += T.e_mmI[te[r]][si1][sj] * gs[r];
-        const int tt = T.rt[te[r]];
-        a += mu[r] * T.e_mlclose * T.e_d3[tt][si1] * T.e_d5[tt][sj];
-        se[r] = a;
-      }
-      // every column refreshes its ring slots every span (zeros where the cell does not exist)
-      sm.stemI[(d & (kRingIn - 1)) * TC + t] = stemI[r];
-      sm.stemB[(d & (kRingIn - 1)) * TC + t] = stemB[r];
-      sm.stem[(d & (kRingStem - 1)) * TC + t] = stem[r];
-      sm.se[(d & (kRingSE - 1)) * TC + t] = se[r];
-      sm.mu[(d & 1) * TC + t] = mu[r];
-      sm.m2[(d & 1) * TC + t] = m2[r];
-      scrM1[d * TC + t] = m1[r];
-      scrM2[d * TC + t] = m2[r];
-      // persistent outputs: owned columns only
-      if (t < ge.TX && i >= 0 && j <= L) {
-        const long long g = ge.g0 + t;
-        c.at(A_STEM, d, g) = stem[r];
-        c.at(A_STEMI, d, g) = stemI[r];
-        c.at(A_STEMB, d, g) = stemB[r];
-        c.at(A_STEMD, d, g) = stemD[r];
-        c.at(A_STEMDE, d, g + d) = stemD[r];
-        c.at(A_MULTI, d, g) = mu[r];
-        c.at(A_MULTI1, d, g) = m1[r];
-        c.at(A_MULTI2, d, g) = m2[r];
-        if (!(K::in_safe_range(stem[r]) && K::in_safe_range(se[r]) && K::in_safe_range(mu[r]) &&
-              K::in_safe_range(m1[r]) && K::in_safe_range(m2[r])))
-          c.flags[cs[r].sq] = 1;
-      }
+    // every column refreshes its ring slots every span (zeros where the cell does not exist)
+    sm.stemI[(d & (kRingIn - 1)) * TC + t] = stemI;
+    sm.stemB[(d & (kRingIn - 1)) * TC + t] = stemB;
+    sm.stem[(d & (kRingStem - 1)) * TC + t] = stem;
+    sm.se[(d & (kRingSE - 1)) * TC + t] = se;
+    sm.mu[(d & 1) * TC + t] = mu;
+    sm.m2[(d & 1) * TC + t] = m2;
+    scrM1[d * TC + t] = m1;
+    scrM2[d * TC + t] = m2;
+    // persistent outputs: owned columns only
+    if (t < ge.TX && i >= 0 && j <= L) {
+      const long long g = ge.g0 + t;
+      c.at(A_STEM, d, g) = stem;
+      c.at(A_STEMI, d, g) = stemI;
+      c.at(A_STEMB, d, g) = stemB;
+      c.at(A_STEMD, d, g) = stemD;
+      c.at(A_STEMDE, d, g + d) = stemD;
+      c.at(A_MULTI, d, g) = mu;
+      c.at(A_MULTI1, d, g) = m1;
+      c.at(A_MULTI2, d, g) = m2;
+      if (!(K::in_safe_range(stem) && K::in_safe_range(se) && K::in_safe_range(mu) && K::in_safe_range(m1) &&
+            K::in_safe_range(m2)))
+        c.flags[cs.sq] = 1;
     }
   }
 
   // ---------------------------------------------------------------------------------------------
-  // outside: thread tq owns local columns tq*R .. tq*R+R-1; cell (p, p + d); global column g0 - H + t.
-  // scrBif: per-CTA global scratch for Beta_multibif, [(W+4)][TC].
+  // outside: thread t = local column t, global column g0 - H + t; cell (p, p + d).  Spans descend.
+  // Deep step at d0 serves the targets d0 - k, k = 0..kTT-1, from rows >= d0 + 1:
+  //   gs[k]  generic interior loops of Beta_stem (raccess.cpp:373-386) over the Beta_stemO ring: source row
+  //          d0 + s serves target k with loop size s + k - 2;
+  //   bs[k]  bulges longer than 1 nt over the Beta_stemB ring (:788-795 seen from the inner pair);
+  //   bm1[k] Beta_multi1 (:310-324) and ks[k], the k-loop of Beta_multi2 (:339-349), from the per-CTA
+  //          Beta_multibif scratch scrBif ([(W+4)][TC]) and the Alpha arrays in HBM.
   // ---------------------------------------------------------------------------------------------
   static PRIB_HD int wrap_out(int r) { return r >= kRingOut ? r - kRingOut : r; }
 
-  template <int R, int TCC = 0>
-  static PRIB_HD void outside_span(const Ctx &c, const ST &T, const Geo &ge, const OutSmem &sm, real *scrBif,
-                                   int tq, const ColState (&cs)[R], int d, int slot_d /* = d % kRingOut */) {
-    const int TC = TCC > 0 ? TCC : ge.TC, W = c.W, c0 = tq * R;
+  struct OutDeep {
+    real gs[kTT], bs[kTT], bm1[kTT], ks[kTT];
+  };
+
+  // One source row (d0 + S of the Beta_stemO / Beta_stemB rings) of the outside stencils for all kTT targets.
+  template <int S, int TCC>
+  static PRIB_HD void out_rows(const OutSmem &sm, int TC, int t, int d0, int slot_d0, int W, const real *bu,
+                               const real *cf, real g0, real g1, real g2, real g3, real g4, real g5, real g6,
+                               OutDeep &o) {
+    if (d0 + S <= W + 1) {  // same cut as `sum <= min(30, W - 1 - d)` per target
+      const int slot = wrap_out(slot_d0 + S);
+      const real *rowB = sm.stemB + slot * (TCC > 0 ? TCC : TC) + t - 1;
+      const real *rowO = sm.stemO + slot * (TCC > 0 ? TCC : TC) + t - 1;
+      const real b0 = rowB[0];
+#pragma unroll
+      for (int k = 0; k < kTT; ++k) {
+        const int u = S + k - 2;
+        if (u >= 2 && u <= kMaxLoop) o.bs[k] += bu[u] * (rowB[-u] + b0);
+      }
+      real rs[kTT];
+#pragma unroll
+      for (int k = 0; k < kTT; ++k) rs[k] = 0;
+#pragma unroll
+      for (int y = 1; y <= S + kTT - 4; ++y) {  // y = u1: source column t - 1 - u1
+        const real v = rowO[-y];
+#pragma unroll
+        for (int k = 0; k < kTT; ++k) {
+          const int sum = S + k - 2;
+          if (sum >= 4 && sum <= kMaxLoop && y <= sum - 1 && !(sum == 4 && y == 2))
+            rs[k] += gsel(K::gidx(y, sum), g0, g1, g2, g3, g4, g5, g6) * v;
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < kTT; ++k) {
+        const int sum = S + k - 2;
+        if (sum >= 4 && sum <= kMaxLoop) o.gs[k] += cf[sum] * rs[k];
+      }
+    }
+    if constexpr (S < kMaxLoop + 2) out_rows<S + 1, TCC>(sm, TC, t, d0, slot_d0, W, bu, cf, g0, g1, g2, g3, g4, g5, g6, o);
+  }
+
+  template <int TCC = 0>
+  static PRIB_HD void outside_deep(const Ctx &c, const ST &T, const Geo &ge, const OutSmem &sm, const real *scrBif,
+                                   int t, const ColState &cs, int d0, int slot_d0 /* = d0 % kRingOut */, OutDeep &o) {
+    const int TC = TCC > 0 ? TCC : ge.TC, W = c.W;
     const real *bu = K::bulge_tab(T), *cf = K::cf_tab(T);
     const real g0 = T.cg[0], g1 = T.cg[1], g2 = T.cg[2], g3 = T.cg[3], g4 = T.cg[4], g5 = T.cg[5], g6 = T.cg[6];
-    real bstem[R], bstemO[R], bstemB[R], bmulti[R], bmulti2[R], bmbif[R], base[R], ls[R], gs[R], dang[R];
-    int t2v[R];
-    bool any = false;
-    const int smax = imin(kMaxLoop, W - 1 - d);  // source row d + sum + 2 <= W + 1
 #pragma unroll
-    for (int r = 0; r < R; ++r) {
-      const int t = c0 + r;
-      const long long g = ge.g0 - ge.H + t;
-      const int L = cs[r].L, p = cs[r].i, q = p + d;
-      bstem[r] = bstemO[r] = bstemB[r] = bmulti[r] = bmulti2[r] = bmbif[r] = base[r] = ls[r] = gs[r] = dang[r] = 0;
-      t2v[r] = 0;
-      // a halo cell is exact iff its end reaches the owned region (all its super-intervals are in the tile)
-      const bool live = p >= 0 && q <= L && t + d >= ge.H;
-      if (!live) continue;
+    for (int k = 0; k < kTT; ++k) o.gs[k] = o.bs[k] = o.bm1[k] = o.ks[k] = 0;
+    // stencils: source row d0 + s; target k: bulge length / loop size s + k - 2
+    out_rows<1, TCC>(sm, TC, t, d0, slot_d0, W, bu, cf, g0, g1, g2, g3, g4, g5, g6, o);
+    // Multiloop sums.  Only cells strictly inside the sequence (p >= 1, q < L) use them (outside_shallow
+    // ignores the sums of all others), and for those the term ranges of the kTT targets line up:
+    //   bm1[k]: m = 5 .. min(L - q_k, W - d_k)  <=>  bif row d0 + s with s = m - k = 5 - k .. min(L - p, W) - d0
+    //   ks[k] : m = 5 .. min(p, W - d_k)
+    // so the loops run on common bounds and every load stays inside the sequence / the scratch rows.
+    const long long g = ge.g0 - ge.H + t;
+    const int L = cs.L, p = cs.i;
+    const long long nc = c.NC;
+    {  // bm1[k] += bif[d0 + s][t] * Alpha_multi2[s + k][g + d0 - k]; a bif element serves all targets
+      const int shi = p >= 1 ? imin(L - p, W) - d0 : -1;
+      const real *pa = scrBif + (long long)(d0 + 5 - (kTT - 1)) * TC + t;                  // bif row d0 + s
+      const real *pb = c.arr[A_MULTI2] + (long long)(5 - (kTT - 1)) * nc + g + d0;          // row s, column q_0
+#pragma unroll
+      for (int s = 5 - (kTT - 1); s < 5; ++s) {  // head: target k joins at s = 5 - k
+        if (s <= shi) {
+          const real a = pa[0];
+#pragma unroll
+          for (int k = 0; k < kTT; ++k)
+            if (s + k >= 5) o.bm1[k] += a * pb[(long long)k * (nc - 1)];
+        }
+        pa += TC;
+        pb += nc;
+      }
+      int s = 5;
+      for (; s + 1 <= shi; s += 2) {  // two rows per round, 10 independent loads in flight
+        const real a0 = pa[0], a1 = pa[TC];
+        real b0[kTT], b1[kTT];
+#pragma unroll
+        for (int k = 0; k < kTT; ++k) {
+          b0[k] = pb[(long long)k * (nc - 1)];
+          b1[k] = pb[(long long)k * (nc - 1) + nc];
+        }
+#pragma unroll
+        for (int k = 0; k < kTT; ++k) {
+          o.bm1[k] += a0 * b0[k];
+          o.bm1[k] += a1 * b1[k];
+        }
+        pa += 2 * TC;
+        pb += 2 * nc;
+      }
+      if (s <= shi) {
+        const real a = pa[0];
+#pragma unroll
+        for (int k = 0; k < kTT; ++k) o.bm1[k] += a * pb[(long long)k * (nc - 1)];
+      }
+    }
+    {  // ks[k] += bif[d0 - k + m][t - m] * Alpha_multi1[m][g - m]; an Alpha element serves all targets
+      const int mhi = p >= 1 ? imin(p, W - d0) : -1;  // common part: all targets take m <= W - d0
+      const real *pa = scrBif + (long long)(d0 + 5) * TC + t - 5;  // bif[d0 + m][t - m]; target k: pa[-k * TC]
+      const real *pb = c.arr[A_MULTI1] + 5 * (nc - 1) + g;         // Alpha_multi1[m][g - m]
+      int m = 5;
+      for (; m + 1 <= mhi; m += 2) {
+        const real b0 = pb[0], b1 = pb[nc - 1];
+        real a0[kTT], a1[kTT];
+#pragma unroll
+        for (int k = 0; k < kTT; ++k) {
+          a0[k] = pa[-k * TC];
+          a1[k] = pa[-k * TC + (TC - 1)];
+        }
+#pragma unroll
+        for (int k = 0; k < kTT; ++k) {
+          o.ks[k] += a0[k] * b0;
+          o.ks[k] += a1[k] * b1;
+        }
+        pa += 2 * (TC - 1);
+        pb += 2 * (nc - 1);
+      }
+      if (m <= mhi) {
+        const real b = pb[0];
+#pragma unroll
+        for (int k = 0; k < kTT; ++k) o.ks[k] += pa[-k * TC] * b;
+      }
+      // tail: m = W - d0 + e, e = 1 .. kTT-1, exists only for the targets with k >= e
+      if (p >= 1) {
+#pragma unroll
+        for (int e = 1; e < kTT; ++e) {
+          const int mm = W - d0 + e;
+          if (mm >= 5 && mm <= p) {
+            const real *qa = scrBif + (long long)(d0 + mm) * TC + t - mm;
+            const real b = c.arr[A_MULTI1][(long long)mm * (nc - 1) + g];
+#pragma unroll
+            for (int k = 0; k < kTT; ++k)
+              if (k >= e) o.ks[k] += qa[-k * TC] * b;
+          }
+        }
+      }
+    }
+  }
+
+  template <int TCC = 0>
+  static PRIB_HD void outside_shallow(const Ctx &c, const ST &T, const Geo &ge, const OutSmem &sm, real *scrBif, int t,
+                                      const ColState &cs, int d, int slot_d /* = d % kRingOut */, real gs, real bs,
+                                      real bm1, real ks) {
+    const int TC = TCC > 0 ? TCC : ge.TC, W = c.W;
+    const real *bu = K::bulge_tab(T);
+    real bstem = 0, bstemO = 0, bstemB = 0, bmulti = 0, bmulti2 = 0, bmbif = 0;
+    const int smax = imin(kMaxLoop, W - 1 - d);  // source row d + sum + 2 <= W + 1
+    const long long g = ge.g0 - ge.H + t;
+    const int L = cs.L, p = cs.i, q = p + d;
+    // a halo cell is exact iff its end reaches the owned region (all its super-intervals are in the tile)
+    const bool live = p >= 0 && q <= L && t + d >= ge.H;
+    if (live) {
       const uint8_t *s = c.S + g;  // the right end q = p + d can lie beyond the tile: bases come from global
       const int sp = s[0], sp1 = s[1], sq_ = s[d], sq1 = s[d + 1];
       const bool inner = (p != 0 && q != L);
@@ -320,69 +446,17 @@ struct Tile {
       const real bse = (inner && d + 2 <= W + 1) ? b2[-1] : 0;  // Beta_stemend(p,q), :277-279
       if (inner) {
         const int tt = T.rt[te];
-        bmulti[r] = (d + 1 <= W + 1 ? sm.mu[((d + 1) & 1) * TC + t - 1] * T.e_mlbase : (real)0) +
-                    T.k2 * bse * T.e_mlclose * T.e_d3[tt][sp1] * T.e_d5[tt][sq_];
-        real bm1 = 0;
-        const int m1max = imin(L - q, W - d);
-        {
-          const real *pa = scrBif + (d + 5) * TC + t;
-          const real *pb = c.arr[A_MULTI2] + 5 * c.NC + g + d;
-          const long long nc = c.NC;
-          int m = 5;
-          for (; m + 7 <= m1max; m += 8) {  // 16 loads in flight; additions in the plain order
-            real av[8], bv[8];
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-              av[k] = pa[k * TC];
-              bv[k] = pb[k * nc];
-            }
-#pragma unroll
-            for (int k = 0; k < 8; ++k) bm1 += av[k] * bv[k];
-            pa += 8 * TC;
-            pb += 8 * nc;
-          }
-          for (; m <= m1max; ++m) {
-            bm1 += pa[0] * pb[0];
-            pa += TC;
-            pb += nc;
-          }
-        }
+        bmulti = (d + 1 <= W + 1 ? sm.mu[((d + 1) & 1) * TC + t - 1] * T.e_mlbase : (real)0) +
+                 T.k2 * bse * T.e_mlclose * T.e_d3[tt][sp1] * T.e_d5[tt][sq_];
         bm1 *= T.inv_cA;
-        real ks = 0;
-        const int m2max = imin(p, W - d);
-        {
-          const real *pa = scrBif + (d + 5) * TC + t - 5;
-          const real *pb = c.arr[A_MULTI1] + 5 * c.NC + g - 5;
-          const long long nc1 = c.NC - 1;
-          int m = 5;
-          for (; m + 7 <= m2max; m += 8) {
-            real av[8], bv[8];
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-              av[k] = pa[k * (TC - 1)];
-              bv[k] = pb[k * nc1];
-            }
-#pragma unroll
-            for (int k = 0; k < 8; ++k) ks += av[k] * bv[k];
-            pa += 8 * (TC - 1);
-            pb += 8 * nc1;
-          }
-          for (; m <= m2max; ++m) {
-            ks += pa[0] * pb[0];
-            pa += TC - 1;
-            pb += nc1;
-          }
-        }
-        bmulti2[r] = bm1 + sm.m2[((d + 1) & 1) * TC + t] * T.e_mlbase + ks * T.inv_cA;
-        bmbif[r] = bm1 + bmulti[r];
+        bmulti2 = bm1 + sm.m2[((d + 1) & 1) * TC + t] * T.e_mlbase + ks * T.inv_cA;
+        bmbif = bm1 + bmulti;
       }
       const int t2 = T.bp[sp1][sq_];
-      t2v[r] = t2;
       if (t2) {
-        any = true;
         const int t2r = T.rt[t2];
-        dang[r] = K::e_dangle(T, t2, p > 0, sp, q < L, sq1);
-        base[r] = (real)exp(c.lao[g] + c.lbo[g + d] - c.lao[cs[r].zcol]) * dang[r] * T.sB[d];
+        const real dang = K::e_dangle(T, t2, p > 0, sp, q < L, sq1);
+        const real base = (real)exp(c.lao[g] + c.lbo[g + d] - c.lao[cs.zcol]) * dang * T.sB[d];
         real l = 0;
         if (smax >= 0) l += bse * T.e_stack[te][t2r];
         const real *b3 = sm.stem + ((d + 3) & (kRingStem - 1)) * TC + t;
@@ -397,16 +471,6 @@ struct Tile {
         if (smax >= 2) {
           const int to = T.bp[s[-1]][s[d + 2]];
           l += b4[-2] * c.e_int11[idx11(to, t2r, sp, sq1)];
-          real bs = 0;
-          int slot = wrap_out(slot_d + 4);
-#pragma unroll
-          for (int u = 2; u <= kMaxLoop; ++u) {
-            if (u <= smax) {
-              const real *row = sm.stemB + slot * TC + t - 1;
-              bs += bu[u] * (row[-u] + row[0]);
-              slot = wrap_out(slot + 1);
-            }
-          }
           l += T.tau[t2r] * bs;
         }
         if (smax >= 3) {
@@ -418,79 +482,28 @@ struct Tile {
         if (smax >= 4) {
           const int tc = T.bp[s[-2]][s[d + 3]];
           l += b6[-3] * c.e_int22[idx22(tc, t2r, s[-1], sp, sq1, s[d + 2])];
+          l += T.e_mmI[t2r][sq1][sp] * gs;
         }
-        ls[r] = l;
+        bstem = base + T.k2 * l + bmulti2 * T.e_mlintern * dang;
+        bstemO = bstem * T.e_mmI[t2][s[2]][s[d - 1]];
+        bstemB = bstem * T.tau[t2];
       }
     }
-    // generic loops: joint stencil over B_STEMO.  Target r (column c0 + r) takes source u1 from local
-    // column c0 + r - 1 - u1; the elements are read as aligned vectors going left from c0 + R - 1.
-    if (any && smax >= 4) {
-      int slot = wrap_out(slot_d + 6);
-#pragma unroll
-      for (int sum = 4; sum <= kMaxLoop; ++sum) {
-        if (sum <= smax) {
-          const real *row = sm.stemO + slot * TC + c0;
-          real rs[R];
-#pragma unroll
-          for (int r = 0; r < R; ++r) rs[r] = 0;
-          // aligned blocks [c0 - yb - R, c0 - yb - 1], yb = 0, R, ...; for ascending u1 per target the
-          // blocks are visited right to left and their elements right to left
-#pragma unroll
-          for (int yb = -R; yb <= sum - 1; yb += R) {
-            real v[R];
-            if (c0 - yb - R >= 0) {
-              load_vec<R>(row - yb - R, v);
-            } else {  // left of the tile: only columns that are not live could ask for it
-#pragma unroll
-              for (int k = 0; k < R; ++k) v[k] = 0;
-            }
-#pragma unroll
-            for (int k = R - 1; k >= 0; --k) {
-              const int e = -yb - R + k;  // column offset from c0
-#pragma unroll
-              for (int r = 0; r < R; ++r) {
-                const int u1 = r - 1 - e;
-                if (u1 >= 1 && u1 <= sum - 1 && !(sum == 4 && u1 == 2))
-                  rs[r] += gsel(K::gidx(u1, sum), g0, g1, g2, g3, g4, g5, g6) * v[k];
-              }
-            }
-          }
-#pragma unroll
-          for (int r = 0; r < R; ++r) gs[r] += cf[sum] * rs[r];
-          slot = wrap_out(slot + 1);
-        }
-      }
-    }
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-      const int t = c0 + r;
-      const long long g = ge.g0 - ge.H + t;
-      const int L = cs[r].L, p = cs[r].i, q = p + d;
-      if (t2v[r]) {
-        const uint8_t *s = c.S + g;
-        const int t2 = t2v[r], t2r = T.rt[t2];
-        real l = ls[r];
-        if (smax >= 4) l += T.e_mmI[t2r][s[d + 1]][s[0]] * gs[r];
-        bstem[r] = base[r] + T.k2 * l + bmulti2[r] * T.e_mlintern * dang[r];
-        bstemO[r] = bstem[r] * T.e_mmI[t2][s[2]][s[d - 1]];
-        bstemB[r] = bstem[r] * T.tau[t2];
-      }
-      sm.stemO[slot_d * TC + t] = bstemO[r];
-      sm.stemB[slot_d * TC + t] = bstemB[r];
-      sm.stem[(d & (kRingStem - 1)) * TC + t] = bstem[r];
-      sm.mu[(d & 1) * TC + t] = bmulti[r];
-      sm.m2[(d & 1) * TC + t] = bmulti2[r];
-      scrBif[d * TC + t] = bmbif[r];
-      if (t >= ge.H && p >= 0 && q <= L) {
-        c.at(B_STEM, d, g) = bstem[r];
-        c.at(B_STEMO, d, g) = bstemO[r];
-        c.at(B_STEMB, d, g) = bstemB[r];
-        c.at(B_MULTI, d, g) = bmulti[r];
-        c.at(B_MULTI2, d, g) = bmulti2[r];
-        if (!(K::in_safe_range(bstem[r]) && K::in_safe_range(bmulti[r]) && K::in_safe_range(bmulti2[r]) &&
-              K::in_safe_range(bmbif[r])))
-          c.flags[cs[r].sq] = 1;
-      }
+    sm.stemO[slot_d * TC + t] = bstemO;
+    sm.stemB[slot_d * TC + t] = bstemB;
+    sm.stem[(d & (kRingStem - 1)) * TC + t] = bstem;
+    sm.mu[(d & 1) * TC + t] = bmulti;
+    sm.m2[(d & 1) * TC + t] = bmulti2;
+    scrBif[d * TC + t] = bmbif;
+    if (t >= ge.H && p >= 0 && q <= L) {
+      c.at(B_STEM, d, g) = bstem;
+      c.at(B_STEMO, d, g) = bstemO;
+      c.at(B_STEMB, d, g) = bstemB;
+      c.at(B_MULTI, d, g) = bmulti;
+      c.at(B_MULTI2, d, g) = bmulti2;
+      if (!(K::in_safe_range(bstem) && K::in_safe_range(bmulti) && K::in_safe_range(bmulti2) &&
+            K::in_safe_range(bmbif)))
+        c.flags[cs.sq] = 1;
     }
   }
 };

@@ -86,30 +86,39 @@ void run_dp(EmuT<real> &e) {
     for (long long g = 0; g < c.NC; g++) K::outside_cell(c, g, d);
 }
 
-// Emulation of the tile-persistent kernels (acc_tile.h): one "CTA" per tile, TC "threads", a barrier
-// (= end of the inner loop over t) after every span.
-template <typename real, int R>
+// Emulation of the tile-persistent, time-tiled kernels (acc_tile.h): one "CTA" per tile, TC "threads"; a
+// loop over t = everything the threads do between two barriers.
+template <typename real>
 void run_dp_tiled(EmuT<real> &e, int TC) {
   typedef Tile<real> TL;
   typedef Core<real> K;
   const typename K::Ctx &c = e.c;
   const int W = c.W, H = W + 1, TX = TC - H;
   const long long ntiles = (c.NC + TX - 1) / TX;
-  std::vector<real> smem((size_t)kTileRows * TC), scr((size_t)2 * (W + 4) * TC);
+  std::vector<real> smem((size_t)kTilePad + (size_t)kTileRows * TC), scr((size_t)2 * (W + 4) * TC);
   std::vector<uint8_t> sS((size_t)TC + 16);
   std::vector<typename TL::ColState> cs(TC);
+  real *base = smem.data() + kTilePad;
+  const int dfirst = TL::first_group(W);
+  struct InDeep { real gs[kTT], mb[kTT]; };
+  std::vector<InDeep> din(TC);
+  std::vector<typename TL::OutDeep> dout(TC);
+  real *scrM1 = scr.data(), *scrM2 = scr.data() + (size_t)(W + 4) * TC;
   for (long long tile = 0; tile < ntiles; tile++) {
     typename TL::Geo ge{tile * TX, TC, TX, H};
     std::fill(smem.begin(), smem.end(), (real)0);
+    if (g_poison) std::fill(scr.begin(), scr.end(), std::numeric_limits<real>::quiet_NaN());
     for (int k = 0; k < TC + 8; k++) sS[k] = (ge.g0 + k < c.NC) ? c.S[ge.g0 + k] : 0;
     for (int t = 0; t < TC; t++) TL::col_state(c, ge.g0 + t, cs[t]);
-    typename TL::InSmem sm = TL::carve_in(smem.data(), TC, sS.data());
-    for (int d = kTurn; d <= W + 1; d++)
-      for (int tq = 0; tq < TC / R; tq++) {
-        typename TL::ColState csr[R];
-        for (int r = 0; r < R; r++) csr[r] = cs[tq * R + r];
-        TL::template inside_span<R>(c, *c.T, ge, sm, scr.data(), scr.data() + (size_t)(W + 4) * TC, tq, csr, d);
+    typename TL::InSmem sm = TL::carve_in(base, TC, sS.data());
+    for (int d0 = dfirst; d0 <= W + 1; d0 += kTT) {
+      for (int t = 0; t < TC; t++) TL::template inside_deep<0>(*c.T, ge, sm, scrM1, scrM2, t, d0, din[t].gs, din[t].mb);
+      for (int k = 0; k < kTT; k++) {
+        if (d0 + k < kTurn) continue;
+        for (int t = 0; t < TC; t++)
+          TL::template inside_shallow<0>(c, *c.T, ge, sm, scrM1, scrM2, t, cs[t], d0 + k, din[t].gs[k], din[t].mb[k]);
       }
+    }
   }
   double ring[256];
   for (int k = 0; k < c.nseq; k++) {
@@ -119,14 +128,21 @@ void run_dp_tiled(EmuT<real> &e, int TC) {
   for (long long tile = 0; tile < ntiles; tile++) {
     typename TL::Geo ge{tile * TX, TC, TX, H};
     std::fill(smem.begin(), smem.end(), (real)0);
+    if (g_poison) std::fill(scr.begin(), scr.end(), std::numeric_limits<real>::quiet_NaN());
     for (int t = 0; t < TC; t++) TL::col_state(c, ge.g0 - H + t, cs[t]);
-    typename TL::OutSmem sm = TL::carve_out(smem.data(), TC);
-    for (int d = W + 1; d >= kTurn; d--)
-      for (int tq = 0; tq < TC / R; tq++) {
-        typename TL::ColState csr[R];
-        for (int r = 0; r < R; r++) csr[r] = cs[tq * R + r];
-        TL::template outside_span<R>(c, *c.T, ge, sm, scr.data(), tq, csr, d, d % kRingOut);
+    typename TL::OutSmem sm = TL::carve_out(base, TC);
+    for (int d0 = W + 1; d0 >= dfirst + kTT - 1; d0 -= kTT) {
+      for (int t = 0; t < TC; t++)
+        TL::template outside_deep<0>(c, *c.T, ge, sm, scr.data(), t, cs[t], d0, ((d0 % kRingOut) + kRingOut) % kRingOut,
+                                     dout[t]);
+      for (int k = 0; k < kTT; k++) {
+        const int d = d0 - k;
+        if (d < kTurn) continue;
+        for (int t = 0; t < TC; t++)
+          TL::template outside_shallow<0>(c, *c.T, ge, sm, scr.data(), t, cs[t], d, d % kRingOut, dout[t].gs[k],
+                                          dout[t].bs[k], dout[t].bm1[k], dout[t].ks[k]);
       }
+    }
   }
 }
 
@@ -210,7 +226,7 @@ namespace {
 template <typename real>
 int run_tiled(int n, const char *const *seqs, const int32_t *lens, int W, int delta, float *out,
               const int64_t *acc_off, const int64_t *cond_off, int TC, const ScaleSpec &spec, int32_t *flags_out,
-              int R = 1) {
+              int /*unused*/ = 1) {
   EmuT<real> e;
   for (int k = 0; k < n; k++) {
     std::memset(out + acc_off[k], 0, sizeof(float) * (size_t)lens[k]);
@@ -223,25 +239,18 @@ int run_tiled(int n, const char *const *seqs, const int32_t *lens, int W, int de
     std::fill(e.lao.begin(), e.lao.end(), std::numeric_limits<double>::quiet_NaN());
     std::fill(e.lbo.begin(), e.lbo.end(), std::numeric_limits<double>::quiet_NaN());
   }
-  if (R == 4) run_dp_tiled<real, 4>(e, TC);
-  else if (R == 2) run_dp_tiled<real, 2>(e, TC);
-  else run_dp_tiled<real, 1>(e, TC);
+  run_dp_tiled<real>(e, TC);
   run_acc(e, TC >= 256 ? 128 : 64);
   if (flags_out) std::memcpy(flags_out, e.flags.data(), sizeof(int32_t) * (size_t)n);
   return 1;
 }
 }  // namespace
 
-static int g_cols_per_thread = 1;
-
 extern "C" {
 
 // poison = 1: fill every DP array with NaN before the run (emulates a device that does not zero its state):
 // any read of a never-written cell then shows up in the output
 void hostemu_set_poison(int on) { g_poison = on; }
-
-// columns per emulated thread (register tiling of the stencils): 1, 2 or 4
-void hostemu_set_cols_per_thread(int R) { g_cols_per_thread = R; }
 
 // FP32 band arithmetic with span scaling; flags_out[k] != 0 marks sequences whose stored values left
 // the safe range (the product re-runs those in FP64).
@@ -252,7 +261,7 @@ int hostemu_run_batch_tiled_f32(int n, const char *const *seqs, const int32_t *l
   spec.klog2 = klog2;
   spec.alog2 = alog2;
   spec.blog2 = blog2;
-  return run_tiled<float>(n, seqs, lens, W, delta, out, acc_off, cond_off, TC, spec, flags_out, g_cols_per_thread);
+  return run_tiled<float>(n, seqs, lens, W, delta, out, acc_off, cond_off, TC, spec, flags_out);
 }
 
 // Same batch through the tile-persistent formulation; TC = emulated CTA width.
@@ -263,7 +272,7 @@ int hostemu_run_batch_tiled(int n, const char *const *seqs, const int32_t *lens,
   spec.klog2 = klog2;
   spec.alog2 = alog2;
   spec.blog2 = blog2;
-  return run_tiled<double>(n, seqs, lens, W, delta, out, acc_off, cond_off, TC, spec, nullptr, g_cols_per_thread);
+  return run_tiled<double>(n, seqs, lens, W, delta, out, acc_off, cond_off, TC, spec, nullptr);
 }
 
 int hostemu_run(const char *seq, int L, int W, int delta, float *acc, float *cond) {

@@ -116,21 +116,6 @@ def test_tiled_formulation_vs_reference(emu, name):
     assert_close_kcal(out[L:2 * L], case["cond"], ATOL_VS_REF, RTOL_VS_REF, "cond")
 
 
-@pytest.mark.parametrize("R", [2, 4])
-@pytest.mark.parametrize("W,TC", [(70, 352), (20, 64), (150, 352), (70, 104)])
-def test_register_tiled_stencil_is_bit_identical(emu, R, W, TC):
-    """R columns per thread (vector shared-memory loads, shared source elements) must give the same bits as
-    one column per thread."""
-    emu.lib.hostemu_set_cols_per_thread(1)
-    ref, _, _ = _tiled(emu.lib, _MIX, W, 5, TC)
-    emu.lib.hostemu_set_cols_per_thread(R)
-    try:
-        got, _, _ = _tiled(emu.lib, _MIX, W, 5, TC)
-    finally:
-        emu.lib.hostemu_set_cols_per_thread(1)
-    assert np.array_equal(ref.view(np.uint32), got.view(np.uint32))
-
-
 @pytest.mark.parametrize("W,TC,delta", [(70, 352, 5), (20, 64, 2), (150, 352, 10)])
 def test_no_kernel_reads_a_cell_it_did_not_write(emu, W, TC, delta):
     """The device does not clear its DP state between batches: with every array poisoned with NaN the tile
