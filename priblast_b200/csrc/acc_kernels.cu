@@ -233,13 +233,18 @@ __global__ void __launch_bounds__(512) k_biloop_tile(typename Core<real>::Ctx c)
   ge.rows = c.W - 5 > 0 ? c.W - 5 : 0;
   real *tile = reinterpret_cast<real *>(smem_raw);
   uint8_t *list = reinterpret_cast<uint8_t *>(tile + (size_t)ge.rows * ge.cols);
+  int *rem = reinterpret_cast<int *>(list + (size_t)(c.W + 1) * ge.TXb);  // (W + 1) * TXb is a multiple of 4
   const int total = ge.rows * ge.cols;
   constexpr int COLS = TXB > 0 ? TXB + 32 : 0;  // TXB > 0: block width (hence the tile row stride) known at compile time
   typename BT::Strand st;
+  // which cells exist, per start column of the tile (the dense pass reads every element)
+  for (int x = threadIdx.x; x < BT::rem_count(LEFT, ge.cols, c.W); x += blockDim.x)
+    rem[x] = BT::max_span_from(c, BT::rem_col(LEFT, ge, c.W, x));
+  __syncthreads();
   // generic loops out of the Alpha_stemI tile
   for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
     const int r = idx / ge.cols + 5, x = idx - (r - 5) * ge.cols;
-    tile[idx] = LEFT ? BT::load_left(c, ge, r, x, A_STEMI) : BT::load_right(c, ge, r, x, A_STEMI);
+    tile[idx] = LEFT ? BT::load_left_checked(c, ge, rem, r, x) : BT::load_right_checked(c, ge, rem, r, x);
   }
   __syncthreads();
   if (LEFT) BT::template left<COLS, ULO>(c, ge, tile, list, threadIdx.x, st);
@@ -656,9 +661,12 @@ int setup_engine(prib_ctx *c, const ScaleSpec &spec, size_t smem_max, std::strin
   // interior-loop tiles: the widest block (<= 512 threads) whose Alpha_stemI tile + span lists fit
   const int rows = c->W - 5 > 0 ? c->W - 5 : 0;
   int TXb = 512;
-  while (TXb > 32 && (size_t)rows * (TXb + 32) * sizeof(real) + (size_t)(c->W + 1) * TXb + 64 > smem_max) TXb -= 32;
+  auto bi_bytes = [&](int txb) {
+    return (size_t)rows * (txb + 32) * sizeof(real) + (size_t)(c->W + 1) * txb + (size_t)(txb + 32 + c->W) * sizeof(int) + 64;
+  };
+  while (TXb > 32 && bi_bytes(TXb) > smem_max) TXb -= 32;
   e.TXb = TXb;
-  e.bi_smem = (size_t)rows * (TXb + 32) * sizeof(real) + (size_t)(c->W + 1) * TXb + 64;
+  e.bi_smem = bi_bytes(TXb);
   if (e.bi_smem > smem_max) return fail(PRIB_ECUDA, "shared memory too small for the interior-loop tiles");
   CU(cudaFuncSetAttribute(k_outer_scans_warp<real>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                           (int)(smem_max - 16 * 1024)));

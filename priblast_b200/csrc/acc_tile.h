@@ -546,6 +546,89 @@ struct BiTile {
     return (col >= 0 && col < c.NC) ? c.ld(arr, r, col) : (real)0;
   }
 
+  // Largest span of a cell that STARTS at global column col (L - i), or -1 for padding / outside the batch.
+  // The dense generic pass multiplies every tile element by a (possibly zero) coefficient, so elements of
+  // cells that do not exist must read as 0 rather than as whatever an earlier batch left in the DP state.
+  static PRIB_HD int max_span_from(const Ctx &c, long long col) {
+    if (col < 0 || col >= c.NC) return -1;
+    const int sq = c.col_seq[col];
+    if (sq < 0) return -1;
+    return c.seq_len[sq] - (int)(col - c.seq_off[sq]);
+  }
+  // rem[] for the tile of one CTA: left kernel: column g0 + x, x in [0, cols); right kernel: start columns
+  // g0 - 31 - (W - 1) + x, x in [0, cols + W - 1)
+  static PRIB_HD int rem_count(bool left_side, int cols, int W) { return left_side ? cols : cols + W - 1; }
+  static PRIB_HD long long rem_col(bool left_side, const Geo &ge, int W, int x) {
+    return left_side ? ge.g0 + x : ge.g0 - 31 - (W - 1) + x;
+  }
+  static PRIB_HD real load_left_checked(const Ctx &c, const Geo &ge, const int *rem, int r, int x) {
+    return r <= rem[x] ? c.ld(A_STEMI, r, ge.g0 + x) : (real)0;
+  }
+  static PRIB_HD real load_right_checked(const Ctx &c, const Geo &ge, const int *rem, int r, int x) {
+    const int xs = x - r + (c.W - 1);  // index of the start column g0 - 31 + x - r in rem[]
+    return r <= rem[xs] ? c.ld(A_STEMI, r, ge.g0 - 31 + x - r) : (real)0;
+  }
+
+  // ---------------------------------------------------------------------------------------------
+  // Dense, time-tiled generic pass.  Outer spans dp0 + k (k = 0..kTT-1) of one column are handled together:
+  // tile row dp0 - S (inner span) holds, at offset DIR * u, the inner cell of the loops with kept strand
+  // length u and loop size S + k for target k, so
+  //     m[u] += row[DIR * u] * sum_k w[k] * conv[u][S + k - u]
+  // with w[k] = Beta_stemO of the outer pair (0 when it does not close).  Where all kTT coefficients sit in
+  // the saturated ninio zone (|u1 - u2| >= 6) the inner sum does not depend on u and is formed once per row.
+  // All indices are compile-time: conv[][] entries are constant-bank operands.
+  // ---------------------------------------------------------------------------------------------
+  static PRIB_HD constexpr bool dn_valid(int u, int sum) { return sum <= kMaxLoop && sum - u >= 1 && sum >= 4 && !(u == 2 && sum == 4); }
+  static PRIB_HD constexpr bool dn_sat(int u, int sum) { return (2 * u - sum >= 6) || (sum - 2 * u >= 6); }
+  static PRIB_HD constexpr bool dn_allsat(int u, int S) {
+    for (int k = 0; k < kTT; ++k)
+      if (!dn_valid(u, S + k) || !dn_sat(u, S + k)) return false;
+    return true;
+  }
+  static PRIB_HD constexpr bool dn_row_has_sat(int S, int ulo) {
+    for (int u = ulo; u <= kMaxLoop; ++u)
+      if (dn_allsat(u, S)) return true;
+    return false;
+  }
+  static PRIB_HD constexpr bool dn_any(int u, int S) {
+    for (int k = 0; k < kTT; ++k)
+      if (dn_valid(u, S + k)) return true;
+    return false;
+  }
+
+  template <int S, int U, int ULO, int DIR>
+  static PRIB_HD void dense_cols(const real *row, const real *cv, const real (&w)[kTT], real qsat,
+                                 real (&m)[kMaxLoop + 1]) {
+    if constexpr (dn_any(U, S)) {
+      real q;
+      if constexpr (dn_allsat(U, S)) {
+        q = qsat;
+      } else {
+        q = 0;
+#pragma unroll
+        for (int k = 0; k < kTT; ++k)
+          if (dn_valid(U, S + k)) q += w[k] * cv[U * 32 + (S + k - U)];
+      }
+      m[U] += row[DIR * U] * q;
+    }
+    if constexpr (U < kMaxLoop) dense_cols<S, U + 1, ULO, DIR>(row, cv, w, qsat, m);
+  }
+
+  template <int S, int COLS, int ULO, int DIR>
+  static PRIB_HD void dense_rows(const real *base, int cols, int dp0, const real *cv, const real (&w)[kTT],
+                                 real (&m)[kMaxLoop + 1]) {
+    if (dp0 - S >= 5) {  // uniform: inner spans below 5 hold no stems
+      const real *row = base - S * (COLS > 0 ? COLS : cols);
+      real qsat = 0;
+      if constexpr (dn_row_has_sat(S, ULO)) {
+#pragma unroll
+        for (int k = 0; k < kTT; ++k) qsat += w[k] * cv[(S + k - 1) * 32 + 1];  // conv[sum - 1][1]: saturated, sum >= 8
+      }
+      dense_cols<S, ULO, ULO, DIR>(row, cv, w, qsat, m);
+    }
+    if constexpr (S < kMaxLoop) dense_rows<S + 1, COLS, ULO, DIR>(base, cols, dp0, cv, w, m);
+  }
+
   // Per-thread state carried from the generic pass (Alpha_stemI tile) to the bulge pass (Alpha_stemB tile).
   struct Strand {
     real w[kMaxLoop + 1];  // strand weights by strand length
@@ -596,28 +679,12 @@ struct BiTile {
           }
         }
       }
-      // pass B (each lane at its own span): generic interior loops out of the shared-memory tile, walked by
-      // loop size: all terms of one size share a tile row, every offset and coefficient is compile-time
-      real bseO_next = cnt > 0 ? c.ld(B_STEMO, list[t] + 2, g - 1) : (real)0;
-      for (int k = 0; k < cnt; ++k) {
-        const int dp = list[k * TXb + t];
-        const real bseO = bseO_next;  // fetched one iteration ahead: the gather latency hides behind the stencil
-        if (k + 1 < cnt) bseO_next = c.ld(B_STEMO, list[(k + 1) * TXb + t] + 2, g - 1);
-        const int smax = imin(kMaxLoop, dp - 5);
-        const real *base = tile + (dp - 5) * cols + t;
-        real a[kMaxLoop];
+      // pass B: generic interior loops out of the shared-memory tile, dense over groups of kTT outer spans
+      for (int dp0 = delta + 5; dp0 <= dpmax; dp0 += kTT) {
+        real w[kTT];
 #pragma unroll
-        for (int u1 = 0; u1 < kMaxLoop; ++u1) a[u1] = 0;
-#pragma unroll
-        for (int sum = ULO + 1; sum <= kMaxLoop; ++sum) {
-          if (sum <= smax) {
-            const real *row = base - sum * cols;  // span dp - sum
-#pragma unroll
-            for (int u1 = ULO; u1 < sum; ++u1) a[u1] += cv[u1 * 32 + sum - u1] * row[u1];
-          }
-        }
-#pragma unroll
-        for (int u1 = ULO; u1 < kMaxLoop; ++u1) ml[u1] += bseO * a[u1];
+        for (int k = 0; k < kTT; ++k) w[k] = (dp0 + k <= dpmax) ? c.ld(B_STEMO, dp0 + k + 2, g - 1) : (real)0;
+        dense_rows<1, COLS, ULO, 1>(tile + (dp0 - 5) * cols + t, cols, dp0, cv, w, ml);
       }
     }
     st.cnt = cnt;
@@ -693,29 +760,12 @@ struct BiTile {
           }
         }
       }
-      real bseO_next = cnt > 0 ? c.ld(B_STEMO, list[t] + 2, g2 - list[t] - 1) : (real)0;
-      for (int k = 0; k < cnt; ++k) {
-        const int dp = list[k * TXb + t];
-        const real bseO = bseO_next;
-        if (k + 1 < cnt) {
-          const int dn = list[(k + 1) * TXb + t];
-          bseO_next = c.ld(B_STEMO, dn + 2, g2 - dn - 1);
-        }
-        const int smax = imin(kMaxLoop, dp - 5);
-        const real *base = tile + (dp - 5) * cols + t + 31;
-        real a[kMaxLoop];
+      for (int dp0 = delta + 5; dp0 <= dpmax; dp0 += kTT) {
+        real w[kTT];
 #pragma unroll
-        for (int u2 = 0; u2 < kMaxLoop; ++u2) a[u2] = 0;
-#pragma unroll
-        for (int sum = ULO + 1; sum <= kMaxLoop; ++sum) {
-          if (sum <= smax) {
-            const real *row = base - sum * cols;  // span dp - sum, end-indexed: the inner cell ends at j' - u2
-#pragma unroll
-            for (int u2 = ULO; u2 < sum; ++u2) a[u2] += cv[u2 * 32 + sum - u2] * row[-u2];
-          }
-        }
-#pragma unroll
-        for (int u2 = ULO; u2 < kMaxLoop; ++u2) mr[u2] += bseO * a[u2];
+        for (int k = 0; k < kTT; ++k)
+          w[k] = (dp0 + k <= dpmax) ? c.ld(B_STEMO, dp0 + k + 2, g2 - dp0 - k - 1) : (real)0;
+        dense_rows<1, COLS, ULO, -1>(tile + (dp0 - 5) * cols + t + 31, cols, dp0, cv, w, mr);
       }
     }
     st.cnt = cnt;
