@@ -222,6 +222,38 @@ __global__ void __launch_bounds__(32 * kScanWarps) k_outer_scans_warp(typename C
   warp_scan<real, false>(c, sq, rings[warp], wbuf, usm, lane);
 }
 
+// Cooperative load of one band-array tile (rows = spans 5..W-1) into shared memory: thread = tile column,
+// rows in batches of 8 so that 8 independent loads are in flight per thread; the 32 halo columns are
+// spread over all threads.  lim: this thread's column limit, lim_halo[32]: limits of the halo columns.
+template <typename real, bool LEFT>
+__device__ __forceinline__ void load_band_tile(const typename Core<real>::Ctx &c, const typename BiTile<real>::Geo &ge,
+                                               int arr, real *tile, int lim, const int *lim_halo) {
+  typedef BiTile<real> BT;
+  const int tid = threadIdx.x, rows = ge.rows, cols = ge.cols;
+  for (int r0 = 0; r0 < rows; r0 += 8) {
+    real v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = (r0 + k < rows) ? BT::tile_elem(c, ge, LEFT, arr, r0 + k + 5, tid, lim) : (real)0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      if (r0 + k < rows) tile[(r0 + k) * cols + tid] = v[k];
+  }
+  const int nh = rows * 32;
+  for (int e0 = tid; e0 < nh; e0 += 4 * ge.TXb) {
+    real v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int e = e0 + k * ge.TXb;
+      v[k] = e < nh ? BT::tile_elem(c, ge, LEFT, arr, (e >> 5) + 5, ge.TXb + (e & 31), lim_halo[e & 31]) : (real)0;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int e = e0 + k * ge.TXb;
+      if (e < nh) tile[(e >> 5) * cols + ge.TXb + (e & 31)] = v[k];
+    }
+  }
+}
+
 template <typename real, bool LEFT, int ULO, int TXB>
 __global__ void __launch_bounds__(512) k_biloop_tile(typename Core<real>::Ctx c) {
   typedef BiTile<real> BT;
@@ -233,28 +265,20 @@ __global__ void __launch_bounds__(512) k_biloop_tile(typename Core<real>::Ctx c)
   ge.rows = c.W - 5 > 0 ? c.W - 5 : 0;
   real *tile = reinterpret_cast<real *>(smem_raw);
   uint8_t *list = reinterpret_cast<uint8_t *>(tile + (size_t)ge.rows * ge.cols);
-  int *rem = reinterpret_cast<int *>(list + (size_t)(c.W + 1) * ge.TXb);  // (W + 1) * TXb is a multiple of 4
-  const int total = ge.rows * ge.cols;
+  int *lim_halo = reinterpret_cast<int *>(list + (size_t)(c.W + 1) * ge.TXb);  // (W + 1) * TXb is a multiple of 4
   constexpr int COLS = TXB > 0 ? TXB + 32 : 0;  // TXB > 0: block width (hence the tile row stride) known at compile time
   typename BT::Strand st;
-  // which cells exist, per start column of the tile (the dense pass reads every element)
-  for (int x = threadIdx.x; x < BT::rem_count(LEFT, ge.cols, c.W); x += blockDim.x)
-    rem[x] = BT::max_span_from(c, BT::rem_col(LEFT, ge, c.W, x));
+  const int lim = BT::tile_col_limit(c, ge, LEFT, threadIdx.x);
+  if (threadIdx.x < 32) lim_halo[threadIdx.x] = BT::tile_col_limit(c, ge, LEFT, ge.TXb + threadIdx.x);
   __syncthreads();
   // generic loops out of the Alpha_stemI tile
-  for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
-    const int r = idx / ge.cols + 5, x = idx - (r - 5) * ge.cols;
-    tile[idx] = LEFT ? BT::load_left_checked(c, ge, rem, r, x) : BT::load_right_checked(c, ge, rem, r, x);
-  }
+  load_band_tile<real, LEFT>(c, ge, A_STEMI, tile, lim, lim_halo);
   __syncthreads();
   if (LEFT) BT::template left<COLS, ULO>(c, ge, tile, list, threadIdx.x, st);
   else BT::template right<COLS, ULO>(c, ge, tile, list, threadIdx.x, st);
   __syncthreads();
   // bulges out of the Alpha_stemB tile (same buffer)
-  for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
-    const int r = idx / ge.cols + 5, x = idx - (r - 5) * ge.cols;
-    tile[idx] = LEFT ? BT::load_left(c, ge, r, x, A_STEMB) : BT::load_right(c, ge, r, x, A_STEMB);
-  }
+  load_band_tile<real, LEFT>(c, ge, A_STEMB, tile, lim, lim_halo);
   __syncthreads();
   if (LEFT) BT::template left_bulge<COLS, ULO>(c, ge, tile, list, threadIdx.x, st);
   else BT::template right_bulge<COLS, ULO>(c, ge, tile, list, threadIdx.x, st);
@@ -660,9 +684,10 @@ int setup_engine(prib_ctx *c, const ScaleSpec &spec, size_t smem_max, std::strin
   CU(cudaFuncSetAttribute(k_outside_tile<real>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
   // interior-loop tiles: the widest block (<= 512 threads) whose Alpha_stemI tile + span lists fit
   const int rows = c->W - 5 > 0 ? c->W - 5 : 0;
-  int TXb = 512;
+  int TXb = 256;  // two CTAs per SM: one loads its tile while the other computes (measured: 256 beats 512)
+  if (const char *te = getenv("PRIB_TXB")) TXb = std::max(32, std::min(512, atoi(te) / 32 * 32));  // tuning knob
   auto bi_bytes = [&](int txb) {
-    return (size_t)rows * (txb + 32) * sizeof(real) + (size_t)(c->W + 1) * txb + (size_t)(txb + 32 + c->W) * sizeof(int) + 64;
+    return (size_t)rows * (txb + 32) * sizeof(real) + (size_t)(c->W + 1) * txb + 32 * sizeof(int) + 64;
   };
   while (TXb > 32 && bi_bytes(TXb) > smem_max) TXb -= 32;
   e.TXb = TXb;

@@ -535,38 +535,23 @@ struct BiTile {
     int rows;      // W - 5: spans 5 .. W-1
   };
 
-  // element of the start-indexed tile: span r, global column g0 + x        (left kernel)
-  static PRIB_HD real load_left(const Ctx &c, const Geo &ge, int r, int x, int arr = A_STEMI) {
-    const long long col = ge.g0 + x;
-    return col < c.NC ? c.ld(arr, r, col) : (real)0;
-  }
-  // element of the end-indexed tile: span r, END column g0 - 31 + x        (right kernel)
-  static PRIB_HD real load_right(const Ctx &c, const Geo &ge, int r, int x, int arr = A_STEMI) {
-    const long long col = ge.g0 - 31 + x - r;
-    return (col >= 0 && col < c.NC) ? c.ld(arr, r, col) : (real)0;
-  }
-
-  // Largest span of a cell that STARTS at global column col (L - i), or -1 for padding / outside the batch.
-  // The dense generic pass multiplies every tile element by a (possibly zero) coefficient, so elements of
-  // cells that do not exist must read as 0 rather than as whatever an earlier batch left in the DP state.
-  static PRIB_HD int max_span_from(const Ctx &c, long long col) {
+  // Tiles.  Left kernel: start-indexed, element (r, x) = cell of span r starting at column g0 + x.  Right
+  // kernel: end-indexed, element (r, x) = cell of span r ENDING at column g0 - 31 + x.  The dense generic
+  // pass multiplies every tile element by a (possibly zero) coefficient, so elements of cells that do not
+  // exist must read as 0 rather than as whatever an earlier batch left in the DP state.  A cell exists iff
+  // its span is <= the limit of its tile column: L - i of the start column (left), left index of the end
+  // column (right); -1 for padding columns and columns outside the batch.
+  static PRIB_HD int tile_col_limit(const Ctx &c, const Geo &ge, bool left_side, int x) {
+    const long long col = left_side ? ge.g0 + x : ge.g0 - 31 + x;
     if (col < 0 || col >= c.NC) return -1;
     const int sq = c.col_seq[col];
     if (sq < 0) return -1;
-    return c.seq_len[sq] - (int)(col - c.seq_off[sq]);
+    const int i = (int)(col - c.seq_off[sq]);
+    return left_side ? c.seq_len[sq] - i : i;
   }
-  // rem[] for the tile of one CTA: left kernel: column g0 + x, x in [0, cols); right kernel: start columns
-  // g0 - 31 - (W - 1) + x, x in [0, cols + W - 1)
-  static PRIB_HD int rem_count(bool left_side, int cols, int W) { return left_side ? cols : cols + W - 1; }
-  static PRIB_HD long long rem_col(bool left_side, const Geo &ge, int W, int x) {
-    return left_side ? ge.g0 + x : ge.g0 - 31 - (W - 1) + x;
-  }
-  static PRIB_HD real load_left_checked(const Ctx &c, const Geo &ge, const int *rem, int r, int x) {
-    return r <= rem[x] ? c.ld(A_STEMI, r, ge.g0 + x) : (real)0;
-  }
-  static PRIB_HD real load_right_checked(const Ctx &c, const Geo &ge, const int *rem, int r, int x) {
-    const int xs = x - r + (c.W - 1);  // index of the start column g0 - 31 + x - r in rem[]
-    return r <= rem[xs] ? c.ld(A_STEMI, r, ge.g0 - 31 + x - r) : (real)0;
+  static PRIB_HD real tile_elem(const Ctx &c, const Geo &ge, bool left_side, int arr, int r, int x, int limit) {
+    if (r > limit) return (real)0;
+    return c.ld(arr, r, left_side ? ge.g0 + x : ge.g0 - 31 + x - r);
   }
 
   // ---------------------------------------------------------------------------------------------

@@ -157,22 +157,17 @@ void run_biloop_tiled(EmuT<real> &e, int TXb) {
   std::vector<real> tile((size_t)ge.rows * ge.cols + 1);
   std::vector<uint8_t> list((size_t)(c.W + 1) * TXb);
   std::vector<typename BT::Strand> st(TXb);
-  std::vector<int> rem;
   for (int side = 0; side < 2; side++)
     for (long long g0 = 0; g0 < c.NC; g0 += TXb) {
       ge.g0 = g0;
       auto fill = [&](int arr) {
-        for (int r = 5; r < 5 + ge.rows; r++)
-          for (int x = 0; x < ge.cols; x++)
-            tile[(size_t)(r - 5) * ge.cols + x] = side == 0 ? BT::load_left(c, ge, r, x, arr) : BT::load_right(c, ge, r, x, arr);
+        for (int x = 0; x < ge.cols; x++) {
+          const int lim = BT::tile_col_limit(c, ge, side == 0, x);
+          for (int r = 5; r < 5 + ge.rows; r++)
+            tile[(size_t)(r - 5) * ge.cols + x] = BT::tile_elem(c, ge, side == 0, arr, r, x, lim);
+        }
       };
-      const int nrem = BT::rem_count(side == 0, ge.cols, c.W);
-      rem.resize(nrem);
-      for (int x = 0; x < nrem; x++) rem[x] = BT::max_span_from(c, BT::rem_col(side == 0, ge, c.W, x));
-      for (int r = 5; r < 5 + ge.rows; r++)
-        for (int x = 0; x < ge.cols; x++)
-          tile[(size_t)(r - 5) * ge.cols + x] = side == 0 ? BT::load_left_checked(c, ge, rem.data(), r, x)
-                                                          : BT::load_right_checked(c, ge, rem.data(), r, x);
+      fill(A_STEMI);
       for (int t = 0; t < TXb; t++) {
         if (side == 0) {
           if (c.delta >= 5) BT::template left<0, 5>(c, ge, tile.data(), list.data(), t, st[t]);
