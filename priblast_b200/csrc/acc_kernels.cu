@@ -145,11 +145,20 @@ __device__ __forceinline__ double warp_sum(double v) {
 
 // Blocked scan: 32 consecutive positions per round, lane = position.  In "step" coordinates (step = i for
 // Alpha_outer, L - i for Beta_outer) both recurrences read  v[st] = v[st-1] + sum_d w(st,d) v[st-d].
+//  (0) the weights of the NEXT block stream into the other half of a double buffer with cp.async while
+//      this block is computed (the loads are HBM-latency bound, the chain below is shuffle-latency bound);
 //  (1) partners before the block: every lane sums its own <= W terms, no communication;
 //  (2) partners inside the block: 32 sequential sub-steps, each = one 64-bit broadcast + one FMA on the
 //      lanes at distance >= 5; the critical chain is  v[s] = v[s-1] + ext[s]  (ext[s] is final 5 sub-steps
 //      earlier), i.e. one shuffle + one add per position.
-// wbuf: per-warp [W + 2][32] weights (each lane only touches its own column), usm: us[] in shared memory.
+// wbuf: per-warp 2 x [W + 2][32] weights (each lane only touches its own column), usm: us[] in shared memory.
+template <int BYTES>
+__device__ __forceinline__ void cp_async_or_zero(void *smem_dst, const void *gsrc, bool pred) {
+  const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
+  const int src_bytes = pred ? BYTES : 0;  // 0: nothing is read, the destination is zero-filled
+  asm volatile("cp.async.ca.shared.global [%0], [%1], %2, %3;" ::"r"(dst), "l"(gsrc), "n"(BYTES), "r"(src_bytes) : "memory");
+}
+
 template <typename real, bool ALPHA>
 __device__ void warp_scan(const typename Core<real>::Ctx &c, int sq, double *ring, real *wbuf, const double *usm,
                           int lane) {
@@ -158,30 +167,38 @@ __device__ void warp_scan(const typename Core<real>::Ctx &c, int sq, double *rin
   const double kBig = 1.3407807929942597e154, kLn2 = 0.6931471805599453094;
   double *dst = ALPHA ? c.lao : c.lbo;
   const real *src = c.arr[ALPHA ? A_STEMDE : A_STEMD];
+  const int half = (W + 2) * 32;
   long long e2 = 0;
   if (lane == 0) {
     ring[0] = 1.0;
     dst[off + (ALPHA ? 0 : L)] = 0.0;
   }
+  auto stage = [&](int st0, real *buf) {  // this lane's weights of block st0: w(st, d), d = 5 .. W + 1
+    const int st = st0 + lane;
+    const int dhi = st <= L ? imin(W + 1, st) : 0;
+    const real *col = src + off + (ALPHA ? st : L - st);
+    for (int d = 5; d <= W + 1; ++d)
+      cp_async_or_zero<(int)sizeof(real)>(buf + (d - 5) * 32 + lane, d <= dhi ? col + (long long)d * c.NC : src, d <= dhi);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  int cur = 0;
+  stage(1, wbuf);
   __syncwarp();
   for (int st0 = 1; st0 <= L; st0 += 32) {
     const int st = st0 + lane;
     const bool ok = st <= L;
     const int i = ALPHA ? st : L - st;
     const int dhi = ok ? imin(W + 1, st) : 0;  // partner step st - d >= 0
-    // stage this position's weights, 8 independent loads in flight at a time
-    const real *col = src + off + i;
-    for (int d0 = 5; d0 <= W + 1; d0 += 8) {
-      real tmp[8];
-#pragma unroll
-      for (int k = 0; k < 8; ++k) tmp[k] = (d0 + k <= dhi) ? col[(long long)(d0 + k) * c.NC] : (real)0;
-#pragma unroll
-      for (int k = 0; k < 8; ++k)
-        if (d0 + k <= W + 1) wbuf[(d0 + k - 5) * 32 + lane] = tmp[k];
+    if (st0 + 32 <= L) {
+      stage(st0 + 32, wbuf + (cur ^ 1) * half);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
+    const real *wb = wbuf + cur * half;
     double ext = 0;
     for (int d = imax(5, lane + 1); d <= dhi; ++d)  // partners before the block
-      ext += (double)wbuf[(d - 5) * 32 + lane] * usm[d] * ring[(st - d) & 255];
+      ext += (double)wb[(d - 5) * 32 + lane] * usm[d] * ring[(st - d) & 255];
     double vprev = ring[(st0 - 1) & 255];
     double myv = 0;
     const int nsub = imin(32, L - st0 + 1);
@@ -190,7 +207,7 @@ __device__ void warp_scan(const typename Core<real>::Ctx &c, int sq, double *rin
       if (lane == s) myv = vs;
       vprev = vs;
       const int dd = lane - s;
-      if (dd >= 5 && dd <= dhi) ext += (double)wbuf[(dd - 5) * 32 + lane] * usm[dd] * vs;
+      if (dd >= 5 && dd <= dhi) ext += (double)wb[(dd - 5) * 32 + lane] * usm[dd] * vs;
     }
     if (ok) {
       ring[st & 255] = myv;
@@ -203,9 +220,11 @@ __device__ void warp_scan(const typename Core<real>::Ctx &c, int sq, double *rin
       e2 += 512;
       __syncwarp();
     }
+    cur ^= 1;
   }
 }
 
+// One warp per (sequence, direction): the two outer arrays of a sequence are independent chains.
 template <typename real>
 __global__ void __launch_bounds__(32 * kScanWarps) k_outer_scans_warp(typename Core<real>::Ctx c) {
   __shared__ double rings[kScanWarps][256];
@@ -214,12 +233,12 @@ __global__ void __launch_bounds__(32 * kScanWarps) k_outer_scans_warp(typename C
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int k = threadIdx.x; k < kMaxSpan + 8; k += blockDim.x) usm[k] = c.T->us[k];
   __syncthreads();
-  const int sq = blockIdx.x * kScanWarps + warp;
+  const int job = blockIdx.x * (blockDim.x >> 5) + warp;  // job = 2 * sequence + direction
+  const int sq = job >> 1;
   if (sq >= c.nseq) return;
-  real *wbuf = reinterpret_cast<real *>(scan_smem) + (size_t)warp * (c.W + 2) * 32;
-  warp_scan<real, true>(c, sq, rings[warp], wbuf, usm, lane);
-  __syncwarp();
-  warp_scan<real, false>(c, sq, rings[warp], wbuf, usm, lane);
+  real *wbuf = reinterpret_cast<real *>(scan_smem) + (size_t)warp * 2 * (c.W + 2) * 32;
+  if ((job & 1) == 0) warp_scan<real, true>(c, sq, rings[warp], wbuf, usm, lane);
+  else warp_scan<real, false>(c, sq, rings[warp], wbuf, usm, lane);
 }
 
 // Cooperative load of one band-array tile (rows = spans 5..W-1) into shared memory: thread = tile column,
@@ -391,6 +410,7 @@ struct Engine {
   int TC = 0;
   size_t tile_smem = 0;
   int TXb = 0;            // biloop tile width
+  int scan_warps = kScanWarps;  // warps (= scan jobs) per CTA of k_outer_scans_warp
   size_t bi_smem = 0;
   long long max_cols = 0;
 
@@ -622,8 +642,8 @@ int run_batch(prib_ctx *c, const Batch &b, bool timed) {
   real *scratch = reinterpret_cast<real *>(c->d_tile_scratch);
   k_inside_tile<real><<<tgrid, e.TC, e.tile_smem, st>>>(k, TX, ntiles, scratch);
   if (timed) CU(cudaEventRecord(c->evp[2], st));
-  k_outer_scans_warp<real><<<(b.n + kScanWarps - 1) / kScanWarps, 32 * kScanWarps,
-                             (size_t)kScanWarps * (c->W + 2) * 32 * sizeof(real), st>>>(k);
+  k_outer_scans_warp<real><<<(2 * b.n + e.scan_warps - 1) / e.scan_warps, 32 * e.scan_warps,
+                             (size_t)e.scan_warps * 2 * (c->W + 2) * 32 * sizeof(real), st>>>(k);
   if (timed) CU(cudaEventRecord(c->evp[3], st));
   k_outside_tile<real><<<tgrid, e.TC, e.tile_smem, st>>>(k, TX, ntiles, scratch);
   if (timed) CU(cudaEventRecord(c->evp[4], st));
@@ -695,6 +715,11 @@ int setup_engine(prib_ctx *c, const ScaleSpec &spec, size_t smem_max, std::strin
   if (e.bi_smem > smem_max) return fail(PRIB_ECUDA, "shared memory too small for the interior-loop tiles");
   CU(cudaFuncSetAttribute(k_outer_scans_warp<real>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                           (int)(smem_max - 16 * 1024)));
+  {  // double-buffered weights per warp: as many warps per CTA as fit (wide spans in FP64 take > 100 KB each)
+    const size_t per_warp = (size_t)2 * (c->W + 2) * 32 * sizeof(real);
+    e.scan_warps = (int)std::max<size_t>(1, std::min<size_t>(kScanWarps, (smem_max - 16 * 1024) / per_warp));
+    if (per_warp > smem_max - 16 * 1024) return fail(PRIB_ECUDA, "shared memory too small for the outer-array scans");
+  }
 #define PRIB_BI_ATTR(L, U, X) \
   CU(cudaFuncSetAttribute((k_biloop_tile<real, L, U, X>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max))
   PRIB_BI_ATTR(true, 5, 512); PRIB_BI_ATTR(true, 2, 512); PRIB_BI_ATTR(false, 5, 512); PRIB_BI_ATTR(false, 2, 512);
