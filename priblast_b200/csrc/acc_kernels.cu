@@ -329,6 +329,38 @@ __global__ void __launch_bounds__(kThreads) k_finalize(typename Core<real>::Ctx 
   if (g < c.NC) Core<real>::finalize_position(c, g);
 }
 
+// Device-side batch layout (what build_layout() of acc_tables.cpp does on the host for the tests): the host
+// only ships the raw sequence bytes; base coding (raccess.cpp:55-68) and the column -> sequence map are
+// produced here, one thread per column.
+__device__ __forceinline__ uint8_t encode_base_dev(unsigned char ch) {
+  ch |= 0x20;  // fold case
+  return ch == 'a' ? 1 : ch == 'c' ? 2 : ch == 'g' ? 3 : (ch == 'u' || ch == 't') ? 4 : 0;
+}
+__global__ void __launch_bounds__(256) k_build_layout(long long NC, int nseq, const long long *seq_off,
+                                                       const int32_t *seq_len, const long long *raw_off,
+                                                       const unsigned char *raw, uint8_t *S, int32_t *col_seq) {
+  const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= NC) return;
+  int lo = 0, hi = nseq;  // last sequence with seq_off <= g
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (seq_off[mid] <= g) lo = mid + 1;
+    else hi = mid;
+  }
+  const int sq = lo - 1;
+  int32_t cs = -1;
+  uint8_t b = 0;
+  if (sq >= 0) {
+    const long long i = g - seq_off[sq];
+    if (i <= seq_len[sq]) {
+      cs = sq;
+      if (i >= 1) b = encode_base_dev(raw[raw_off[sq] + i - 1]);
+    }
+  }
+  S[g] = b;
+  col_seq[g] = cs;
+}
+
 // Issue-rate probes for the roofline denominators (MEASURED_PEAKS.json has no SFU / FP32 /
 // FP64 figure, so they are measured here): 8 independent dependency chains per thread.
 template <int OP>
@@ -398,8 +430,9 @@ struct Batch {
   std::vector<long long> acc_off, cond_off;  // absolute float offsets into d_out
   uint8_t *d_S = nullptr;
   int32_t *d_col_seq = nullptr, *d_seq_len = nullptr, *d_flags = nullptr;
-  long long *d_seq_off = nullptr, *d_acc_off = nullptr, *d_cond_off = nullptr;
-  long long cap_cols = 0, cap_seqs = 0;  // device buffers are grow-only and reused from stage to stage
+  long long *d_seq_off = nullptr, *d_acc_off = nullptr, *d_cond_off = nullptr, *d_raw_off = nullptr;
+  unsigned char *d_raw = nullptr;
+  long long cap_cols = 0, cap_seqs = 0, cap_raw = 0;  // device buffers are grow-only and reused from stage to stage
 };
 
 template <typename real>
@@ -450,6 +483,8 @@ struct prib_ctx {
   bool staged = false, computed = false;
   float *h_stage = nullptr;
   long long h_stage_floats = 0;
+  unsigned char *h_in = nullptr;  // pinned staging of one batch's inputs
+  size_t h_in_cap = 0;
   int32_t *h_flags = nullptr;
   long long h_flags_cap = 0;
   prib_acc_counters cnt{};
@@ -469,6 +504,8 @@ void free_batch(Batch &b) {
   cudaFree(b.d_seq_off);
   cudaFree(b.d_acc_off);
   cudaFree(b.d_cond_off);
+  cudaFree(b.d_raw_off);
+  cudaFree(b.d_raw);
   b = Batch();
 }
 
@@ -541,18 +578,44 @@ int make_batch(prib_ctx *c, const std::vector<int> &ids, const std::vector<long 
   b.acc_off = acc_off;
   b.cond_off = cond_off;
   b.n = (int)ids.size();
-  std::vector<const char *> sp(b.n);
-  std::vector<int32_t> sl(b.n);
+  // host side: offsets only; the raw bytes go up as they are (pinned staging), the device builds the layout
+  const size_t n1 = (size_t)std::max(b.n, 1);
+  std::vector<int32_t> sl(n1);
+  std::vector<long long> so(n1), ro(n1 + 1);
   b.nt = 0;
+  long long g = kPad;
   for (int k = 0; k < b.n; k++) {
-    sp[k] = c->seqs[ids[k]].data();
     sl[k] = (int32_t)c->seqs[ids[k]].size();
+    so[k] = g;
+    ro[k] = b.nt;
+    g += layout_columns(sl[k]);
     b.nt += sl[k];
   }
-  BatchLayout lay;
-  build_layout(b.n, sp.data(), sl.data(), lay);
-  b.NC = lay.NC;
-  const size_t n1 = (size_t)std::max(b.n, 1);
+  ro[b.n] = b.nt;
+  b.NC = (g + kPad + 31) / 32 * 32;
+  const long long raw_bytes = std::max<long long>(b.nt, 1);
+  // one pinned staging block: [raw | seq_len | seq_off | raw_off | acc_off | cond_off]
+  const size_t need = (size_t)((raw_bytes + 15) / 16 * 16) + n1 * 4 + 16 + (n1 * 4 + 1) * 8;
+  if (c->h_in_cap < need) {
+    if (c->h_in) cudaFreeHost(c->h_in);
+    c->h_in = nullptr;
+    c->h_in_cap = 0;
+    CU(cudaMallocHost(&c->h_in, need));
+    c->h_in_cap = need;
+  }
+  unsigned char *h_raw = c->h_in;
+  long long *h_so = reinterpret_cast<long long *>(c->h_in + (raw_bytes + 15) / 16 * 16);
+  long long *h_ro = h_so + n1, *h_ao = h_ro + n1 + 1, *h_co = h_ao + n1;
+  int32_t *h_sl = reinterpret_cast<int32_t *>(h_co + n1);
+  for (int k = 0; k < b.n; k++) {
+    std::memcpy(h_raw + ro[k], c->seqs[ids[k]].data(), (size_t)sl[k]);
+    h_so[k] = so[k];
+    h_ro[k] = ro[k];
+    h_ao[k] = acc_off[k];
+    h_co[k] = cond_off[k];
+    h_sl[k] = sl[k];
+  }
+  h_ro[b.n] = b.nt;
   if (b.NC > b.cap_cols) {
     cudaFree(b.d_S);
     cudaFree(b.d_col_seq);
@@ -563,35 +626,48 @@ int make_batch(prib_ctx *c, const std::vector<int> &ids, const std::vector<long 
     CU(cudaMalloc(&b.d_col_seq, (size_t)b.NC * sizeof(int32_t)));
     b.cap_cols = b.NC;
   }
+  if (raw_bytes > b.cap_raw) {
+    cudaFree(b.d_raw);
+    b.d_raw = nullptr;
+    b.cap_raw = 0;
+    CU(cudaMalloc(&b.d_raw, (size_t)raw_bytes));
+    b.cap_raw = raw_bytes;
+  }
   if ((long long)n1 > b.cap_seqs) {
     cudaFree(b.d_seq_len);
     cudaFree(b.d_flags);
     cudaFree(b.d_seq_off);
     cudaFree(b.d_acc_off);
     cudaFree(b.d_cond_off);
+    cudaFree(b.d_raw_off);
     b.d_seq_len = b.d_flags = nullptr;
-    b.d_seq_off = b.d_acc_off = b.d_cond_off = nullptr;
+    b.d_seq_off = b.d_acc_off = b.d_cond_off = b.d_raw_off = nullptr;
     b.cap_seqs = 0;
     CU(cudaMalloc(&b.d_seq_len, n1 * sizeof(int32_t)));
     CU(cudaMalloc(&b.d_flags, n1 * sizeof(int32_t)));
     CU(cudaMalloc(&b.d_seq_off, n1 * sizeof(long long)));
     CU(cudaMalloc(&b.d_acc_off, n1 * sizeof(long long)));
     CU(cudaMalloc(&b.d_cond_off, n1 * sizeof(long long)));
+    CU(cudaMalloc(&b.d_raw_off, (n1 + 1) * sizeof(long long)));
     b.cap_seqs = (long long)n1;
   }
   CU(cudaEventRecord(c->ev0, c->stream));
-  CU(cudaMemcpyAsync(b.d_S, lay.S.data(), (size_t)b.NC, cudaMemcpyHostToDevice, c->stream));
-  CU(cudaMemcpyAsync(b.d_col_seq, lay.col_seq.data(), (size_t)b.NC * 4, cudaMemcpyHostToDevice, c->stream));
-  CU(cudaMemcpyAsync(b.d_seq_len, sl.data(), (size_t)b.n * 4, cudaMemcpyHostToDevice, c->stream));
-  CU(cudaMemcpyAsync(b.d_seq_off, lay.seq_off.data(), (size_t)b.n * 8, cudaMemcpyHostToDevice, c->stream));
-  CU(cudaMemcpyAsync(b.d_acc_off, acc_off.data(), (size_t)b.n * 8, cudaMemcpyHostToDevice, c->stream));
-  CU(cudaMemcpyAsync(b.d_cond_off, cond_off.data(), (size_t)b.n * 8, cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemcpyAsync(b.d_raw, h_raw, (size_t)raw_bytes, cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemcpyAsync(b.d_seq_len, h_sl, (size_t)b.n * 4, cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemcpyAsync(b.d_seq_off, h_so, (size_t)b.n * 8, cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemcpyAsync(b.d_raw_off, h_ro, (size_t)(b.n + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemcpyAsync(b.d_acc_off, h_ao, (size_t)b.n * 8, cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemcpyAsync(b.d_cond_off, h_co, (size_t)b.n * 8, cudaMemcpyHostToDevice, c->stream));
   CU(cudaEventRecord(c->ev1, c->stream));
-  CU(cudaStreamSynchronize(c->stream));  // host staging vectors go out of scope
+  k_build_layout<<<(unsigned)((b.NC + 255) / 256), 256, 0, c->stream>>>(b.NC, b.n, b.d_seq_off, b.d_seq_len,
+                                                                         b.d_raw_off, b.d_raw, b.d_S, b.d_col_seq);
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(c->stream));  // the pinned staging block is reused by the next batch
   float ms = 0;
   CU(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
   c->cnt.h2d_ms += ms;
-  c->cnt.h2d_bytes += b.NC * 5 + (long long)b.n * 28;
+  c->cnt.h2d_bytes += raw_bytes + (long long)b.n * 36 + 8;
+  c->cnt.kernel_launches += 1;
   return PRIB_OK;
 }
 
@@ -831,6 +907,7 @@ void prib_acc_destroy(prib_ctx *c) {
   c->e64.release();
   cudaFree(c->d_log);
   if (c->h_stage) cudaFreeHost(c->h_stage);
+  if (c->h_in) cudaFreeHost(c->h_in);
   if (c->h_flags) cudaFreeHost(c->h_flags);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
@@ -957,16 +1034,36 @@ int prib_acc_fetch(prib_ctx *c, float *out, const int64_t *acc_off, const int64_
   if (!c || !out || !acc_off || !cond_off) return fail(PRIB_EINVAL, "null argument");
   if (!c->computed) return fail(PRIB_ESTATE, "prib_acc_fetch called before prib_acc_compute");
   CU(cudaSetDevice(c->prm.device));
-  if (c->h_stage_floats < c->out_floats) {
-    if (c->h_stage) cudaFreeHost(c->h_stage);
-    c->h_stage = nullptr;
-    CU(cudaMallocHost(&c->h_stage, (size_t)c->out_floats * sizeof(float)));
-    c->h_stage_floats = c->out_floats;
+  // Fast path: the caller's buffer is page-locked (prib_host_alloc / cudaHostRegister) and uses the packed
+  // [acc L | cond L] layout in caller order: the device image is copied straight into it.
+  bool direct = c->out_floats > 0;
+  {
+    long long o = 0;
+    for (size_t k = 0; k < c->seqs.size() && direct; k++) {
+      const long long L = (long long)c->seqs[k].size();
+      direct = acc_off[k] == o && cond_off[k] == o + L;
+      o += 2 * L;
+    }
+    if (direct) {
+      cudaPointerAttributes at;
+      direct = cudaPointerGetAttributes(&at, out) == cudaSuccess && at.type == cudaMemoryTypeHost;
+      cudaGetLastError();  // an unregistered pointer is not an error for us
+    }
+  }
+  float *dst = out;
+  if (!direct) {
+    if (c->h_stage_floats < c->out_floats) {
+      if (c->h_stage) cudaFreeHost(c->h_stage);
+      c->h_stage = nullptr;
+      c->h_stage_floats = 0;
+      CU(cudaMallocHost(&c->h_stage, (size_t)c->out_floats * sizeof(float)));
+      c->h_stage_floats = c->out_floats;
+    }
+    dst = c->h_stage;
   }
   if (c->out_floats > 0) {
     CU(cudaEventRecord(c->ev0, c->stream));
-    CU(cudaMemcpyAsync(c->h_stage, c->d_out, (size_t)c->out_floats * sizeof(float), cudaMemcpyDeviceToHost,
-                       c->stream));
+    CU(cudaMemcpyAsync(dst, c->d_out, (size_t)c->out_floats * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaEventRecord(c->ev1, c->stream));
   }
   CU(cudaStreamSynchronize(c->stream));
@@ -977,12 +1074,14 @@ int prib_acc_fetch(prib_ctx *c, float *out, const int64_t *acc_off, const int64_
     c->cnt.d2h_ms += ms;
     c->cnt.d2h_bytes += c->out_floats * (long long)sizeof(float);
   }
-  long long o = 0;
-  for (size_t k = 0; k < c->seqs.size(); k++) {
-    const size_t L = c->seqs[k].size();
-    std::memcpy(out + acc_off[k], c->h_stage + o, sizeof(float) * L);
-    std::memcpy(out + cond_off[k], c->h_stage + o + L, sizeof(float) * L);
-    o += 2LL * (long long)L;
+  if (!direct) {
+    long long o = 0;
+    for (size_t k = 0; k < c->seqs.size(); k++) {
+      const size_t L = c->seqs[k].size();
+      std::memcpy(out + acc_off[k], c->h_stage + o, sizeof(float) * L);
+      std::memcpy(out + cond_off[k], c->h_stage + o + L, sizeof(float) * L);
+      o += 2LL * (long long)L;
+    }
   }
   return PRIB_OK;
 }
