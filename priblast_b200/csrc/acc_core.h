@@ -255,8 +255,9 @@ static PRIB_HD void inside_cell(const Ctx &c, long long g, int d) {
     if (smax >= 2) {
       const int t2 = T.rt[T.bp[s[2]][s[d - 1]]];  // 1x1 :797-798
       acc += c.ld(A_STEM, d - 2, g + 1) * c.e_int11[idx11(te, t2, si1, sj)];
-      real bs = 0;  // longer bulges :788-795
-      for (int u = 2; u <= smax; ++u) bs += T.e_bulge[u] * (c.ld(A_STEMB, d - u, g + u) + c.ld(A_STEMB, d - u, g));
+      real bs = 0;  // longer bulges :788-795; lengths >= 4 first, then 2 and 3 (the order of the tile kernels)
+      for (int u = 4; u <= smax; ++u) bs += T.e_bulge[u] * (c.ld(A_STEMB, d - u, g + u) + c.ld(A_STEMB, d - u, g));
+      for (int u = 2; u <= imin(3, smax); ++u) bs += T.e_bulge[u] * (c.ld(A_STEMB, d - u, g + u) + c.ld(A_STEMB, d - u, g));
       acc += T.tau[te] * bs;
     }
     if (smax >= 3) {  // 1x2 and 2x1 :799-804

@@ -77,12 +77,12 @@ k_inside_tile(typename Core<real>::Ctx c, int TX, long long ntiles, real *scratc
     TL::col_state(c, ge.g0 + t, cs);
     __syncthreads();
     for (int d0 = dfirst; d0 <= W + 1; d0 += kTT) {
-      real gs[kTT], mb[kTT];
-      TL::template inside_deep<TC>(T, ge, sm, scrM1, scrM2, t, d0, gs, mb);
+      real gs[kTT], mb[kTT], bs[kTT];
+      TL::template inside_deep<TC>(T, ge, sm, scrM1, scrM2, t, d0, gs, mb, bs);
 #pragma unroll
       for (int k = 0; k < kTT; ++k) {
         if (d0 + k >= kTurn) {  // uniform
-          TL::template inside_shallow<TC>(c, T, ge, sm, scrM1, scrM2, t, cs, d0 + k, gs[k], mb[k]);
+          TL::template inside_shallow<TC>(c, T, ge, sm, scrM1, scrM2, t, cs, d0 + k, gs[k], mb[k], bs[k]);
           __syncthreads();
         }
       }

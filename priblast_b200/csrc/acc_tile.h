@@ -100,12 +100,12 @@ struct Tile {
     return s;
   }
 
-  // One source row of the inside generic stencil (row d0 - S of the Alpha_stemI ring) for all kTT targets;
+  // One source row of the inside stencils (row d0 - S of the Alpha_stemI / Alpha_stemB rings) for all kTT targets;
   // S is a template parameter so that every coefficient choice and column offset is resolved at compile
   // time (a plain `#pragma unroll` nest of this size is not unrolled by nvcc).
   template <int S, int TCC>
-  static PRIB_HD void in_rows(const InSmem &sm, int TC, int t, int d0, const real *cf, real g0, real g1, real g2,
-                              real g3, real g4, real g5, real g6, real (&gs)[kTT]) {
+  static PRIB_HD void in_rows(const InSmem &sm, int TC, int t, int d0, const real *cf, const real *bu, real g0, real g1,
+                              real g2, real g3, real g4, real g5, real g6, real (&gs)[kTT], real (&bs)[kTT]) {
     if (d0 - S >= 5) {  // rows below span 5 hold no stems; same cut as `sum <= min(30, d - 5)` per target
       const real *row = sm.stemI + ((d0 - S) & (kRingIn - 1)) * (TCC > 0 ? TCC : TC) + t;
       real rs[kTT];
@@ -124,27 +124,34 @@ struct Tile {
 #pragma unroll
       for (int k = 0; k < kTT; ++k)
         if (S + k >= 4 && S + k <= kMaxLoop) gs[k] += cf[S + k] * rs[k];
+      // bulges of length u = S + k >= 4 out of the Alpha_stemB ring (same slot): inner cells (i + u, j) and (i, j - u)
+      const real *rowB = row + kRingIn * (TCC > 0 ? TCC : TC);
+      const real b0 = rowB[0];
+#pragma unroll
+      for (int k = 0; k < kTT; ++k)
+        if (S + k >= 4 && S + k <= kMaxLoop) bs[k] += bu[S + k] * (rowB[S + k] + b0);
     }
-    if constexpr (S < kMaxLoop) in_rows<S + 1, TCC>(sm, TC, t, d0, cf, g0, g1, g2, g3, g4, g5, g6, gs);
+    if constexpr (S < kMaxLoop) in_rows<S + 1, TCC>(sm, TC, t, d0, cf, bu, g0, g1, g2, g3, g4, g5, g6, gs, bs);
   }
 
   // ---------------------------------------------------------------------------------------------
   // inside, deep step: thread t = local column t; targets are the cells (i, i + d0 + k), k = 0..kTT-1.
   //   gs[k] = generic interior loops of Alpha_stemend (raccess.cpp:201-215, 808-812) as a stencil over the
   //           Alpha_stemI ring: source row d0 - s serves target k with loop size s + k;
+  //   bs[k] = bulges of length >= 4 (:788-795) over the Alpha_stemB ring, same rows;
   //   mb[k] = Alpha_multibif (:131-143) from the per-CTA scratch rows scrM1 / scrM2 ([(W+4)][TC]).
   // Only rows <= d0 - 1 are read, so all kTT targets are legal at once.  TCC: compile-time tile width
   // (0 = ge.TC at run time, host emulation): every ring row offset becomes an immediate.
   // ---------------------------------------------------------------------------------------------
   template <int TCC = 0>
   static PRIB_HD void inside_deep(const ST &T, const Geo &ge, const InSmem &sm, const real *scrM1, const real *scrM2,
-                                  int t, int d0, real (&gs)[kTT], real (&mb)[kTT]) {
+                                  int t, int d0, real (&gs)[kTT], real (&mb)[kTT], real (&bs)[kTT]) {
     const int TC = TCC > 0 ? TCC : ge.TC;
-    const real *cf = K::cf_tab(T);
+    const real *cf = K::cf_tab(T), *bu = K::bulge_tab(T);
     const real g0 = T.cg[0], g1 = T.cg[1], g2 = T.cg[2], g3 = T.cg[3], g4 = T.cg[4], g5 = T.cg[5], g6 = T.cg[6];
 #pragma unroll
-    for (int k = 0; k < kTT; ++k) gs[k] = mb[k] = 0;
-    in_rows<1, TCC>(sm, TC, t, d0, cf, g0, g1, g2, g3, g4, g5, g6, gs);
+    for (int k = 0; k < kTT; ++k) gs[k] = mb[k] = bs[k] = 0;
+    in_rows<1, TCC>(sm, TC, t, d0, cf, bu, g0, g1, g2, g3, g4, g5, g6, gs, bs);
     // multibif: mb[k] = sum over m = 5 .. d0+k-5 of multi1[m][t] * multi2[d0+k-m][t+m]; a multi1 element
     // serves all kTT targets.  Two running pointers, every other offset is an immediate.
     {
@@ -183,7 +190,7 @@ struct Tile {
   // ---------------------------------------------------------------------------------------------
   template <int TCC = 0>
   static PRIB_HD void inside_shallow(const Ctx &c, const ST &T, const Geo &ge, const InSmem &sm, real *scrM1,
-                                     real *scrM2, int t, const ColState &cs, int d, real gs, real mb) {
+                                     real *scrM2, int t, const ColState &cs, int d, real gs, real mb, real bs) {
     const int TC = TCC > 0 ? TCC : ge.TC;
     const real *bu = K::bulge_tab(T);
     real stem = 0, stemI = 0, stemB = 0, stemD = 0, se = 0, mu = 0, m1 = 0, m2 = 0;
@@ -222,9 +229,9 @@ struct Tile {
         if (smax >= 2) {
           const int t2 = T.rt[T.bp[s[2]][s[d - 1]]];
           a += st2[1] * c.e_int11[idx11(te, t2, si1, sj)];
-          real bs = 0;
+          // long bulges: lengths >= 4 were summed by the deep step, 2 and 3 (rows d-2, d-3) follow here
 #pragma unroll
-          for (int u = 2; u <= kMaxLoop; ++u) {
+          for (int u = 2; u <= 3; ++u) {
             if (u <= smax) {
               const real *row = sm.stemB + ((d - u) & (kRingIn - 1)) * TC + t;
               bs += bu[u] * (row[u] + row[0]);

@@ -100,7 +100,7 @@ void run_dp_tiled(EmuT<real> &e, int TC) {
   std::vector<typename TL::ColState> cs(TC);
   real *base = smem.data() + kTilePad;
   const int dfirst = TL::first_group(W);
-  struct InDeep { real gs[kTT], mb[kTT]; };
+  struct InDeep { real gs[kTT], mb[kTT], bs[kTT]; };
   std::vector<InDeep> din(TC);
   std::vector<typename TL::OutDeep> dout(TC);
   real *scrM1 = scr.data(), *scrM2 = scr.data() + (size_t)(W + 4) * TC;
@@ -112,11 +112,12 @@ void run_dp_tiled(EmuT<real> &e, int TC) {
     for (int t = 0; t < TC; t++) TL::col_state(c, ge.g0 + t, cs[t]);
     typename TL::InSmem sm = TL::carve_in(base, TC, sS.data());
     for (int d0 = dfirst; d0 <= W + 1; d0 += kTT) {
-      for (int t = 0; t < TC; t++) TL::template inside_deep<0>(*c.T, ge, sm, scrM1, scrM2, t, d0, din[t].gs, din[t].mb);
+      for (int t = 0; t < TC; t++) TL::template inside_deep<0>(*c.T, ge, sm, scrM1, scrM2, t, d0, din[t].gs, din[t].mb, din[t].bs);
       for (int k = 0; k < kTT; k++) {
         if (d0 + k < kTurn) continue;
         for (int t = 0; t < TC; t++)
-          TL::template inside_shallow<0>(c, *c.T, ge, sm, scrM1, scrM2, t, cs[t], d0 + k, din[t].gs[k], din[t].mb[k]);
+          TL::template inside_shallow<0>(c, *c.T, ge, sm, scrM1, scrM2, t, cs[t], d0 + k, din[t].gs[k], din[t].mb[k],
+                                         din[t].bs[k]);
       }
     }
   }
