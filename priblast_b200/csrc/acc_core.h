@@ -38,7 +38,6 @@ enum Arr {
   A_STEMI,     // A_STEM * exp(mismatchI[rt t][s[j+1]][s[i]])       inner-pair factor of :810-811
   A_STEMB,     // A_STEM * tau[t]                                   inner-pair TermAU of :789-794
   A_STEMD,     // A_STEM * exp(Dangle(t,i,j))                       :151, :236, :266
-  A_STEMDE,    // same value, stored at the END column (g+d) for the Alpha_outer scan
   A_STEMEND,   // Alpha_stemend                                     :193-226
   A_MULTI,     // Alpha_multi                                       :177-191
   A_MULTI1,    // Alpha_multi1                                      :164-175
@@ -288,7 +287,6 @@ static PRIB_HD void inside_cell(const Ctx &c, long long g, int d) {
   c.at(A_STEMI, d, g) = t ? stem * T.e_mmI[T.rt[t]][sj1][si] : 0;
   c.at(A_STEMB, d, g) = stem * T.tau[t];
   c.at(A_STEMD, d, g) = stemD;
-  c.at(A_STEMDE, d, g + d) = stemD;
   c.at(A_STEMEND, d, g) = se;
   c.at(A_MULTI, d, g) = mu;
   c.at(A_MULTI1, d, g) = m1;
@@ -309,7 +307,7 @@ static PRIB_HD void scan_alpha_outer(const Ctx &c, int sq, double *ring) {
   for (int i = 1; i <= L; ++i) {
     double v = ring[(i - 1) & 255];
     const int dmax = imin(W + 1, i);
-    for (int d = 5; d <= dmax; ++d) v += (double)c.ld(A_STEMDE, d, off + i) * c.T->us[d] * ring[(i - d) & 255];
+    for (int d = 5; d <= dmax; ++d) v += (double)c.ld(A_STEMD, d, off + i - d) * c.T->us[d] * ring[(i - d) & 255];
     if (v > kBig) {
       for (int k = imax(0, i - W - 2); k < i; ++k) ring[k & 255] *= 1.0 / kBig;
       v *= 1.0 / kBig;

@@ -166,7 +166,7 @@ __device__ void warp_scan(const typename Core<real>::Ctx &c, int sq, double *rin
   const long long off = c.seq_off[sq];
   const double kBig = 1.3407807929942597e154, kLn2 = 0.6931471805599453094;
   double *dst = ALPHA ? c.lao : c.lbo;
-  const real *src = c.arr[ALPHA ? A_STEMDE : A_STEMD];
+  const real *src = c.arr[A_STEMD];  // cell (st - d, st) sits at column st - d: row stride NC - 1 for Alpha_outer
   const int half = (W + 2) * 32;
   long long e2 = 0;
   if (lane == 0) {
@@ -178,7 +178,8 @@ __device__ void warp_scan(const typename Core<real>::Ctx &c, int sq, double *rin
     const int dhi = st <= L ? imin(W + 1, st) : 0;
     const real *col = src + off + (ALPHA ? st : L - st);
     for (int d = 5; d <= W + 1; ++d)
-      cp_async_or_zero<(int)sizeof(real)>(buf + (d - 5) * 32 + lane, d <= dhi ? col + (long long)d * c.NC : src, d <= dhi);
+      cp_async_or_zero<(int)sizeof(real)>(buf + (d - 5) * 32 + lane, d <= dhi ? col + (long long)d * (c.NC - (ALPHA ? 1 : 0)) : src,
+                                           d <= dhi);
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
   int cur = 0;

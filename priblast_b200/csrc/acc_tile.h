@@ -267,11 +267,10 @@ struct Tile {
     // persistent outputs: owned columns only
     if (t < ge.TX && i >= 0 && j <= L) {
       const long long g = ge.g0 + t;
-      c.at(A_STEM, d, g) = stem;
+      if (c.delta == 2) c.at(A_STEM, d, g) = stem;  // only the 2x1 / 2x2 loops of delta == 2 read it (BiTile)
       c.at(A_STEMI, d, g) = stemI;
       c.at(A_STEMB, d, g) = stemB;
       c.at(A_STEMD, d, g) = stemD;
-      c.at(A_STEMDE, d, g + d) = stemD;
       c.at(A_MULTI, d, g) = mu;
       c.at(A_MULTI1, d, g) = m1;
       c.at(A_MULTI2, d, g) = m2;
