@@ -7,7 +7,7 @@
 //   k_outer_scans_warp               the two outer arrays, one warp per sequence
 //   k_biloop_left/right, k_hairpin_suffix, k_finalize   accessibility, one thread per column
 // Every kernel exists for float and double band arithmetic.  The float engine (span-scaled, range
-// guarded) is the fast path for W <= kFp32MaxSpan; sequences whose stored values leave the safe range
+// guarded) is the fast path (spans up to kFp32MaxSpan); sequences whose stored values leave the safe range
 // are flagged on the device and re-run by the double engine inside the same prib_acc_compute call, on
 // the GPU.  There is no CPU path.
 #include <cuda_runtime.h>
@@ -32,7 +32,8 @@ namespace {
 
 constexpr int kThreads = 128;
 constexpr int kScanWarps = 4;
-constexpr int kFp32MaxSpan = 100;
+constexpr int kFp32MaxSpan = kMaxSpan;  // always try FP32 first: at W = 150 a quarter of random 2 kb sequences
+                                         // is flagged and re-run in FP64, still 1.7x faster than FP64 for all (profiles/r1/sweep.json)
 // widest CTA of the tile kernels per precision (227 KB of rings / 80 rows): bounds the register budget
 template <typename real> struct TileMaxThreads { static constexpr int value = sizeof(real) == 4 ? 704 : 320; };
 
@@ -849,7 +850,9 @@ int prib_acc_create(prib_ctx **out, const prib_acc_params *params) {
   c->W = params->maximal_span;
   c->delta = params->min_accessible_length;
   const char *pe = getenv("PRIB_PRECISION");
-  c->use_fp32 = params->mode == 0 && c->W <= kFp32MaxSpan && !(pe && strcmp(pe, "fp64") == 0);
+  int fp32_max_span = kFp32MaxSpan;
+  if (const char *me = getenv("PRIB_FP32_MAXSPAN")) fp32_max_span = atoi(me);  // tuning knob
+  c->use_fp32 = params->mode == 0 && c->W <= fp32_max_span && !(pe && strcmp(pe, "fp64") == 0);
   auto bail = [&](int code) {
     std::string keep = g_err;
     prib_acc_destroy(c);
