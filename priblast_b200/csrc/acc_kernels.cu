@@ -135,15 +135,9 @@ k_outside_tile(typename Core<real>::Ctx c, int TX, long long ntiles, real *scrat
   }
 }
 
-// Outer arrays (raccess.cpp:230-241, 260-271): serial in the position, but each step is a W-term dot
-// product: lanes split the terms, a butterfly adds them, the window of scaled values lives in shared
-// memory.  Values stay linear with an exact power-of-two rescale; logs are taken 32 positions at a time.
-__device__ __forceinline__ double warp_sum(double v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
-
+// Outer arrays (raccess.cpp:230-241, 260-271): serial in the position.  Values stay linear with an exact
+// power-of-two rescale; the window of scaled values lives in shared memory; logs are taken 32 positions
+// at a time.
 // Blocked scan: 32 consecutive positions per round, lane = position.  In "step" coordinates (step = i for
 // Alpha_outer, L - i for Beta_outer) both recurrences read  v[st] = v[st-1] + sum_d w(st,d) v[st-d].
 //  (0) the weights of the NEXT block stream into the other half of a double buffer with cp.async while

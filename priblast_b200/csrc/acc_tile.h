@@ -640,7 +640,7 @@ struct BiTile {
     if (!K::col_info(c, g, ci)) return;
     st.active = true;
     const ST &T = *c.T;
-    const real *cv = K::conv_tab(T), *bu = K::bulge_tab(T);
+    const real *cv = K::conv_tab(T);
     const int L = ci.L, i = ci.i, W = c.W, delta = c.delta, TXb = ge.TXb, cols = COLS > 0 ? COLS : ge.cols;
     const uint8_t *s = c.S + g;
     real (&ml)[kMaxLoop + 1] = st.w;
@@ -722,7 +722,7 @@ struct BiTile {
     if (!K::col_info(c, g2, ci)) return;
     st.active = true;
     const ST &T = *c.T;
-    const real *cv = K::conv_tab(T), *bu = K::bulge_tab(T);
+    const real *cv = K::conv_tab(T);
     const int L = ci.L, jp = ci.i, W = c.W, delta = c.delta, TXb = ge.TXb, cols = COLS > 0 ? COLS : ge.cols;
     real (&mr)[kMaxLoop + 1] = st.w;
 #pragma unroll
