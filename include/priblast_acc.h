@@ -110,6 +110,12 @@ const char *prib_version(void);
 int64_t prib_acc_record_bytes(int32_t len, int32_t delta);
 int64_t prib_acc_write_record(const float *acc, const float *cond, int32_t len, int32_t delta, void *dst);
 
+/* Suffix array of one encoded database page on the GPU.  Replaces `sais(T, SA, n)` (sais.cpp:656) as called
+ * by DbConstruction::ConstructSuffixArray (db_construction.cpp:330-335): text = the reversed, encoded,
+ * sentinel-terminated sequences of the page (symbols 0..9, encoder.hpp:36-78), sa = n int32 in host memory.
+ * The suffix array of a text is unique, so the bytes equal the reference's.  Blocking; uses `device`. */
+int prib_suffix_array(const unsigned char *text, int32_t n, int32_t *sa, int32_t device);
+
 #ifdef __cplusplus
 }
 #endif

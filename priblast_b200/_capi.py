@@ -65,6 +65,7 @@ SIGNATURES = {
     "prib_version": (ctypes.c_char_p, []),
     "prib_acc_record_bytes": (ctypes.c_int64, [ctypes.c_int32, ctypes.c_int32]),
     "prib_acc_write_record": (ctypes.c_int64, [c_f32p, c_f32p, ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p]),
+    "prib_suffix_array": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, c_i32p, ctypes.c_int32]),
 }
 
 _lib = None

@@ -20,8 +20,8 @@ NVCC_FLAGS = [
     "-ccbin", HOST_CXX,
 ]
 
-SOURCES = ["acc_kernels.cu", "acc_tables.cpp"]
-DEPS = SOURCES + ["acc_core.h", "acc_tables.h", "turner_params.h", "turner_blob.c",
+SOURCES = ["acc_kernels.cu", "sa_gpu.cu", "acc_tables.cpp"]
+DEPS = SOURCES + ["acc_core.h", "acc_tile.h", "acc_tables.h", "turner_params.h", "turner_blob.c",
                   os.path.join("..", "..", "include", "priblast_acc.h")]
 
 
@@ -42,11 +42,23 @@ def is_stale() -> bool:
 def build_library(force: bool = False, verbose: bool = False, extra: list[str] | None = None) -> str:
     if not force and not is_stale():
         return LIB
-    obj = os.path.join(CSRC, "turner_blob.o")
+    from concurrent.futures import ThreadPoolExecutor
+    blob_obj = os.path.join(CSRC, "turner_blob.o")
     subprocess.run([HOST_CC, "-O2", "-fPIC", "-c", os.path.join(CSRC, "turner_blob.c"),
-                    f'-DPRIB_TURNER_BIN="{BLOB}"', "-o", obj], check=True)
-    cmd = [nvcc_path(), *NVCC_FLAGS, *(extra or []), "-shared",
-           *[os.path.join(CSRC, s) for s in SOURCES], obj, "-o", LIB]
+                    f'-DPRIB_TURNER_BIN="{BLOB}"', "-o", blob_obj], check=True)
+    nvcc = nvcc_path()
+
+    def compile_one(src: str) -> str:  # one object per source, compiled side by side (CUB makes sa_gpu.cu slow)
+        obj = os.path.join(CSRC, os.path.splitext(src)[0] + ".o")
+        cmd = [nvcc, *NVCC_FLAGS, *(extra or []), "-c", os.path.join(CSRC, src), "-o", obj]
+        if verbose:
+            print(" ".join(cmd))
+        subprocess.run(cmd, check=True)
+        return obj
+
+    with ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
+        objs = list(ex.map(compile_one, SOURCES))
+    cmd = [nvcc, *NVCC_FLAGS, "-shared", *objs, blob_obj, "-o", LIB]
     if verbose:
         print(" ".join(cmd))
     subprocess.run(cmd, check=True)

@@ -302,10 +302,7 @@ __global__ void __launch_bounds__(512) k_biloop_tile(typename Core<real>::Ctx c)
 template <typename real, bool LEFT>
 void launch_biloop(const typename Core<real>::Ctx &k, unsigned grid, int TXb, size_t smem, cudaStream_t st) {
   const bool d5 = k.delta >= 5;
-  if (TXb == 512) {
-    if (d5) k_biloop_tile<real, LEFT, 5, 512><<<grid, TXb, smem, st>>>(k);
-    else k_biloop_tile<real, LEFT, 2, 512><<<grid, TXb, smem, st>>>(k);
-  } else if (TXb == 256) {
+  if (TXb == 256) {  // the default width: row stride known at compile time
     if (d5) k_biloop_tile<real, LEFT, 5, 256><<<grid, TXb, smem, st>>>(k);
     else k_biloop_tile<real, LEFT, 2, 256><<<grid, TXb, smem, st>>>(k);
   } else {
@@ -794,7 +791,6 @@ int setup_engine(prib_ctx *c, const ScaleSpec &spec, size_t smem_max, std::strin
   }
 #define PRIB_BI_ATTR(L, U, X) \
   CU(cudaFuncSetAttribute((k_biloop_tile<real, L, U, X>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max))
-  PRIB_BI_ATTR(true, 5, 512); PRIB_BI_ATTR(true, 2, 512); PRIB_BI_ATTR(false, 5, 512); PRIB_BI_ATTR(false, 2, 512);
   PRIB_BI_ATTR(true, 5, 256); PRIB_BI_ATTR(true, 2, 256); PRIB_BI_ATTR(false, 5, 256); PRIB_BI_ATTR(false, 2, 256);
   PRIB_BI_ATTR(true, 5, 0); PRIB_BI_ATTR(true, 2, 0); PRIB_BI_ATTR(false, 5, 0); PRIB_BI_ATTR(false, 2, 0);
 #undef PRIB_BI_ATTR
@@ -820,6 +816,7 @@ int settle_kernel_time(prib_ctx *c) {
 extern "C" {
 
 const char *prib_last_error(void) { return g_err.c_str(); }
+void prib_internal_set_error(const char *msg) { g_err = msg ? msg : ""; }  // for the other translation units
 const char *prib_version(void) { return "priblast-b200 0.2 (sm_100a; fp32 span-scaled tiles + fp64 re-run)"; }
 
 int prib_acc_create(prib_ctx **out, const prib_acc_params *params) {

@@ -251,7 +251,8 @@ bool write_acc(const std::string &db, const std::vector<std::string> &seqs, cons
   return ok;
 }
 
-bool write_seq_ind(const std::string &db, const std::vector<std::string> &seqs, const DbParams &p, std::string &err) {
+bool write_seq_ind(const std::string &db, const std::vector<std::string> &seqs, const DbParams &p, std::string &err,
+                   SaBuilder sa_builder) {
   std::FILE *fs = std::fopen((db + ".seq").c_str(), "wb");
   std::FILE *fi = std::fopen((db + ".ind").c_str(), "wb");
   if (!fs || !fi) {
@@ -274,7 +275,14 @@ bool write_seq_ind(const std::string &db, const std::vector<std::string> &seqs, 
       break;
     }
     std::vector<int32_t> sa;
-    build_suffix_array(text.data(), (int)text.size(), sa);
+    if (sa_builder) {
+      if (!sa_builder(text.data(), (int)text.size(), sa, err)) {
+        ok = false;
+        break;
+      }
+    } else {
+      build_suffix_array(text.data(), (int)text.size(), sa);
+    }
     std::vector<std::vector<int32_t>> sh, eh;
     build_kmer_hash(text, sa, p.hash_size, sh, eh);
     const int32_t nseq = (int32_t)count, nbytes = (int32_t)text.size();

@@ -20,8 +20,13 @@ bool encode_reversed(const std::vector<std::string> &seqs, size_t first, size_t 
                      std::vector<uint8_t> &out);
 
 // Suffix array of a byte text (the reference calls sais(), sais.cpp:656; the suffix array of a text is
-// unique, so any correct construction yields the same bytes).  Prefix doubling with radix passes.
+// unique, so any correct construction yields the same bytes).  Host prefix doubling with radix passes:
+// TEST INFRASTRUCTURE (checker of prib_suffix_array, and the PRIB_DB_FORMATS_ONLY test switch); the
+// `db` front-end builds the array on the GPU.
 void build_suffix_array(const uint8_t *text, int n, std::vector<int32_t> &sa);
+
+// Suffix-array builder used by write_seq_ind: returns false and sets err on failure.
+typedef bool (*SaBuilder)(const uint8_t *text, int n, std::vector<int32_t> &sa, std::string &err);
 
 // ConstructHashForShortSubstring + Search (db_construction.cpp:337-369, 438-500): for every k-mer over
 // {2,3,4,5} of length 1..hash_size the suffix-array interval [start, end], with the reference's
@@ -39,7 +44,8 @@ bool write_bas(const std::string &db, const DbParams &p, std::string &err);
 bool write_nam(const std::string &db, const std::vector<std::string> &names, std::string &err);
 bool write_acc(const std::string &db, const std::vector<std::string> &seqs, const float *image,
                const std::vector<int64_t> &acc_off, const std::vector<int64_t> &cond_off, int delta, std::string &err);
-bool write_seq_ind(const std::string &db, const std::vector<std::string> &seqs, const DbParams &p, std::string &err);
+bool write_seq_ind(const std::string &db, const std::vector<std::string> &seqs, const DbParams &p, std::string &err,
+                   SaBuilder sa_builder = nullptr /* nullptr: the host checker */);
 
 // Length-balanced partition of sequences over `parts` devices: longest-processing-time greedy on the
 // cost model c(L) = L (the DP is linear in L for fixed span), the same idea as the reference's heap

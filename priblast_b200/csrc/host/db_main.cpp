@@ -8,6 +8,7 @@
 
 #include <cstdio>
 #include <cstdlib>
+#include <algorithm>
 #include <cstring>
 #include <string>
 #include <thread>
@@ -21,6 +22,17 @@ using namespace prib;
 static int die(const std::string &msg) {
   std::fprintf(stderr, "%s\n", msg.c_str());
   return 1;
+}
+
+// <db>.ind: the suffix array of every page is built on GPU 0 (prib_suffix_array replaces sais(),
+// db_construction.cpp:330-335)
+static bool gpu_suffix_array(const uint8_t *text, int n, std::vector<int32_t> &sa, std::string &err) {
+  sa.resize((size_t)std::max(n, 0));
+  if (prib_suffix_array(text, n, sa.data(), 0) != PRIB_OK) {
+    err = std::string("Error: suffix array: ") + prib_last_error();
+    return false;
+  }
+  return true;
 }
 
 static void usage() {
@@ -128,7 +140,7 @@ int main(int argc, char *argv[]) {
   }
 
   // ---- database files --------------------------------------------------------------------------
-  if (!write_seq_ind(db, seqs, prm, err)) return die(err);
+  if (!write_seq_ind(db, seqs, prm, err, formats_only ? nullptr : gpu_suffix_array)) return die(err);
   if (!formats_only && !write_acc(db, seqs, image, acc_off, cond_off, delta, err)) return die(err);
   if (!write_nam(db, names, err)) return die(err);
   if (!write_bas(db, prm, err)) return die(err);

@@ -16,7 +16,8 @@ int prib_lpt_partition(int n, const int *lens, int parts, int *part_of) {
   return 0;
 }
 
-int prib_suffix_array(const unsigned char *text, int n, int *sa) {
+// the HOST checker of the GPU builder (the C-ABI prib_suffix_array lives in libpriblast_acc.so)
+int prib_suffix_array_host(const unsigned char *text, int n, int *sa) {
   std::vector<int32_t> v;
   prib::build_suffix_array(text, n, v);
   std::memcpy(sa, v.data(), sizeof(int32_t) * v.size());

@@ -159,3 +159,16 @@ class Raccess:
         d = {k: getattr(c, k) for k, _ in c._fields_}
         d["phase_ms"] = dict(zip(_capi.PHASE_NAMES, list(c.phase_ms)))
         return d
+
+
+def suffix_array(text, device: int = 0) -> np.ndarray:
+    """Suffix array (int32) of an encoded database page on the GPU: the drop-in for the reference's
+    `sais(T, SA, n)` (sais.cpp:656, called at db_construction.cpp:334).  `text`: bytes / uint8 array of
+    symbols 0..9 (encoder.hpp:36-78)."""
+    t = np.ascontiguousarray(np.frombuffer(text, dtype=np.uint8) if isinstance(text, (bytes, bytearray)) else text,
+                             dtype=np.uint8)
+    sa = np.empty(len(t), dtype=np.int32)
+    lib = _capi.load()
+    _capi.check(lib.prib_suffix_array(t.ctypes.data_as(ctypes.c_void_p), len(t), sa.ctypes.data_as(_capi.c_i32p),
+                                      int(device)))
+    return sa

@@ -91,7 +91,7 @@ def test_suffix_array_and_partitioner():
         text[rng.integers(0, n, max(1, n // 50))] = 0   # sentinels
         text[-1] = 0
         sa = np.zeros(n, np.int32)
-        lib.prib_suffix_array(text.ctypes.data_as(ctypes.c_void_p), n, sa.ctypes.data_as(ctypes.c_void_p))
+        lib.prib_suffix_array_host(text.ctypes.data_as(ctypes.c_void_p), n, sa.ctypes.data_as(ctypes.c_void_p))
         raw = text.tobytes()
         want = sorted(range(n), key=lambda i: raw[i:])
         assert sa.tolist() == want
@@ -99,7 +99,7 @@ def test_suffix_array_and_partitioner():
     text = np.full(2000, 2, np.uint8)
     text[-1] = 0
     sa = np.zeros(2000, np.int32)
-    lib.prib_suffix_array(text.ctypes.data_as(ctypes.c_void_p), 2000, sa.ctypes.data_as(ctypes.c_void_p))
+    lib.prib_suffix_array_host(text.ctypes.data_as(ctypes.c_void_p), 2000, sa.ctypes.data_as(ctypes.c_void_p))
     assert sa.tolist() == list(range(1999, -1, -1))
     # LPT: every sequence assigned once, loads balanced within the longest item
     lens = np.clip(rng.lognormal(np.log(1500), 0.75, 4000), 200, 5000).astype(np.int32)
