@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <algorithm>
+#include <chrono>
 #include <cstring>
 #include <string>
 #include <thread>
@@ -34,6 +35,17 @@ static bool gpu_suffix_array(const uint8_t *text, int n, std::vector<int32_t> &s
   }
   return true;
 }
+
+// PRIB_DB_TIMING=1: wall time of every stage on stderr
+struct StageTimer {
+  bool on = std::getenv("PRIB_DB_TIMING") != nullptr;
+  std::chrono::steady_clock::time_point t = std::chrono::steady_clock::now();
+  void lap(const char *what) {
+    const auto now = std::chrono::steady_clock::now();
+    if (on) std::fprintf(stderr, "[db] %-28s %9.3f s\n", what, std::chrono::duration<double>(now - t).count());
+    t = now;
+  }
+};
 
 static void usage() {
   std::printf(
@@ -76,7 +88,9 @@ int main(int argc, char *argv[]) {
 
   std::vector<std::string> names, seqs;
   std::string err;
+  StageTimer timer;
   if (!read_fasta(input, names, seqs, err)) return die(err);
+  timer.lap("read FASTA");
   if (db.empty()) return die("Error: -o option is required");                                   // raccess.hpp:42-45
   if (prm.min_accessible_length <= 1) return die("Error: -d option must be greater than 1");   // raccess.hpp:47-50
   if (prm.repeat_flag < 0 || prm.repeat_flag > 2) return die("Error: -r option must be 0, 1, or 2");
@@ -102,6 +116,7 @@ int main(int argc, char *argv[]) {
     if (ngpu <= 0) return die("Error: no CUDA device available (there is no CPU path)");
     image = (float *)prib_host_alloc(sizeof(float) * (size_t)std::max<int64_t>(total, 1));
     if (!image) return die(std::string("Error: ") + prib_last_error());
+    timer.lap("pinned output image");
     std::vector<std::vector<int>> part;
     lpt_partition(seqs, ngpu, part);
     std::vector<std::string> errors(ngpu);
@@ -116,10 +131,12 @@ int main(int argc, char *argv[]) {
         ap.min_accessible_length = delta;
         ap.device = d;
         prib_ctx *ctx = nullptr;
+        StageTimer wt;
         if (prib_acc_create(&ctx, &ap) != PRIB_OK) {
           errors[d] = prib_last_error();
           return;
         }
+        wt.lap("  context (CUDA init, tables)");
         std::vector<const char *> sp(ids.size());
         std::vector<int32_t> sl(ids.size());
         std::vector<int64_t> ao(ids.size()), co(ids.size());
@@ -131,7 +148,9 @@ int main(int argc, char *argv[]) {
         }
         if (prib_acc_run(ctx, (int32_t)ids.size(), sp.data(), sl.data(), image, ao.data(), co.data()) != PRIB_OK)
           errors[d] = prib_last_error();
+        wt.lap("  prib_acc_run");
         prib_acc_destroy(ctx);
+        wt.lap("  context teardown");
       });
     }
     for (auto &w : workers) w.join();
@@ -139,11 +158,15 @@ int main(int argc, char *argv[]) {
       if (!errors[d].empty()) return die("Error: GPU " + std::to_string(d) + ": " + errors[d]);
   }
 
+  timer.lap("accessibility (GPU)");
   // ---- database files --------------------------------------------------------------------------
   if (!write_seq_ind(db, seqs, prm, err, formats_only ? nullptr : gpu_suffix_array)) return die(err);
+  timer.lap(".seq/.ind (SA on GPU, hash)");
   if (!formats_only && !write_acc(db, seqs, image, acc_off, cond_off, delta, err)) return die(err);
+  timer.lap(".acc");
   if (!write_nam(db, names, err)) return die(err);
   if (!write_bas(db, prm, err)) return die(err);
+  timer.lap(".nam/.bas");
   if (image) prib_host_free(image);
   return 0;
 }
