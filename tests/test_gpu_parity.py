@@ -186,3 +186,18 @@ def test_record_bytes_match_reference_file():
     n1 = np.frombuffer(rec[:4], np.int32)[0]
     assert n1 == 96 and len(rec) == 8 + 4 * (200 - 5 + 1)
     assert_close_kcal(np.frombuffer(rec[4:4 + 4 * n1], np.float32), case["acc"][:n1], ATOL_VS_REF, RTOL_VS_REF)
+
+
+@pytest.mark.parametrize("W,delta", [(1, 2), (3, 2), (4, 3), (5, 5), (6, 2), (7, 5), (10, 5), (12, 4), (33, 3), (34, 30),
+                                      (99, 7), (200, 5)])
+def test_span_and_window_sweep_vs_oracle(oracle_lib, W, delta):
+    """Spans around every structural threshold of the kernels (no band cells, first stem at 5, time-tile group
+    boundaries, MAXLOOP = 30 +- a few, the widest span) and window lengths up to 30, against the oracle."""
+    rng = np.random.default_rng(3)
+    seqs = ["".join("ACGU"[k] for k in rng.integers(0, 4, L)) for L in (40, 200, 333, 75)]
+    with __import__("priblast_b200").Raccess(W, delta, max_batch_bytes=4 << 30) as r:
+        got = r.run_batch(seqs)
+    want, _ = oracle_lib.run_batch(seqs, W, delta)
+    for s, (a, c), (oa, oc) in zip(seqs, got, want):
+        assert_close_kcal(a, oa, ATOL_VS_REF, RTOL_VS_REF, f"W={W} d={delta} L={len(s)} acc")
+        assert_close_kcal(c, oc, ATOL_VS_REF, RTOL_VS_REF, f"W={W} d={delta} L={len(s)} cond")
