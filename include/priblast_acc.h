@@ -36,8 +36,11 @@ typedef struct prib_acc_params {
   int32_t maximal_span;          /* W: reference `-w`, default 70 (db_construction_parameters.hpp:48) */
   int32_t min_accessible_length; /* delta: reference `-d`, default 5; must be > 1 (raccess.hpp:47)   */
   int32_t device;                /* CUDA device ordinal                                               */
-  int32_t mode;                  /* 0 = auto: FP32 span-scaled engine (W <= 100) with on-GPU FP64 re-run
-                                    of range-flagged sequences; 1 = FP64 engine only                  */
+  int32_t mode;                  /* 0 = auto: FP32 span-scaled engine with on-GPU FP64 re-run of
+                                    range-flagged sequences; 1 = FP64 engine only; 2 = exact: the
+                                    reference's own log-domain arithmetic (float-table logsumexp,
+                                    raccess.cpp:414-419, in its summation order) on the GPU: results are
+                                    bit-identical to the reference built without FMA contraction     */
   int64_t max_batch_bytes;       /* device-memory budget for DP state; 0 = 60 % of free memory        */
 } prib_acc_params;
 

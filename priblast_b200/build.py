@@ -20,8 +20,10 @@ NVCC_FLAGS = [
     "-ccbin", HOST_CXX,
 ]
 
-SOURCES = ["acc_kernels.cu", "sa_gpu.cu", "acc_tables.cpp"]
-DEPS = SOURCES + ["acc_core.h", "acc_tile.h", "acc_tables.h", "turner_params.h", "turner_blob.c",
+SOURCES = ["acc_kernels.cu", "acc_exact.cu", "sa_gpu.cu", "acc_tables.cpp"]
+# the exact engine reproduces the reference's IEEE arithmetic bit for bit: no FMA contraction in that TU
+PER_SOURCE_FLAGS = {"acc_exact.cu": ["-fmad=false"]}
+DEPS = SOURCES + ["acc_core.h", "acc_tile.h", "acc_tables.h", "acc_exact.h", "turner_params.h", "turner_blob.c",
                   os.path.join("..", "..", "include", "priblast_acc.h")]
 
 
@@ -50,7 +52,7 @@ def build_library(force: bool = False, verbose: bool = False, extra: list[str] |
 
     def compile_one(src: str) -> str:  # one object per source, compiled side by side (CUB makes sa_gpu.cu slow)
         obj = os.path.join(CSRC, os.path.splitext(src)[0] + ".o")
-        cmd = [nvcc, *NVCC_FLAGS, *(extra or []), "-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [nvcc, *NVCC_FLAGS, *PER_SOURCE_FLAGS.get(src, []), *(extra or []), "-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             print(" ".join(cmd))
         subprocess.run(cmd, check=True)

@@ -23,6 +23,7 @@
 
 #include "../../include/priblast_acc.h"
 #include "acc_core.h"
+#include "acc_exact.h"
 #include "acc_tables.h"
 #include "acc_tile.h"
 
@@ -462,6 +463,8 @@ struct prib_ctx {
   bool phases_pending = false, kernel_timed = true;
   Engine<float> e32;
   Engine<double> e64;
+  ExactEngine *ex = nullptr;  // mode 2: the reference's own arithmetic (acc_exact.h)
+  long long ex_max_cols = 0;
   float *d_log = nullptr;
   int grid_tiles = 0;
   char *d_tile_scratch = nullptr;
@@ -731,6 +734,31 @@ int run_batch(prib_ctx *c, const Batch &b, bool timed) {
   return PRIB_OK;
 }
 
+// mode 2: every kernel of acc_exact.cu for one batch (phase events in the same slots as the fast engines)
+int run_batch_exact(prib_ctx *c, const Batch &b) {
+  if (settle_phases(c) != PRIB_OK) return PRIB_ECUDA;
+  const long long used = exact_state_bytes_per_column(c->W) * b.NC;
+  if (used > c->state_cap_bytes) return fail(PRIB_ECUDA, "internal: batch exceeds the DP state allocation");
+  if (used > c->cnt.dp_state_bytes_used) c->cnt.dp_state_bytes_used = used;
+  ExactBatch eb;
+  eb.NC = b.NC;
+  eb.n = b.n;
+  eb.S = b.d_S;
+  eb.col_seq = b.d_col_seq;
+  eb.seq_len = b.d_seq_len;
+  eb.seq_off = b.d_seq_off;
+  eb.acc_off = b.d_acc_off;
+  eb.cond_off = b.d_cond_off;
+  eb.out = c->d_out;
+  int launches = 0;
+  const int e = exact_run(c->ex, eb, c->d_state, c->stream, c->evp, &launches);
+  if (e != 0) return fail(PRIB_ECUDA, std::string("exact engine: ") + cudaGetErrorString((cudaError_t)e));
+  c->phases_pending = true;
+  c->cnt.kernel_launches += launches;
+  c->cnt.batches += 1;
+  return PRIB_OK;
+}
+
 template <typename real>
 int setup_engine(prib_ctx *c, const ScaleSpec &spec, size_t smem_max, std::string &err) {
   Engine<real> &e = engine<real>(c);
@@ -828,7 +856,8 @@ int prib_acc_create(prib_ctx **out, const prib_acc_params *params) {
     return fail(PRIB_EINVAL, "maximal span must be in 1.." + std::to_string((int)kMaxSpan));
   if (params->min_accessible_length > kMaxLoop)
     return fail(PRIB_EINVAL, "minimum accessible length above 30 is not supported");
-  if (params->mode != 0 && params->mode != 1) return fail(PRIB_EINVAL, "mode must be 0 (auto) or 1 (fp64 only)");
+  if (params->mode < 0 || params->mode > 2)
+    return fail(PRIB_EINVAL, "mode must be 0 (auto), 1 (fp64 only) or 2 (exact: reference arithmetic)");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
     return fail(PRIB_ECUDA, "no CUDA device available (this library has no CPU fallback)");
@@ -873,6 +902,10 @@ int prib_acc_create(prib_ctx **out, const prib_acc_params *params) {
     rc = setup_engine<float>(c, default_scale_fp32(), prop.sharedMemPerBlockOptin, err);
     if (rc != PRIB_OK) return bail(rc == PRIB_EINVAL ? fail(rc, err) : rc);
   }
+  if (params->mode == 2) {
+    c->ex = exact_create(c->W, c->delta, err);
+    if (!c->ex) return bail(fail(PRIB_ECUDA, err));
+  }
   const size_t scr64 = (size_t)2 * (c->W + 4) * c->e64.TC * sizeof(double);
   const size_t scr32 = (size_t)2 * (c->W + 4) * c->e32.TC * sizeof(float);
   CUB(cudaMalloc(&c->d_tile_scratch, (size_t)c->grid_tiles * std::max(scr64, scr32)));
@@ -883,6 +916,7 @@ int prib_acc_create(prib_ctx **out, const prib_acc_params *params) {
   if (budget > (long long)(free_b * 0.9)) budget = (long long)(free_b * 0.9);
   c->e64.max_cols = budget / state_bytes_per_column(c->W, 8) / 32 * 32;
   c->e32.max_cols = budget / state_bytes_per_column(c->W, 4) / 32 * 32;
+  c->ex_max_cols = budget / exact_state_bytes_per_column(c->W) / 32 * 32;
   if (c->e64.max_cols < 4096) return bail(fail(PRIB_ECUDA, "device memory budget too small for the DP state"));
   c->state_cap_bytes = budget;
   CUB(cudaMalloc(&c->d_state, (size_t)c->state_cap_bytes));
@@ -900,6 +934,7 @@ void prib_acc_destroy(prib_ctx *c) {
   cudaFree(c->d_tile_scratch);
   c->e32.release();
   c->e64.release();
+  exact_destroy(c->ex);
   cudaFree(c->d_log);
   if (c->h_stage) cudaFreeHost(c->h_stage);
   if (c->h_in) cudaFreeHost(c->h_in);
@@ -925,10 +960,10 @@ int prib_acc_stage(prib_ctx *c, int32_t n, const char *const *seq, const int32_t
   CU(cudaSetDevice(c->prm.device));
   c->staged = c->computed = false;
   c->n_batches = 0;
-  const long long max_cols = c->use_fp32 ? c->e32.max_cols : c->e64.max_cols;
+  const long long max_cols = c->ex ? c->ex_max_cols : c->use_fp32 ? c->e32.max_cols : c->e64.max_cols;
   for (int k = 0; k < n; k++) {
     if (len[k] < 0) return fail(PRIB_EINVAL, "negative sequence length");
-    if (layout_columns(len[k]) + 2 * kPad > c->e64.max_cols)
+    if (layout_columns(len[k]) + 2 * kPad > std::min(max_cols, c->e64.max_cols))
       return fail(PRIB_ECUDA, "sequence " + std::to_string(k) + " does not fit the device DP budget");
   }
   c->seqs.resize(n);
@@ -972,7 +1007,7 @@ int prib_acc_compute(prib_ctx *c) {
   for (size_t bi = 0; bi < c->n_batches; ++bi) {
     const Batch &b = c->batches[bi];
     if (b.n == 0) continue;
-    int rc = c->use_fp32 ? run_batch<float>(c, b, true) : run_batch<double>(c, b, true);
+    int rc = c->ex ? run_batch_exact(c, b) : c->use_fp32 ? run_batch<float>(c, b, true) : run_batch<double>(c, b, true);
     if (rc != PRIB_OK) return rc;
     c->cnt.sequences += b.n;
     c->cnt.nucleotides += b.nt;

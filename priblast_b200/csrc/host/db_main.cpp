@@ -52,8 +52,11 @@ static void usage() {
       "pRIblast-b200 db: database construction with GPU accessibility\n"
       "usage: pRIblast_b200 db -i InputFastaFile -o OutputDbName [-r RepeatMaskingStyle] [-s LookupTableSize]\n"
       "                        [-w MaximalSpan] [-d MinAccessibleLength] [-c ChunkSize] [-a block|heap|dynamic]\n"
-      "                        [-p TmpPath]\n"
+      "                        [-p TmpPath] [-m auto|fp64|exact]\n"
       "defaults: -r 0 -s 8 -w 70 -d 5 -a heap -c INT_MAX   (reference: main.cpp:43-73)\n"
+      "-m (extension; also PRIB_ACC_MODE): auto = FP32 span-scaled engine with FP64 re-run (default; .acc within\n"
+      "   1e-4 kcal/mol of the reference), fp64, exact = the reference's own arithmetic on the GPU (.acc, hence\n"
+      "   the whole database and the ris output, byte-identical to the reference; ~50x slower than auto)\n"
       "environment: PRIB_NUM_GPUS=n limits the GPUs used (default: all visible)\n");
 }
 
@@ -67,10 +70,11 @@ int main(int argc, char *argv[]) {
     return 0;
   }
   std::string input, db, tmp_path, alg = "heap";
+  std::string mode = std::getenv("PRIB_ACC_MODE") ? std::getenv("PRIB_ACC_MODE") : "auto";
   DbParams prm;
   int c;
   optind = 1;
-  while ((c = getopt(argc - 1, argv + 1, "i:o:r:s:w:d:t:p:a:c:")) != -1) {
+  while ((c = getopt(argc - 1, argv + 1, "i:o:r:s:w:d:t:p:a:c:m:")) != -1) {
     switch (c) {
       case 'i': input = optarg; break;
       case 'o': db = optarg; break;
@@ -81,10 +85,13 @@ int main(int argc, char *argv[]) {
       case 'p': tmp_path = optarg; break;  // accepted; there are no temp files any more
       case 'a': alg = optarg; break;
       case 'c': prm.chunk_size = std::atoi(optarg); break;
+      case 'm': mode = optarg; break;
       default: return die("Error: invalid argument");  // incl. -t, as in the reference
     }
   }
   if (alg != "block" && alg != "heap" && alg != "dynamic") return die("Error: parallel algorithm not supported");
+  if (mode != "auto" && mode != "fp64" && mode != "exact") return die("Error: -m must be auto, fp64 or exact");
+  const int acc_mode = mode == "exact" ? 2 : mode == "fp64" ? 1 : 0;
 
   std::vector<std::string> names, seqs;
   std::string err;
@@ -130,6 +137,7 @@ int main(int argc, char *argv[]) {
         ap.maximal_span = prm.maximal_span;
         ap.min_accessible_length = delta;
         ap.device = d;
+        ap.mode = acc_mode;
         prib_ctx *ctx = nullptr;
         StageTimer wt;
         if (prib_acc_create(&ctx, &ap) != PRIB_OK) {

@@ -90,3 +90,41 @@ def test_gpu_db_then_reference_ris(tmp_path):
     for a, b in zip(hr, hg):
         assert abs(a[3] - b[3]) <= 2e-4 and abs(a[4] - b[4]) <= 1e-9 and abs(a[5] - b[5]) <= 2e-4
     print(f"{len(hr)} hits identical in structure; energies within 2e-4 kcal/mol")
+
+
+def test_exact_mode_database_and_ris_output_byte_identical(tmp_path):
+    """`db -m exact` (csrc/acc_exact.cu: the reference's own arithmetic on the GPU): ALL five database files
+    byte-identical to the reference program's, and the unmodified reference `ris` prints the same lines."""
+    if not os.path.exists(REFBIN):
+        pytest.skip("oracle/_ref/pRIblast_ref not built")
+    subprocess.run(["make", "-C", os.path.join(ROOT, "priblast_b200", "csrc", "host")], check=True,
+                   stdout=subprocess.DEVNULL)
+    rng = np.random.default_rng(78)
+    lens = list(rng.integers(120, 900, 30)) + [5, 6, 3100]  # shortest legal records and one Z > 690 (log-sum path)
+    db_seqs = ["".join("ACGU"[k] for k in rng.integers(0, 4, int(L))) for L in lens]
+    db_seqs[3] = db_seqs[3][:100] + "NNNNnnacgu" + db_seqs[3][110:]
+    comp = {"A": "U", "C": "G", "G": "C", "U": "A"}
+    queries = []
+    for k in range(5):
+        src = db_seqs[4 * k + 1]
+        st = int(rng.integers(10, len(src) - 50))
+        site = "".join(comp.get(b, "A") for b in reversed(src[st:st + 26]))
+        pad = "".join("ACGU"[i] for i in rng.integers(0, 4, 140))
+        queries.append(pad[:70] + site + pad[70:])
+    fa, qa = str(tmp_path / "db.fa"), str(tmp_path / "q.fa")
+    _write(fa, db_seqs, "t")
+    _write(qa, queries, "q")
+    env = dict(os.environ, OMP_NUM_THREADS="8")
+    subprocess.run([REFBIN, "db", "-i", fa, "-o", str(tmp_path / "ref"), "-c", "12"], check=True, env=env, cwd=tmp_path)
+    subprocess.run([FRONT, "db", "-i", fa, "-o", str(tmp_path / "gpu"), "-c", "12", "-m", "exact"], check=True, env=env)
+    for ext in (".acc", ".seq", ".ind", ".nam", ".bas"):
+        assert open(str(tmp_path / "ref") + ext, "rb").read() == open(str(tmp_path / "gpu") + ext, "rb").read(), ext
+    for name in ("ref", "gpu"):
+        subprocess.run([REFBIN, "ris", "-i", qa, "-o", str(tmp_path / f"hits_{name}.txt"), "-d", str(tmp_path / name)],
+                       check=True, env=env, cwd=tmp_path)
+    def lines(fn):  # the reference numbers hits in the order its OpenMP threads finish: drop the Id column, sort
+        return sorted(ln.split(",", 1)[1] if ln[:1].isdigit() else ln for ln in open(fn).read().splitlines())
+
+    lr, lg = lines(str(tmp_path / "hits_ref.txt")), lines(str(tmp_path / "hits_gpu.txt"))
+    assert len(lr) > 2, "test set produced no hits"
+    assert lr == lg, "ris output differs"  # every printed digit of every energy equal
