@@ -503,76 +503,185 @@ __global__ void __launch_bounds__(128) k_ex_hairpin(ExCtx c) {
 
 // ---- bulge / interior-loop probabilities: raccess.cpp:614-681 (direct) and :683-771 (log-sum) ----------------
 // The reference walks the loops (i, j, p, q) once and adds each term to every window start k inside the two
-// unpaired strands.  Floating-point addition is not associative, so to get its bits each position k walks the
-// SAME loops in the SAME order, restricted to the ones whose strands contain k:
+// unpaired strands.  Floating-point addition is not associative, so to get its bits each position k must fold
+// the terms of the loops whose strands contain it in the reference's order (i, j, p, q ascending):
 //   left strand : i + 1 <= k <= p - w   (k == p - w feeds bp, otherwise cbp)      :644-650 / :713-729
 //   right strand: q + 1 <= k <= j - w   (k == j - w feeds bp, otherwise cbp)      :652-658 / :731-745
 // (the two cases exclude each other: left needs p > k, right q < k, and q > p).
-__global__ void __launch_bounds__(128) k_ex_biloop(ExCtx c) {
-  const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  Seq sq;
-  int k;
-  if (!seq_of_column(c, g, sq, k)) return;
-  const int L = sq.L, W = c.W, w = c.delta;
-  if (k < 1 || k > L) return;
+// One CTA owns kBiB consecutive columns.  It walks the outer pairs (i, j) that can reach any of its positions;
+// for each pair the threads evaluate the <= 496 inner pairs ONCE, in parallel (flat index n -> (u1, u2) in the
+// order of the reference's p, q loops), compact the existing terms in order into shared memory, and then each
+// position folds its own sub-sequence of them: first the right-strand prefixes of the rows p < k + w, then the
+// row p == k + w (bp) and all later rows (cbp) — contiguous ranges of the compacted list.
+constexpr int kBiB = 256;
+constexpr int kTri = 496;  // (u1, u2) with u1 + u2 <= 30
+
+__device__ __forceinline__ int tri_row_start(int u1) { return 31 * u1 - (u1 * (u1 - 1)) / 2; }
+
+__global__ void __launch_bounds__(kBiB) k_ex_biloop(ExCtx c) {
+  __shared__ double s_T[kTri];
+  __shared__ unsigned char s_u1[kTri + 16], s_u2[kTri + 16], s_cu2[kTri + 16];
+  __shared__ unsigned int s_mask[16];
+  __shared__ short s_cstart[34];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long long g0 = (long long)blockIdx.x * kBiB;
   const ExTab &T = *c.T;
-  const uint8_t *s = sq.s;
-  const double Z = c.vec[0 * c.NC + sq.off + L];
-  const bool direct = Z >= -690 && Z <= 690;  // raccess.cpp:436-443
-  double b = 0, cc = 0;
-  bool bf = false, cf = false;
-  int ilo = k + w - W;
-  if (ilo < 1) ilo = 1;
-  int ihi = k - 1;
-  if (ihi > L - kTurn - 3) ihi = L - kTurn - 3;  // i < L - TURN - 2
-  for (int i = ilo; i <= ihi; i++) {
-    const int jhi = i + W < L ? i + W : L;
-    int jlo = i + kTurn + 3;
-    if (jlo < k + w) jlo = k + w;
-    for (int j = jlo; j <= jhi; j++) {
-      const int t = T.bp[s[i]][s[j]];
-      if (t == 0) continue;
-      const double be = AT(c, sq, EB_STEMEND, i, j - i - 1);
-      if (be == EX_NEG) continue;
-      const int phi = i + kMaxLoop + 1 < j - kTurn - 2 ? i + kMaxLoop + 1 : j - kTurn - 2;
-      for (int p = i + 1; p <= phi; p++) {
-        const int u1 = p - i - 1;
-        const int q0 = p + kTurn + 1 > j - kMaxLoop + u1 - 1 ? p + kTurn + 1 : j - kMaxLoop + u1 - 1;
-        const bool left = p >= k + w;
-        const int qhi = left ? j - 1 : (j - 1 < k - 1 ? j - 1 : k - 1);
-        const bool to_b = left ? (k == p - w) : (k == j - w);
-        for (int q = q0; q <= qhi; q++) {
-          const int t2 = T.bp[s[p]][s[q]];
-          if (t2 == 0 || (p == i + 1 && q == j - 1)) continue;
-          const double as = AT(c, sq, EA_STEM, p - 1, q - p + 1);
-          if (as == EX_NEG) continue;
-          const double e = be + ex_loop(c, sq, t, T.rt[t2], i, j, p, q) + as;
-          if (direct) {
-            const double tv = ex_expd(T, e);
-            if (to_b) b += tv;
-            else cc += tv;
-          } else if (to_b) {
-            b = bf ? ex_lse(T, b, e) : e;
-            bf = true;
-          } else {
-            cc = cf ? ex_lse(T, cc, e) : e;
-            cf = true;
-          }
-        }
-      }
+  const int W = c.W, w = c.delta;
+  if (tid < 31) {  // row u1 = tid: u2 = 30 - u1 .. 0 (q ascending)
+    int n = tri_row_start(tid);
+    for (int u2 = 30 - tid; u2 >= 0; --u2, ++n) {
+      s_u1[n] = (unsigned char)tid;
+      s_u2[n] = (unsigned char)u2;
     }
   }
-  if (direct) {  // :667-680
-    if (b != 0) b = ex_expd(T, (double)ex_logf(T, (float)(b + cc)) - Z);
-    if (cc != 0) cc = ex_expd(T, (double)ex_logf(T, (float)cc) - Z);
-  } else {  // :754-770
-    if (bf && cf) b = ex_lse(T, b, cc);
-    if (!bf && cf) b = cc;
-    if (bf) b = ex_expd(T, b - Z);
-    if (cf) cc = ex_expd(T, cc - Z);
+  __syncthreads();
+  // first sequence that can overlap [g0, g0 + kBiB): the last one starting at or before g0
+  int lo = 0, hi = c.nseq;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (c.seq_off[mid] <= g0) lo = mid + 1;
+    else hi = mid;
   }
-  c.vec[4 * c.NC + g] = b;
-  c.vec[5 * c.NC + g] = cc;
+  for (int id = lo > 0 ? lo - 1 : 0; id < c.nseq && c.seq_off[id] < g0 + kBiB; ++id) {
+    Seq sq;
+    sq.off = c.seq_off[id];
+    sq.L = c.seq_len[id];
+    sq.s = c.S + sq.off;
+    const uint8_t *s = sq.s;
+    const int L = sq.L;
+    const long long rel0 = g0 - sq.off;  // position of thread 0 in this sequence (may be negative)
+    const int klo = rel0 > 1 ? (int)rel0 : 1;
+    const int khi = (long long)(L - w + 1) < rel0 + kBiB - 1 ? L - w + 1 : (int)(rel0 + kBiB - 1);
+    if (klo > khi) continue;  // uniform
+    const int k = (int)(rel0 + tid);
+    const bool mine = k >= klo && k <= khi;
+    const double Z = c.vec[0 * c.NC + sq.off + L];
+    const bool direct = Z >= -690 && Z <= 690;  // raccess.cpp:436-443
+    double b = 0, cc = 0;
+    bool bf = false, cf = false;
+    auto add = [&](bool to_b, double v) {
+      if (direct) {
+        if (to_b) b += v;
+        else cc += v;
+      } else if (to_b) {
+        b = bf ? ex_lse(T, b, v) : v;
+        bf = true;
+      } else {
+        cc = cf ? ex_lse(T, cc, v) : v;
+        cf = true;
+      }
+    };
+    int ilo = klo + w - W;
+    if (ilo < 1) ilo = 1;
+    int ihi = khi - 1;
+    if (ihi > L - kTurn - 3) ihi = L - kTurn - 3;  // i < L - TURN - 2
+    for (int i = ilo; i <= ihi; i++) {
+      const int jhi = i + W < L ? i + W : L;
+      int jlo = i + kTurn + 3;
+      if (jlo < klo + w) jlo = klo + w;
+      for (int j = jlo; j <= jhi; j++) {
+        // everything up to the barriers is uniform over the CTA
+        const int t = T.bp[s[i]][s[j]];
+        if (t == 0) continue;
+        {  // can a strand of this pair contain one of our positions?
+          int lhi = i + kMaxLoop + 1 - w < j - w ? i + kMaxLoop + 1 - w : j - w;
+          if (lhi > khi) lhi = khi;
+          const bool left_ok = (klo > i + 1 ? klo : i + 1) <= lhi;
+          int rlo = j - kMaxLoop > i + 1 ? j - kMaxLoop : i + 1;
+          if (rlo < klo) rlo = klo;
+          const bool right_ok = rlo <= (khi < j - w ? khi : j - w);
+          if (!left_ok && !right_ok) continue;
+        }
+        const double be = AT(c, sq, EB_STEMEND, i, j - i - 1);
+        if (be == EX_NEG) continue;
+        const int u1max = (j - i - 6 < kMaxLoop) ? j - i - 6 : kMaxLoop;  // p <= min(i + 31, j - 5)
+        const int nflat = tri_row_start(u1max + 1);
+        // 1. evaluate the inner pairs (two rounds of kBiB), note which exist
+        double tv[2];
+        int wi[2];
+        unsigned int mk[2];
+        bool ok[2];
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          const int n = r * kBiB + tid;
+          ok[r] = false;
+          tv[r] = 0;
+          if (n < nflat) {
+            const int u1 = s_u1[n], u2 = s_u2[n];
+            const int p = i + 1 + u1, q = j - 1 - u2;
+            if (q >= p + kTurn + 1 && (u1 | u2) != 0) {
+              const int t2 = T.bp[s[p]][s[q]];
+              if (t2 != 0) {
+                const double as = AT(c, sq, EA_STEM, p - 1, q - p + 1);
+                if (as != EX_NEG) {
+                  const double e = be + ex_loop(c, sq, t, T.rt[t2], i, j, p, q) + as;
+                  tv[r] = direct ? ex_expd(T, e) : e;
+                  ok[r] = true;
+                }
+              }
+            }
+          }
+          mk[r] = __ballot_sync(0xffffffffu, ok[r]);
+          wi[r] = r * (kBiB / 32) + warp;
+          if (lane == 0) s_mask[wi[r]] = mk[r];
+        }
+        __syncthreads();
+        // 2. compact in order; start of every row in the compacted list
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          if (ok[r]) {
+            int pos = __popc(mk[r] & ((1u << lane) - 1));
+            for (int x = 0; x < wi[r]; ++x) pos += __popc(s_mask[x]);
+            s_T[pos] = tv[r];
+            s_cu2[pos] = s_u2[r * kBiB + tid];
+          }
+        }
+        if (tid <= u1max + 1) {
+          const int bit = tri_row_start(tid);
+          int pos = 0;
+          for (int x = 0; x < (bit >> 5); ++x) pos += __popc(s_mask[x]);
+          if ((bit & 31) != 0) pos += __popc(s_mask[bit >> 5] & ((1u << (bit & 31)) - 1));
+          s_cstart[tid] = (short)pos;
+        }
+        __syncthreads();
+        // 3. every position folds its terms
+        if (mine && i <= k - 1 && j >= k + w) {
+          const int u1min = k + w - i - 1;  // the row with p - w == k
+          const int thr = j - k;            // right strand: q <= k - 1  <=>  u2 >= j - k
+          int rmax = u1min < u1max + 1 ? u1min : u1max + 1;
+          if (rmax > kMaxLoop + 1 - thr) rmax = kMaxLoop + 1 - thr;
+          const bool to_b_r = (k == j - w);
+          for (int u1 = 0; u1 < rmax; ++u1) {
+            const int xe = s_cstart[u1 + 1];
+            for (int x = s_cstart[u1]; x < xe; ++x) {
+              if ((int)s_cu2[x] < thr) break;
+              add(to_b_r, s_T[x]);
+            }
+          }
+          if (u1min <= u1max) {
+            const int x1 = s_cstart[u1min + 1], x2 = s_cstart[u1max + 1];
+            for (int x = s_cstart[u1min]; x < x1; ++x) add(true, s_T[x]);
+            for (int x = x1; x < x2; ++x) add(false, s_T[x]);
+          }
+        }
+        // no barrier here: the next pair only writes s_mask before its first barrier, and nobody reads
+        // s_mask in step 3; s_T / s_cu2 / s_cstart are rewritten after that barrier
+      }
+    }
+    if (mine) {
+      if (direct) {  // :667-680
+        if (b != 0) b = ex_expd(T, (double)ex_logf(T, (float)(b + cc)) - Z);
+        if (cc != 0) cc = ex_expd(T, (double)ex_logf(T, (float)cc) - Z);
+      } else {  // :754-770
+        if (bf && cf) b = ex_lse(T, b, cc);
+        if (!bf && cf) b = cc;
+        if (bf) b = ex_expd(T, b - Z);
+        if (cf) cc = ex_expd(T, cc - Z);
+      }
+      c.vec[4 * c.NC + g0 + tid] = b;
+      c.vec[5 * c.NC + g0 + tid] = cc;
+    }
+  }
 }
 
 // raccess.cpp:581-612
@@ -793,7 +902,7 @@ int exact_run(ExactEngine *e, const ExactBatch &b, char *d_state, cudaStream_t s
   EX_EV(3);
   for (int d = W + 1; d >= kTurn; d--, ++nl) k_ex_outside<<<grid, 128, 0, st>>>(c, d);
   EX_EV(4);
-  k_ex_biloop<<<grid, 128, 0, st>>>(c);
+  k_ex_biloop<<<(unsigned)((b.NC + kBiB - 1) / kBiB), kBiB, 0, st>>>(c);
   ++nl;
   EX_EV(5);
   EX_EV(6);
