@@ -469,7 +469,8 @@ struct prib_ctx {
   int grid_tiles = 0;
   char *d_tile_scratch = nullptr;
   char *d_state = nullptr;
-  long long state_cap_bytes = 0;
+  long long state_cap_bytes = 0;  // current size of d_state (grow-only)
+  long long state_budget = 0;     // upper bound fixed at create time (batches are sized for it)
   // staged work
   std::vector<Batch> batches;
   std::vector<std::string> seqs;  // host copies (needed to re-run flagged sequences in double)
@@ -564,6 +565,28 @@ int settle_phases(prib_ctx *c) {
     c->cnt.phase_ms[p] += ms;
   }
   c->phases_pending = false;
+  return PRIB_OK;
+}
+
+// The DP state is allocated on first use and only grows (up to the budget fixed at create time): a small job
+// does not pay for allocating and freeing 100 GB.
+int ensure_state(prib_ctx *c, long long bytes) {
+  if (bytes <= c->state_cap_bytes) return PRIB_OK;
+  if (bytes > c->state_budget) return fail(PRIB_ECUDA, "internal: batch exceeds the DP state budget");
+  CU(cudaStreamSynchronize(c->stream));  // nothing may still be using the old block
+  cudaFree(c->d_state);
+  c->d_state = nullptr;
+  c->state_cap_bytes = 0;
+  // batches are built longest-first and filled greedily, so the first one is (nearly) the largest: round up a
+  // little to avoid a second allocation for a slightly larger later batch
+  long long want = std::min(c->state_budget, bytes + bytes / 16);
+  if (cudaMalloc(&c->d_state, (size_t)want) != cudaSuccess) {
+    cudaGetLastError();
+    want = bytes;
+    CU(cudaMalloc(&c->d_state, (size_t)want));
+  }
+  c->state_cap_bytes = want;
+  c->cnt.dp_state_bytes = want;
   return PRIB_OK;
 }
 
@@ -697,9 +720,9 @@ template <typename real>
 int run_batch(prib_ctx *c, const Batch &b, bool timed) {
   Engine<real> &e = engine<real>(c);
   if (timed && settle_phases(c) != PRIB_OK) return PRIB_ECUDA;
-  const typename Core<real>::Ctx k = make_ctx<real>(c, b);
   const long long used = state_bytes_per_column(c->W, sizeof(real)) * b.NC;
-  if (used > c->state_cap_bytes) return fail(PRIB_ECUDA, "internal: batch exceeds the DP state allocation");
+  if (ensure_state(c, used) != PRIB_OK) return PRIB_ECUDA;
+  const typename Core<real>::Ctx k = make_ctx<real>(c, b);
   cudaStream_t st = c->stream;
   if (used > c->cnt.dp_state_bytes_used) c->cnt.dp_state_bytes_used = used;
   if (timed) CU(cudaEventRecord(c->evp[0], st));
@@ -738,7 +761,7 @@ int run_batch(prib_ctx *c, const Batch &b, bool timed) {
 int run_batch_exact(prib_ctx *c, const Batch &b) {
   if (settle_phases(c) != PRIB_OK) return PRIB_ECUDA;
   const long long used = exact_state_bytes_per_column(c->W) * b.NC;
-  if (used > c->state_cap_bytes) return fail(PRIB_ECUDA, "internal: batch exceeds the DP state allocation");
+  if (ensure_state(c, used) != PRIB_OK) return PRIB_ECUDA;
   if (used > c->cnt.dp_state_bytes_used) c->cnt.dp_state_bytes_used = used;
   ExactBatch eb;
   eb.NC = b.NC;
@@ -918,9 +941,7 @@ int prib_acc_create(prib_ctx **out, const prib_acc_params *params) {
   c->e32.max_cols = budget / state_bytes_per_column(c->W, 4) / 32 * 32;
   c->ex_max_cols = budget / exact_state_bytes_per_column(c->W) / 32 * 32;
   if (c->e64.max_cols < 4096) return bail(fail(PRIB_ECUDA, "device memory budget too small for the DP state"));
-  c->state_cap_bytes = budget;
-  CUB(cudaMalloc(&c->d_state, (size_t)c->state_cap_bytes));
-  c->cnt.dp_state_bytes = c->state_cap_bytes;
+  c->state_budget = budget;  // the block itself is allocated by the first batch (ensure_state)
 #undef CUB
   *out = c;
   return PRIB_OK;

@@ -11,6 +11,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cstring>
+#include <future>
 #include <string>
 #include <thread>
 #include <vector>
@@ -116,22 +117,41 @@ int main(int argc, char *argv[]) {
     cond_off[k] = total + (int64_t)seqs[k].size();
     total += 2 * (int64_t)seqs[k].size();
   }
+  // <db>.seq / <db>.ind need only the sequences: they are built (suffix arrays on GPU 0) while the GPUs work on
+  // the accessibility
+  std::string err_si;
+  StageTimer t_si;
+  std::future<bool> seq_ind = std::async(std::launch::async, [&]() {
+    const bool ok = write_seq_ind(db, seqs, prm, err_si, formats_only ? nullptr : gpu_suffix_array);
+    t_si.lap(".seq/.ind (SA on GPU, hash) [overlapped]");
+    return ok;
+  });
   float *image = nullptr;
+  std::vector<std::thread> workers;
   if (!formats_only) {
     int ngpu = prib_device_count();
     if (const char *e = std::getenv("PRIB_NUM_GPUS")) ngpu = std::min(ngpu, std::max(1, std::atoi(e)));
-    if (ngpu <= 0) return die("Error: no CUDA device available (there is no CPU path)");
+    if (ngpu <= 0) {
+      seq_ind.wait();
+      return die("Error: no CUDA device available (there is no CPU path)");
+    }
     image = (float *)prib_host_alloc(sizeof(float) * (size_t)std::max<int64_t>(total, 1));
-    if (!image) return die(std::string("Error: ") + prib_last_error());
+    if (!image) {
+      seq_ind.wait();
+      return die(std::string("Error: ") + prib_last_error());
+    }
     timer.lap("pinned output image");
     std::vector<std::vector<int>> part;
     lpt_partition(seqs, ngpu, part);
     std::vector<std::string> errors(ngpu);
-    std::vector<std::thread> workers;
+    std::vector<std::promise<void>> done(ngpu);  // results of GPU d are in the image (its context may still be tearing down)
     for (int d = 0; d < ngpu; d++) {
       workers.emplace_back([&, d]() {
         const std::vector<int> &ids = part[d];
-        if (ids.empty()) return;
+        if (ids.empty()) {
+          done[d].set_value();
+          return;
+        }
         prib_acc_params ap;
         std::memset(&ap, 0, sizeof(ap));
         ap.maximal_span = prm.maximal_span;
@@ -142,6 +162,7 @@ int main(int argc, char *argv[]) {
         StageTimer wt;
         if (prib_acc_create(&ctx, &ap) != PRIB_OK) {
           errors[d] = prib_last_error();
+          done[d].set_value();
           return;
         }
         wt.lap("  context (CUDA init, tables)");
@@ -157,24 +178,36 @@ int main(int argc, char *argv[]) {
         if (prib_acc_run(ctx, (int32_t)ids.size(), sp.data(), sl.data(), image, ao.data(), co.data()) != PRIB_OK)
           errors[d] = prib_last_error();
         wt.lap("  prib_acc_run");
-        prib_acc_destroy(ctx);
-        wt.lap("  context teardown");
+        done[d].set_value();
+        prib_acc_destroy(ctx);  // freeing the DP state overlaps the file writing below
+        wt.lap("  context teardown [overlapped]");
       });
     }
-    for (auto &w : workers) w.join();
+    for (int d = 0; d < ngpu; d++) done[d].get_future().wait();
     for (int d = 0; d < ngpu; d++)
-      if (!errors[d].empty()) return die("Error: GPU " + std::to_string(d) + ": " + errors[d]);
+      if (!errors[d].empty()) {
+        for (auto &w : workers) w.join();
+        seq_ind.wait();
+        return die("Error: GPU " + std::to_string(d) + ": " + errors[d]);
+      }
   }
 
   timer.lap("accessibility (GPU)");
   // ---- database files --------------------------------------------------------------------------
-  if (!write_seq_ind(db, seqs, prm, err, formats_only ? nullptr : gpu_suffix_array)) return die(err);
-  timer.lap(".seq/.ind (SA on GPU, hash)");
-  if (!formats_only && !write_acc(db, seqs, image, acc_off, cond_off, delta, err)) return die(err);
+  bool ok = true;
+  if (!formats_only && !write_acc(db, seqs, image, acc_off, cond_off, delta, err)) ok = false;
   timer.lap(".acc");
-  if (!write_nam(db, names, err)) return die(err);
-  if (!write_bas(db, prm, err)) return die(err);
+  if (ok && !write_nam(db, names, err)) ok = false;
+  if (ok && !write_bas(db, prm, err)) ok = false;
   timer.lap(".nam/.bas");
+  if (!seq_ind.get()) {
+    ok = false;
+    err = err_si;
+  }
+  timer.lap("wait for .seq/.ind");
+  for (auto &w : workers) w.join();
+  timer.lap("wait for context teardown");
+  if (!ok) return die(err);
   if (image) prib_host_free(image);
   return 0;
 }
