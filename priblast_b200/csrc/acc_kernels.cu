@@ -46,7 +46,7 @@ template <typename real> struct TileMaxThreads { static constexpr int value = si
 template <typename real>
 constexpr size_t tile_smem_bytes() {
   return ((size_t)kTilePad + (size_t)kTileRows * TileMaxThreads<real>::value) * sizeof(real) +
-         Core<real>::kHotBytes + TileMaxThreads<real>::value + 16;
+         Core<real>::kHotBytes + TileMaxThreads<real>::value + kMaxSpan + 16;  // + base codes (outside: TC + W + 8)
 }
 
 template <typename real>
@@ -105,8 +105,9 @@ k_outside_tile(typename Core<real>::Ctx c, int TX, long long ntiles, real *scrat
   for (int k = t; k < Core<real>::kHotBytes / 4; k += TC)
     reinterpret_cast<uint32_t *>(stab)[k] = reinterpret_cast<const uint32_t *>(c.T)[k];
   const typename Core<real>::SmallTables &T = *reinterpret_cast<const typename Core<real>::SmallTables *>(stab);
+  uint8_t *sS = stab + Core<real>::kHotBytes;
   real *scrBif = scratch + (size_t)blockIdx.x * 2 * (W + 4) * TC;
-  const typename TL::OutSmem sm = TL::carve_out(base, TC);
+  const typename TL::OutSmem sm = TL::carve_out(base, TC, sS);
   const int dlast = TL::first_group(W);  // the groups of the inside pass, walked downwards
   for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     typename TL::Geo ge;
@@ -116,6 +117,10 @@ k_outside_tile(typename Core<real>::Ctx c, int TX, long long ntiles, real *scrat
     ge.H = W + 1;
     __syncthreads();
     for (int k = t; k < kTilePad + kTileRows * TC; k += TC) pad[k] = 0;
+    for (int k = t; k < TC + W + kOutBaseTail; k += TC) {
+      const long long col = ge.g0 - ge.H - kOutBaseLead + k;
+      sS[k] = (col >= 0 && col < c.NC) ? c.S[col] : 0;
+    }
     typename TL::ColState cs;
     TL::col_state(c, ge.g0 - ge.H + t, cs);
     __syncthreads();

@@ -30,6 +30,8 @@ enum {
   kRingSE = 4,
   kTileRows = 80,  // shared-memory rows of TC reals per CTA (both passes)
   kTilePad = 64,   // zeroed reals in front of the rings: the outside stencils look up to 33 columns to the left
+  kOutBaseLead = 2,  // outside pass: base codes staged in shared memory start 2 columns left of the tile ...
+  kOutBaseTail = 8,  // ... and reach W + 4 columns past its right edge (s[d + 3] of the last column)
 };
 
 template <typename real>
@@ -89,9 +91,11 @@ struct Tile {
   }
   struct OutSmem {
     real *stemO, *stemB, *stem, *mu, *m2;
+    const uint8_t *S;  // bases of global columns g0 - H - kOutBaseLead .. (TC + W + kOutBaseTail of them): S[kOutBaseLead + t] = column of thread t
   };
-  static PRIB_HD OutSmem carve_out(real *base, int TC) {
+  static PRIB_HD OutSmem carve_out(real *base, int TC, const uint8_t *S) {
     OutSmem s;
+    s.S = S;
     s.stemO = base;
     s.stemB = s.stemO + kRingOut * TC;
     s.stem = s.stemB + kRingOut * TC;
@@ -444,7 +448,7 @@ struct Tile {
     // a halo cell is exact iff its end reaches the owned region (all its super-intervals are in the tile)
     const bool live = p >= 0 && q <= L && t + d >= ge.H;
     if (live) {
-      const uint8_t *s = c.S + g;  // the right end q = p + d can lie beyond the tile: bases come from global
+      const uint8_t *s = sm.S + kOutBaseLead + t;  // staged for columns g0-H-2 .. g0-H+TC+W+5 (the right end q = p + d lies beyond the tile)
       const int sp = s[0], sp1 = s[1], sq_ = s[d], sq1 = s[d + 1];
       const bool inner = (p != 0 && q != L);
       const int te = inner ? T.bp[sp][sq1] : 0;

@@ -5,6 +5,7 @@
 // length-balanced partitioner over the GPUs of this box (db_format.h lpt_partition); output order is the
 // FASTA order, i.e. what the reference emits with -np 1 and -a heap|block.
 #include <getopt.h>
+#include <unistd.h>
 
 #include <cstdio>
 #include <cstdlib>
@@ -48,6 +49,37 @@ struct StageTimer {
   }
 };
 
+// GPUs of this box without touching CUDA: initialising the CUDA driver costs ~0.55 s + ~0.7 s per additional visible
+// B200 (5.4 s with 8 on an NVSwitch box, profiles/r1/cuda_init_8gpu.txt), so the front-end decides how many GPUs a
+// job is worth BEFORE the first CUDA call and hides the rest through CUDA_VISIBLE_DEVICES.
+static int count_device_nodes() {
+  int n = 0;
+  for (int k = 0; k < 64; k++) {
+    const std::string node = "/dev/nvidia" + std::to_string(k);
+    if (FILE *f = std::fopen(node.c_str(), "rb")) {
+      std::fclose(f);
+      ++n;
+    } else if (access(node.c_str(), F_OK) == 0) {
+      ++n;
+    }
+  }
+  return n;
+}
+
+// wall-time model: driver start-up 0.55 + 0.69 (n - 1) s, accessibility at 5.5e7 nt/s per GPU end to end
+static int pick_gpus(double total_nt, int avail) {
+  int best = 1;
+  double best_t = 1e300;
+  for (int n = 1; n <= avail; n++) {
+    const double t = 0.55 + 0.69 * (n - 1) + total_nt / 5.5e7 / n;
+    if (t < best_t) {
+      best_t = t;
+      best = n;
+    }
+  }
+  return best;
+}
+
 static void usage() {
   std::printf(
       "pRIblast-b200 db: database construction with GPU accessibility\n"
@@ -58,7 +90,7 @@ static void usage() {
       "-m (extension; also PRIB_ACC_MODE): auto = FP32 span-scaled engine with FP64 re-run (default; .acc within\n"
       "   1e-4 kcal/mol of the reference), fp64, exact = the reference's own arithmetic on the GPU (.acc, hence\n"
       "   the whole database and the ris output, byte-identical to the reference; ~50x slower than auto)\n"
-      "environment: PRIB_NUM_GPUS=n limits the GPUs used (default: all visible)\n");
+      "environment: PRIB_NUM_GPUS=n fixes the number of GPUs (default: as many as the job is worth, see pick_gpus)\n");
 }
 
 int main(int argc, char *argv[]) {
@@ -117,6 +149,22 @@ int main(int argc, char *argv[]) {
     cond_off[k] = total + (int64_t)seqs[k].size();
     total += 2 * (int64_t)seqs[k].size();
   }
+  int want = 0;
+  if (!formats_only) {
+    // how many GPUs is this job worth?  Decided before the first CUDA call (see count_device_nodes)
+    if (const char *e = std::getenv("PRIB_NUM_GPUS")) want = std::max(1, std::atoi(e));
+    if (!std::getenv("CUDA_VISIBLE_DEVICES")) {
+      const int nodes = count_device_nodes();
+      if (nodes > 1) {
+        const int n = std::min(nodes, want > 0 ? want : pick_gpus((double)total / 2, nodes));
+        if (n < nodes) {
+          std::string vis;
+          for (int k = 0; k < n; k++) vis += (k ? "," : "") + std::to_string(k);
+          setenv("CUDA_VISIBLE_DEVICES", vis.c_str(), 1);
+        }
+      }
+    }
+  }
   // <db>.seq / <db>.ind need only the sequences: they are built (suffix arrays on GPU 0) while the GPUs work on
   // the accessibility
   std::string err_si;
@@ -130,7 +178,8 @@ int main(int argc, char *argv[]) {
   std::vector<std::thread> workers;
   if (!formats_only) {
     int ngpu = prib_device_count();
-    if (const char *e = std::getenv("PRIB_NUM_GPUS")) ngpu = std::min(ngpu, std::max(1, std::atoi(e)));
+    if (want > 0) ngpu = std::min(ngpu, want);
+    if (timer.on) std::fprintf(stderr, "[db] using %d GPU(s)\n", ngpu);
     if (ngpu <= 0) {
       seq_ind.wait();
       return die("Error: no CUDA device available (there is no CPU path)");

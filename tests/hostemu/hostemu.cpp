@@ -131,7 +131,12 @@ void run_dp_tiled(EmuT<real> &e, int TC) {
     std::fill(smem.begin(), smem.end(), (real)0);
     if (g_poison) std::fill(scr.begin(), scr.end(), std::numeric_limits<real>::quiet_NaN());
     for (int t = 0; t < TC; t++) TL::col_state(c, ge.g0 - H + t, cs[t]);
-    typename TL::OutSmem sm = TL::carve_out(base, TC);
+    std::vector<uint8_t> sSo((size_t)TC + c.W + kOutBaseTail);
+    for (int k = 0; k < TC + c.W + kOutBaseTail; k++) {
+      const long long col = ge.g0 - ge.H - kOutBaseLead + k;
+      sSo[k] = (col >= 0 && col < c.NC) ? c.S[col] : 0;
+    }
+    typename TL::OutSmem sm = TL::carve_out(base, TC, sSo.data());
     for (int d0 = W + 1; d0 >= dfirst + kTT - 1; d0 -= kTT) {
       for (int t = 0; t < TC; t++)
         TL::template outside_deep<0>(c, *c.T, ge, sm, scr.data(), t, cs[t], d0, ((d0 % kRingOut) + kRingOut) % kRingOut,
