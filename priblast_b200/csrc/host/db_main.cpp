@@ -153,15 +153,29 @@ int main(int argc, char *argv[]) {
   if (!formats_only) {
     // how many GPUs is this job worth?  Decided before the first CUDA call (see count_device_nodes)
     if (const char *e = std::getenv("PRIB_NUM_GPUS")) want = std::max(1, std::atoi(e));
-    if (!std::getenv("CUDA_VISIBLE_DEVICES")) {
-      const int nodes = count_device_nodes();
-      if (nodes > 1) {
-        const int n = std::min(nodes, want > 0 ? want : pick_gpus((double)total / 2, nodes));
-        if (n < nodes) {
-          std::string vis;
-          for (int k = 0; k < n; k++) vis += (k ? "," : "") + std::to_string(k);
-          setenv("CUDA_VISIBLE_DEVICES", vis.c_str(), 1);
+    // the devices we may use: the caller's CUDA_VISIBLE_DEVICES list if there is one, else the /dev/nvidiaN nodes
+    std::vector<std::string> devs;
+    if (const char *cv = std::getenv("CUDA_VISIBLE_DEVICES")) {
+      std::string item;
+      for (const char *q = cv;; ++q) {
+        if (*q == ',' || *q == 0) {
+          if (!item.empty()) devs.push_back(item);
+          item.clear();
+          if (*q == 0) break;
+        } else {
+          item += *q;
         }
+      }
+    } else {
+      const int nodes = count_device_nodes();
+      for (int k = 0; k < nodes; k++) devs.push_back(std::to_string(k));
+    }
+    if (devs.size() > 1) {
+      const int n = std::min((int)devs.size(), want > 0 ? want : pick_gpus((double)total / 2, (int)devs.size()));
+      if (n < (int)devs.size()) {
+        std::string vis;
+        for (int k = 0; k < n; k++) vis += (k ? "," : "") + devs[k];
+        setenv("CUDA_VISIBLE_DEVICES", vis.c_str(), 1);
       }
     }
   }
