@@ -98,3 +98,41 @@ def test_exact_and_fast_engines_agree_within_reference_noise():
     for k, ((a, c), (b, d)) in enumerate(zip(ex, fa)):
         assert_close_kcal(b, a, ATOL_VS_REF, RTOL_VS_REF, f"seq {k} acc")
         assert_close_kcal(d, c, ATOL_VS_REF, RTOL_VS_REF, f"seq {k} cond")
+
+
+def test_full_size_bench_batch_cross_checked_by_the_exact_engine():
+    """BASELINE config 2 at the size bench.py times (1,536 transcripts, 2.8 M nt, one C-ABI call, one device
+    batch: the tiling / halo / layout paths of a full batch): every output finite and zero-padded as the
+    reference pads, and a strided sample of the batch recomputed by the exact engine — i.e. with the
+    reference's own bits — within the fast engine's stated tolerance."""
+    from conftest import ATOL_VS_REF, RTOL_VS_REF, assert_close_kcal
+    from priblast_b200 import Raccess, workloads
+    seqs = workloads.cfg2(first=1536)
+    with Raccess(70, 5) as fast:
+        res = fast.run_batch(seqs)
+        assert fast.counters()["batches"] == 1
+    for (a, c), s in zip(res, seqs):
+        L = len(s)
+        assert np.all(np.isfinite(a)) and np.all(np.isfinite(c))
+        assert np.all(a[L - 4:] == 0) and np.all(c[:5] == 0)
+        assert a[:L - 4].min() > -7.0 and a[:L - 4].max() < 54.3  # Q4 floor / fmath::log(0f) ceiling (SURVEY Q2)
+    idx = list(range(7, 1536, 96))
+    ex = rac_exact(70, 5).run_batch([seqs[k] for k in idx])
+    worst = 0.0
+    for k, (ea, ec) in zip(idx, ex):
+        worst = max(worst, assert_close_kcal(res[k][0], ea, ATOL_VS_REF, RTOL_VS_REF, f"seq {k} acc"))
+        worst = max(worst, assert_close_kcal(res[k][1], ec, ATOL_VS_REF, RTOL_VS_REF, f"seq {k} cond"))
+    print(f"full bench batch: {len(idx)} transcripts re-done with the reference's bits, max |d| = {worst:.2e} kcal/mol")
+
+
+def test_long_lncrna_fast_engine_against_exact_engine():
+    """BASELINE config 3 in miniature: a 25 kb lncRNA (Z ~ 6,500: far beyond the direct path), fast engine
+    against the reference's bits from the exact engine."""
+    from conftest import ATOL_VS_REF, RTOL_VS_REF, assert_close_kcal
+    from priblast_b200 import Raccess, workloads
+    seq = workloads.cfg3(first=2)[1][:25000]
+    (ea, ec), = rac_exact(70, 5).run_batch([seq])
+    with Raccess(70, 5, max_batch_bytes=4 << 30) as fast:
+        a, c = fast.run(seq)
+    assert_close_kcal(a, ea, ATOL_VS_REF, RTOL_VS_REF, "acc")
+    assert_close_kcal(c, ec, ATOL_VS_REF, RTOL_VS_REF, "cond")
