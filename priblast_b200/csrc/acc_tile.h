@@ -204,6 +204,19 @@ struct Tile {
     if (live) {
       const uint8_t *s = sm.S + t;
       const int si = s[0], si1 = s[1], sj = s[d], sj1 = s[d + 1];
+      const int te = (j != L) ? T.bp[si][sj1] : 0;
+      // Special-loop table entries (1x1, 1x2, 2x1, 2x2: 6.4 KB + 32 KB + 160 KB tables, L2-resident) are fetched
+      // first: their indices depend on the bases only, and the rest of the step hides the L2 latency.
+      real p11 = 0, p21a = 0, p21b = 0, p22 = 0;
+      if (te) {
+        const int sd1 = s[d - 1], sd2 = s[d - 2], s2 = s[2], s3 = s[3];
+        if (smax >= 2) p11 = c.e_int11[idx11(te, T.rt[T.bp[s2][sd1]], si1, sj)];
+        if (smax >= 3) {
+          p21a = c.e_int21[idx21(te, T.rt[T.bp[s2][sd2]], si1, sd1, sj)];
+          p21b = c.e_int21[idx21(T.rt[T.bp[s3][sd1]], te, sj, si1, s2)];
+        }
+        if (smax >= 4) p22 = c.e_int22[idx22(te, T.rt[T.bp[s3][sd2]], si1, s2, sd1, sj)];
+      }
       const int tp = T.bp[si1][sj];
       if (tp) {
         const int t2 = T.bp[s[2]][s[d - 1]];
@@ -219,7 +232,6 @@ struct Tile {
         stemI = stem * T.e_mmI[T.rt[tp]][sj1][si];
         stemB = stem * T.tau[tp];
       }
-      const int te = (j != L) ? T.bp[si][sj1] : 0;
       if (te) {
         real a = T.e_hairpin[d] * (d != 3 ? T.e_mmH[te][si1][sj] : T.tau[te]);
         const real *st1 = sm.stem + ((d - 1) & (kRingStem - 1)) * TC + t;
@@ -231,8 +243,7 @@ struct Tile {
                         st1[0] * T.e_stack[te][T.rt[T.bp[si1][s[d - 1]]]]);
         }
         if (smax >= 2) {
-          const int t2 = T.rt[T.bp[s[2]][s[d - 1]]];
-          a += st2[1] * c.e_int11[idx11(te, t2, si1, sj)];
+          a += st2[1] * p11;
           // long bulges: lengths >= 4 were summed by the deep step, 2 and 3 (rows d-2, d-3) follow here
 #pragma unroll
           for (int u = 2; u <= 3; ++u) {
@@ -244,14 +255,11 @@ struct Tile {
           a += T.tau[te] * bs;
         }
         if (smax >= 3) {
-          const int ta = T.rt[T.bp[s[2]][s[d - 2]]];
-          a += st3[1] * c.e_int21[idx21(te, ta, si1, s[d - 1], sj)];
-          const int tb = T.rt[T.bp[s[3]][s[d - 1]]];
-          a += st3[2] * c.e_int21[idx21(tb, te, sj, si1, s[2])];
+          a += st3[1] * p21a;
+          a += st3[2] * p21b;
         }
         if (smax >= 4) {
-          const int tc = T.rt[T.bp[s[3]][s[d - 2]]];
-          a += st4[2] * c.e_int22[idx22(te, tc, si1, s[2], s[d - 1], sj)];
+          a += st4[2] * p22;
           a += T.e_mmI[te][si1][sj] * gs;
         }
         const int tt = T.rt[te];
@@ -452,6 +460,25 @@ struct Tile {
       const int sp = s[0], sp1 = s[1], sq_ = s[d], sq1 = s[d + 1];
       const bool inner = (p != 0 && q != L);
       const int te = inner ? T.bp[sp][sq1] : 0;
+      // Global operands first (their addresses depend on the bases only; the rest of the step hides the latency):
+      // the exponent of the base term and the special-loop table entries.
+      const int t2_ = T.bp[sp1][sq_];
+      double la = 0, lb = 0, lz = 0;  // loaded here, combined where the base term is formed (in-order issue: a
+                                      // dependent add up here would stall the warp on the loads right away)
+      real p11 = 0, p21a = 0, p21b = 0, p22 = 0;
+      if (t2_) {
+        la = c.lao[g];
+        lb = c.lbo[g + d];
+        lz = c.lao[cs.zcol];
+        const int t2r_ = T.rt[t2_];
+        const int sm1 = s[-1], sm2 = s[-2], sd2 = s[d + 2], sd3 = s[d + 3];
+        if (smax >= 2) p11 = c.e_int11[idx11(T.bp[sm1][sd2], t2r_, sp, sq1)];
+        if (smax >= 3) {
+          p21a = c.e_int21[idx21(T.bp[sm1][sd3], t2r_, sp, sq1, sd2)];
+          p21b = c.e_int21[idx21(t2r_, T.bp[sm2][sd2], sq1, sm1, sp)];
+        }
+        if (smax >= 4) p22 = c.e_int22[idx22(T.bp[sm2][sd3], t2r_, sm1, sp, sq1, sd2)];
+      }
       const real *b2 = sm.stem + ((d + 2) & (kRingStem - 1)) * TC + t;
       const real bse = (inner && d + 2 <= W + 1) ? b2[-1] : 0;  // Beta_stemend(p,q), :277-279
       if (inner) {
@@ -466,7 +493,6 @@ struct Tile {
       if (t2) {
         const int t2r = T.rt[t2];
         const real dang = K::e_dangle(T, t2, p > 0, sp, q < L, sq1);
-        const real base = (real)exp(c.lao[g] + c.lbo[g + d] - c.lao[cs.zcol]) * dang * T.sB[d];
         real l = 0;
         if (smax >= 0) l += bse * T.e_stack[te][t2r];
         const real *b3 = sm.stem + ((d + 3) & (kRingStem - 1)) * TC + t;
@@ -479,21 +505,18 @@ struct Tile {
           l += bu[1] * (b3[-2] * T.e_stack[ta][t2r] + b3[-1] * T.e_stack[tb][t2r]);
         }
         if (smax >= 2) {
-          const int to = T.bp[s[-1]][s[d + 2]];
-          l += b4[-2] * c.e_int11[idx11(to, t2r, sp, sq1)];
+          l += b4[-2] * p11;
           l += T.tau[t2r] * bs;
         }
         if (smax >= 3) {
-          const int ta = T.bp[s[-1]][s[d + 3]];
-          l += b5[-2] * c.e_int21[idx21(ta, t2r, sp, sq1, s[d + 2])];
-          const int tb = T.bp[s[-2]][s[d + 2]];
-          l += b5[-3] * c.e_int21[idx21(t2r, tb, sq1, s[-1], sp)];
+          l += b5[-2] * p21a;
+          l += b5[-3] * p21b;
         }
         if (smax >= 4) {
-          const int tc = T.bp[s[-2]][s[d + 3]];
-          l += b6[-3] * c.e_int22[idx22(tc, t2r, s[-1], sp, sq1, s[d + 2])];
+          l += b6[-3] * p22;
           l += T.e_mmI[t2r][sq1][sp] * gs;
         }
+        const real base = (real)exp(la + lb - lz) * dang * T.sB[d];  // raccess.cpp:370, divided by Z
         bstem = base + T.k2 * l + bmulti2 * T.e_mlintern * dang;
         bstemO = bstem * T.e_mmI[t2][s[2]][s[d - 1]];
         bstemB = bstem * T.tau[t2];
