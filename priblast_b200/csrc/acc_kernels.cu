@@ -44,10 +44,36 @@ template <typename real> struct TileMaxThreads { static constexpr int value = si
 // grid = resident CTAs (one per SM: the rings take ~all shared memory), blockDim = TC, tiles round-robin.
 // dynamic smem: (kTilePad + kTileRows * TC) reals + hot tables + (TC + 16) base codes.
 template <typename real>
-constexpr size_t tile_smem_bytes() {
+__host__ __device__ constexpr size_t tile_smem_bytes() {
   return ((size_t)kTilePad + (size_t)kTileRows * TileMaxThreads<real>::value) * sizeof(real) +
-         Core<real>::kHotBytes + TileMaxThreads<real>::value + kMaxSpan + 16;  // + base codes (outside: TC + W + 8)
+         (Core<real>::kHotBytes + TileMaxThreads<real>::value + kMaxSpan + 16 + 15) / 16 * 16  // + base codes (outside: TC + W + 8)
+         + 16;                                                                                   // + the step barrier (last 16 bytes)
 }
+
+// Split CTA barrier (mbarrier): arrive after the stores other threads will read, wait before reading theirs.
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ unsigned long long mbar_arrive(unsigned long long *bar) {
+  unsigned long long state;
+  asm volatile("mbarrier.arrive.shared::cta.b64 %0, [%1];" : "=l"(state) : "r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+  return state;
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned long long state) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "MBAR_WAIT:\n"
+      "mbarrier.try_wait.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra MBAR_DONE;\n"
+      "bra MBAR_WAIT;\n"
+      "MBAR_DONE:\n"
+      "}" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "l"(state) : "memory");
+}
+struct StepArrive {  // the hook of Tile::inside_shallow / outside_shallow
+  unsigned long long *bar, *state;
+  __device__ __forceinline__ void operator()() const { *state = mbar_arrive(bar); }
+};
 
 template <typename real>
 __global__ void __launch_bounds__(TileMaxThreads<real>::value, 1)
@@ -66,6 +92,10 @@ k_inside_tile(typename Core<real>::Ctx c, int TX, long long ntiles, real *scratc
   real *scrM2 = scrM1 + (size_t)(W + 4) * TC;
   const typename TL::InSmem sm = TL::carve_in(base, TC, sS);
   const int dfirst = TL::first_group(W);
+  constexpr size_t bar_off = tile_smem_bytes<real>() - 16;
+  unsigned long long &step_bar = *reinterpret_cast<unsigned long long *>(smem_raw + bar_off);
+  if (t == 0) mbar_init(&step_bar, TC);
+  __syncthreads();
   for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     typename TL::Geo ge;
     ge.g0 = tile * TX;
@@ -84,8 +114,10 @@ k_inside_tile(typename Core<real>::Ctx c, int TX, long long ntiles, real *scratc
 #pragma unroll
       for (int k = 0; k < kTT; ++k) {
         if (d0 + k >= kTurn) {  // uniform
-          TL::template inside_shallow<TC>(c, T, ge, sm, scrM1, scrM2, t, cs, d0 + k, gs[k], mb[k], bs[k]);
-          __syncthreads();
+          unsigned long long phase;
+          TL::template inside_shallow<TC>(c, T, ge, sm, scrM1, scrM2, t, cs, d0 + k, gs[k], mb[k], bs[k],
+                                          StepArrive{&step_bar, &phase});
+          mbar_wait(&step_bar, phase);
         }
       }
     }
@@ -109,6 +141,10 @@ k_outside_tile(typename Core<real>::Ctx c, int TX, long long ntiles, real *scrat
   real *scrBif = scratch + (size_t)blockIdx.x * 2 * (W + 4) * TC;
   const typename TL::OutSmem sm = TL::carve_out(base, TC, sS);
   const int dlast = TL::first_group(W);  // the groups of the inside pass, walked downwards
+  constexpr size_t bar_off = tile_smem_bytes<real>() - 16;
+  unsigned long long &step_bar = *reinterpret_cast<unsigned long long *>(smem_raw + bar_off);
+  if (t == 0) mbar_init(&step_bar, TC);
+  __syncthreads();
   for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     typename TL::Geo ge;
     ge.g0 = tile * TX;
@@ -131,9 +167,10 @@ k_outside_tile(typename Core<real>::Ctx c, int TX, long long ntiles, real *scrat
 #pragma unroll
       for (int k = 0; k < kTT; ++k) {
         if (d0 - k >= kTurn) {  // uniform
+          unsigned long long phase;
           TL::template outside_shallow<TC>(c, T, ge, sm, scrBif, t, cs, d0 - k, slot, o.gs[k], o.bs[k], o.bm1[k],
-                                           o.ks[k]);
-          __syncthreads();
+                                           o.ks[k], StepArrive{&step_bar, &phase});
+          mbar_wait(&step_bar, phase);
         }
         slot = slot == 0 ? kRingOut - 1 : slot - 1;
       }

@@ -34,6 +34,12 @@ enum {
   kOutBaseTail = 8,  // ... and reach W + 4 columns past its right edge (s[d + 3] of the last column)
 };
 
+// Called by the shallow steps right after their shared-memory / scratch stores: the CUDA kernels arrive at a
+// split barrier there, so the persistent global stores and range checks that follow overlap the barrier skew.
+struct NoStepHook {
+  PRIB_HD void operator()() const {}
+};
+
 template <typename real>
 struct Tile {
   typedef Core<real> K;
@@ -192,9 +198,10 @@ struct Tile {
   // ---------------------------------------------------------------------------------------------
   // inside, shallow step: finishes cell (i, i + d) of column t given its deep sums gs / mb.
   // ---------------------------------------------------------------------------------------------
-  template <int TCC = 0>
+  template <int TCC = 0, typename Hook = NoStepHook>
   static PRIB_HD void inside_shallow(const Ctx &c, const ST &T, const Geo &ge, const InSmem &sm, real *scrM1,
-                                     real *scrM2, int t, const ColState &cs, int d, real gs, real mb, real bs) {
+                                     real *scrM2, int t, const ColState &cs, int d, real gs, real mb, real bs,
+                                     Hook stores_done = Hook()) {
     const int TC = TCC > 0 ? TCC : ge.TC;
     const real *bu = K::bulge_tab(T);
     real stem = 0, stemI = 0, stemB = 0, stemD = 0, se = 0, mu = 0, m1 = 0, m2 = 0;
@@ -276,6 +283,7 @@ struct Tile {
     sm.m2[(d & 1) * TC + t] = m2;
     scrM1[d * TC + t] = m1;
     scrM2[d * TC + t] = m2;
+    stores_done();
     // persistent outputs: owned columns only
     if (t < ge.TX && i >= 0 && j <= L) {
       const long long g = ge.g0 + t;
@@ -443,10 +451,10 @@ struct Tile {
     }
   }
 
-  template <int TCC = 0>
+  template <int TCC = 0, typename Hook = NoStepHook>
   static PRIB_HD void outside_shallow(const Ctx &c, const ST &T, const Geo &ge, const OutSmem &sm, real *scrBif, int t,
                                       const ColState &cs, int d, int slot_d /* = d % kRingOut */, real gs, real bs,
-                                      real bm1, real ks) {
+                                      real bm1, real ks, Hook stores_done = Hook()) {
     const int TC = TCC > 0 ? TCC : ge.TC, W = c.W;
     const real *bu = K::bulge_tab(T);
     real bstem = 0, bstemO = 0, bstemB = 0, bmulti = 0, bmulti2 = 0, bmbif = 0;
@@ -528,6 +536,7 @@ struct Tile {
     sm.mu[(d & 1) * TC + t] = bmulti;
     sm.m2[(d & 1) * TC + t] = bmulti2;
     scrBif[d * TC + t] = bmbif;
+    stores_done();
     if (t >= ge.H && p >= 0 && q <= L) {
       c.at(B_STEM, d, g) = bstem;
       c.at(B_STEMO, d, g) = bstemO;
