@@ -707,10 +707,16 @@ struct BiTile {
         }
       }
       // pass B: generic interior loops out of the shared-memory tile, dense over groups of kTT outer spans
+      // (the outer-pair weights of the next group are loaded while this group is being evaluated)
+      real wn[kTT];
+#pragma unroll
+      for (int k = 0; k < kTT; ++k) wn[k] = (delta + 5 + k <= dpmax) ? c.ld(B_STEMO, delta + 5 + k + 2, g - 1) : (real)0;
       for (int dp0 = delta + 5; dp0 <= dpmax; dp0 += kTT) {
         real w[kTT];
 #pragma unroll
-        for (int k = 0; k < kTT; ++k) w[k] = (dp0 + k <= dpmax) ? c.ld(B_STEMO, dp0 + k + 2, g - 1) : (real)0;
+        for (int k = 0; k < kTT; ++k) w[k] = wn[k];
+#pragma unroll
+        for (int k = 0; k < kTT; ++k) wn[k] = (dp0 + kTT + k <= dpmax) ? c.ld(B_STEMO, dp0 + kTT + k + 2, g - 1) : (real)0;
         dense_rows<1, COLS, ULO, 1>(tile + (dp0 - 5) * cols + t, cols, dp0, cv, w, ml);
       }
     }
@@ -787,11 +793,17 @@ struct BiTile {
           }
         }
       }
+      real wn[kTT];
+#pragma unroll
+      for (int k = 0; k < kTT; ++k)
+        wn[k] = (delta + 5 + k <= dpmax) ? c.ld(B_STEMO, delta + 5 + k + 2, g2 - (delta + 5) - k - 1) : (real)0;
       for (int dp0 = delta + 5; dp0 <= dpmax; dp0 += kTT) {
         real w[kTT];
 #pragma unroll
+        for (int k = 0; k < kTT; ++k) w[k] = wn[k];
+#pragma unroll
         for (int k = 0; k < kTT; ++k)
-          w[k] = (dp0 + k <= dpmax) ? c.ld(B_STEMO, dp0 + k + 2, g2 - dp0 - k - 1) : (real)0;
+          wn[k] = (dp0 + kTT + k <= dpmax) ? c.ld(B_STEMO, dp0 + kTT + k + 2, g2 - dp0 - kTT - k - 1) : (real)0;
         dense_rows<1, COLS, ULO, -1>(tile + (dp0 - 5) * cols + t + 31, cols, dp0, cv, w, mr);
       }
     }
