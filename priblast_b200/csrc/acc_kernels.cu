@@ -360,7 +360,7 @@ __global__ void __launch_bounds__(kThreads) k_hairpin_suffix(typename Core<real>
   if (g < c.NC) Core<real>::hairpin_suffix(c, g);
 }
 template <typename real>
-__global__ void __launch_bounds__(kThreads) k_finalize(typename Core<real>::Ctx c) {
+__global__ void __launch_bounds__(kThreads, 8) k_finalize(typename Core<real>::Ctx c) {
   const long long g = (long long)blockIdx.x * kThreads + threadIdx.x;
   if (g < c.NC) Core<real>::finalize_position(c, g);
 }
