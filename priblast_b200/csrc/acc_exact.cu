@@ -513,8 +513,13 @@ __global__ void __launch_bounds__(128) k_ex_hairpin(ExCtx c) {
 // order of the reference's p, q loops), compact the existing terms in order into shared memory, and then each
 // position folds its own sub-sequence of them: first the right-strand prefixes of the rows p < k + w, then the
 // row p == k + w (bp) and all later rows (cbp) — contiguous ranges of the compacted list.
-constexpr int kBiB = 256;
-constexpr int kTri = 496;  // (u1, u2) with u1 + u2 <= 30
+#ifndef PRIB_EX_BIB
+#define PRIB_EX_BIB 256
+#endif
+constexpr int kBiB = PRIB_EX_BIB;  // positions (= threads) per CTA
+constexpr int kTri = 496;          // (u1, u2) with u1 + u2 <= 30
+constexpr int kBiRounds = (kTri + kBiB - 1) / kBiB;
+static_assert(kBiB % 32 == 0 && kBiRounds * (kBiB / 32) <= 16, "s_mask holds 16 ballot words");
 
 __device__ __forceinline__ int tri_row_start(int u1) { return 31 * u1 - (u1 * (u1 - 1)) / 2; }
 
@@ -527,10 +532,10 @@ __global__ void __launch_bounds__(kBiB) k_ex_biloop(ExCtx c) {
   const long long g0 = (long long)blockIdx.x * kBiB;
   const ExTab &T = *c.T;
   const int W = c.W, w = c.delta;
-  if (tid < 31) {  // row u1 = tid: u2 = 30 - u1 .. 0 (q ascending)
-    int n = tri_row_start(tid);
-    for (int u2 = 30 - tid; u2 >= 0; --u2, ++n) {
-      s_u1[n] = (unsigned char)tid;
+  for (int r = tid; r < 31; r += kBiB) {  // row u1 = r: u2 = 30 - u1 .. 0 (q ascending)
+    int n = tri_row_start(r);
+    for (int u2 = 30 - r; u2 >= 0; --u2, ++n) {
+      s_u1[n] = (unsigned char)r;
       s_u2[n] = (unsigned char)u2;
     }
   }
@@ -596,13 +601,13 @@ __global__ void __launch_bounds__(kBiB) k_ex_biloop(ExCtx c) {
         if (be == EX_NEG) continue;
         const int u1max = (j - i - 6 < kMaxLoop) ? j - i - 6 : kMaxLoop;  // p <= min(i + 31, j - 5)
         const int nflat = tri_row_start(u1max + 1);
-        // 1. evaluate the inner pairs (two rounds of kBiB), note which exist
-        double tv[2];
-        int wi[2];
-        unsigned int mk[2];
-        bool ok[2];
+        // 1. evaluate the inner pairs (kBiRounds rounds of kBiB), note which exist
+        double tv[kBiRounds];
+        int wi[kBiRounds];
+        unsigned int mk[kBiRounds];
+        bool ok[kBiRounds];
 #pragma unroll
-        for (int r = 0; r < 2; ++r) {
+        for (int r = 0; r < kBiRounds; ++r) {
           const int n = r * kBiB + tid;
           ok[r] = false;
           tv[r] = 0;
@@ -628,7 +633,7 @@ __global__ void __launch_bounds__(kBiB) k_ex_biloop(ExCtx c) {
         __syncthreads();
         // 2. compact in order; start of every row in the compacted list
 #pragma unroll
-        for (int r = 0; r < 2; ++r) {
+        for (int r = 0; r < kBiRounds; ++r) {
           if (ok[r]) {
             int pos = __popc(mk[r] & ((1u << lane) - 1));
             for (int x = 0; x < wi[r]; ++x) pos += __popc(s_mask[x]);
@@ -636,12 +641,12 @@ __global__ void __launch_bounds__(kBiB) k_ex_biloop(ExCtx c) {
             s_cu2[pos] = s_u2[r * kBiB + tid];
           }
         }
-        if (tid <= u1max + 1) {
-          const int bit = tri_row_start(tid);
+        for (int r = tid; r <= u1max + 1; r += kBiB) {
+          const int bit = tri_row_start(r);
           int pos = 0;
           for (int x = 0; x < (bit >> 5); ++x) pos += __popc(s_mask[x]);
           if ((bit & 31) != 0) pos += __popc(s_mask[bit >> 5] & ((1u << (bit & 31)) - 1));
-          s_cstart[tid] = (short)pos;
+          s_cstart[r] = (short)pos;
         }
         __syncthreads();
         // 3. every position folds its terms
