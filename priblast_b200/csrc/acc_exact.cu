@@ -508,14 +508,14 @@ __global__ void __launch_bounds__(128) k_ex_hairpin(ExCtx c) {
 //   left strand : i + 1 <= k <= p - w   (k == p - w feeds bp, otherwise cbp)      :644-650 / :713-729
 //   right strand: q + 1 <= k <= j - w   (k == j - w feeds bp, otherwise cbp)      :652-658 / :731-745
 // (the two cases exclude each other: left needs p > k, right q < k, and q > p).
-// One CTA owns kBiB consecutive columns.  It walks the outer pairs (i, j) that can reach any of its positions;
+// One CTA owns kBiB (64) consecutive columns.  It walks the outer pairs (i, j) that can reach any of its positions;
 // for each pair the threads evaluate the <= 496 inner pairs ONCE, in parallel (flat index n -> (u1, u2) in the
 // order of the reference's p, q loops), compact the existing terms in order into shared memory, and then each
 // position folds its own sub-sequence of them: first the right-strand prefixes of the rows p < k + w, then the
 // row p == k + w (bp) and all later rows (cbp) — contiguous ranges of the compacted list.
 #ifndef PRIB_EX_BIB
-#define PRIB_EX_BIB 256
-#endif
+#define PRIB_EX_BIB 64  // measured on B200 (direct / log-sum sets of profiles/exact_split.py): 256 -> 246 / 919 ms,
+#endif                  // 64 -> 160 / 485 ms, 32 -> 302 / 606 ms
 constexpr int kBiB = PRIB_EX_BIB;  // positions (= threads) per CTA
 constexpr int kTri = 496;          // (u1, u2) with u1 + u2 <= 30
 constexpr int kBiRounds = (kTri + kBiB - 1) / kBiB;
