@@ -75,6 +75,9 @@ static __constant__ double g_bulge_d[32];
 static __constant__ float g_bulge_f[32];
 static __constant__ double g_cf_d[32];
 static __constant__ float g_cf_f[32];
+// (cg[a], cg[b]) for a, b = 0..7 (index 7 = 0): coefficient pairs of the packed FP32 stencils (FFMA2 takes the pair
+// as a 64-bit uniform-register operand, so the coefficients cost no vector registers)
+static __constant__ float2 g_cgpair_f[64];
 template <typename real> struct ConstTab;
 template <> struct ConstTab<double> {
   static __device__ __forceinline__ const double *conv() { return g_conv_d; }

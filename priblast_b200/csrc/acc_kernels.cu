@@ -846,6 +846,11 @@ int setup_engine(prib_ctx *c, const ScaleSpec &spec, size_t smem_max, std::strin
     CU(cudaMemcpyToSymbol(g_conv_f, &tab.small.conv[0][0], sizeof(real) * 32 * 32));
     CU(cudaMemcpyToSymbol(g_bulge_f, tab.small.e_bulge, sizeof(real) * 32));
     CU(cudaMemcpyToSymbol(g_cf_f, tab.small.cf, sizeof(real) * 32));
+    float2 pairs[64];
+    for (int a = 0; a < 8; a++)
+      for (int b = 0; b < 8; b++)
+        pairs[a * 8 + b] = make_float2(a < 7 ? (float)tab.small.cg[a] : 0.f, b < 7 ? (float)tab.small.cg[b] : 0.f);
+    CU(cudaMemcpyToSymbol(g_cgpair_f, pairs, sizeof(pairs)));
   }
   if (c->d_log == nullptr) {
     CU(cudaMalloc(&c->d_log, tab.log_tbl.size() * sizeof(float)));

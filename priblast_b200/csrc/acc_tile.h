@@ -34,6 +34,20 @@ enum {
   kOutBaseTail = 8,  // ... and reach W + 4 columns past its right edge (s[d + 3] of the last column)
 };
 
+#if defined(__CUDA_ARCH__)
+// Blackwell packed FP32: one FFMA2 = two FMAs with the same multiplicand v (scalar operand, broadcast to both
+// halves) and a coefficient PAIR from the constant bank (uniform-register operand): acc.lo += v * g.x, acc.hi += v * g.y.
+__device__ __forceinline__ void ffma2_bcast(unsigned long long &acc, float v, float2 g) {
+  unsigned long long vv, gg;
+  asm("mov.b64 %0, {%1, %1};" : "=l"(vv) : "f"(v));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(gg) : "f"(g.x), "f"(g.y));
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(vv), "l"(gg));
+}
+__device__ __forceinline__ void unpack2(unsigned long long p, float &lo, float &hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(p));
+}
+#endif
+
 // Called by the shallow steps right after their shared-memory / scratch stores: the CUDA kernels arrive at a
 // split barrier there, so the persistent global stores and range checks that follow overlap the barrier skew.
 struct NoStepHook {
@@ -71,6 +85,12 @@ struct Tile {
     cs.zcol = c.seq_off[sq] + cs.L;
   }
 
+  // index into the coefficient-pair table of the packed stencils: ninio step of (u1, sum), 7 = "not a term"
+  static PRIB_HD constexpr int in_cidx(int u1, int sum) {
+    if (!(sum >= 4 && sum <= kMaxLoop && u1 <= sum - 1 && !(sum == 4 && u1 == 2))) return 7;
+    const int k = 2 * u1 - sum, a = k < 0 ? -k : k;
+    return a > 6 ? 6 : a;
+  }
   static PRIB_HD real gsel(int k, real g0, real g1, real g2, real g3, real g4, real g5, real g6) {
     return k == 0 ? g0 : k == 1 ? g1 : k == 2 ? g2 : k == 3 ? g3 : k == 4 ? g4 : k == 5 ? g5 : g6;
   }
@@ -121,14 +141,34 @@ struct Tile {
       real rs[kTT];
 #pragma unroll
       for (int k = 0; k < kTT; ++k) rs[k] = 0;
+#if defined(__CUDA_ARCH__)
+      if constexpr (sizeof(real) == 4 && kTT == 4) {
+        // FP32 engine: targets (0, 1) and (2, 3) share one FFMA2 each per source element; a target that does not
+        // take the element gets the coefficient 0 (index 7 of the pair table) — the same sums, two FMAs per issue slot
+        unsigned long long r01 = 0, r23 = 0;
 #pragma unroll
-      for (int x = 1; x <= S + kTT - 2; ++x) {  // x = u1; target k takes it while x <= (S + k) - 1
-        const real v = row[x];
+        for (int x = 1; x <= S + kTT - 2; ++x) {
+          const float v = row[x];
+          const int a0 = in_cidx(x, S), a1 = in_cidx(x, S + 1), a2 = in_cidx(x, S + 2), a3 = in_cidx(x, S + 3);
+          if (a0 != 7 || a1 != 7) ffma2_bcast(r01, v, g_cgpair_f[a0 * 8 + a1]);
+          if (a2 != 7 || a3 != 7) ffma2_bcast(r23, v, g_cgpair_f[a2 * 8 + a3]);
+        }
+        float q0, q1, q2, q3;
+        unpack2(r01, q0, q1);
+        unpack2(r23, q2, q3);
+        rs[0] = q0, rs[1] = q1, rs[2] = q2, rs[3] = q3;
+      } else
+#endif
+      {
 #pragma unroll
-        for (int k = 0; k < kTT; ++k) {
-          const int sum = S + k;
-          if (sum >= 4 && sum <= kMaxLoop && x <= sum - 1 && !(sum == 4 && x == 2))
-            rs[k] += gsel(K::gidx(x, sum), g0, g1, g2, g3, g4, g5, g6) * v;
+        for (int x = 1; x <= S + kTT - 2; ++x) {  // x = u1; target k takes it while x <= (S + k) - 1
+          const real v = row[x];
+#pragma unroll
+          for (int k = 0; k < kTT; ++k) {
+            const int sum = S + k;
+            if (sum >= 4 && sum <= kMaxLoop && x <= sum - 1 && !(sum == 4 && x == 2))
+              rs[k] += gsel(K::gidx(x, sum), g0, g1, g2, g3, g4, g5, g6) * v;
+          }
         }
       }
 #pragma unroll
@@ -333,14 +373,32 @@ struct Tile {
       real rs[kTT];
 #pragma unroll
       for (int k = 0; k < kTT; ++k) rs[k] = 0;
+#if defined(__CUDA_ARCH__)
+      if constexpr (sizeof(real) == 4 && kTT == 4) {  // packed FP32 (see in_rows)
+        unsigned long long r01 = 0, r23 = 0;
 #pragma unroll
-      for (int y = 1; y <= S + kTT - 4; ++y) {  // y = u1: source column t - 1 - u1
-        const real v = rowO[-y];
+        for (int y = 1; y <= S + kTT - 4; ++y) {
+          const float v = rowO[-y];
+          const int a0 = in_cidx(y, S - 2), a1 = in_cidx(y, S - 1), a2 = in_cidx(y, S), a3 = in_cidx(y, S + 1);
+          if (a0 != 7 || a1 != 7) ffma2_bcast(r01, v, g_cgpair_f[a0 * 8 + a1]);
+          if (a2 != 7 || a3 != 7) ffma2_bcast(r23, v, g_cgpair_f[a2 * 8 + a3]);
+        }
+        float q0, q1, q2, q3;
+        unpack2(r01, q0, q1);
+        unpack2(r23, q2, q3);
+        rs[0] = q0, rs[1] = q1, rs[2] = q2, rs[3] = q3;
+      } else
+#endif
+      {
 #pragma unroll
-        for (int k = 0; k < kTT; ++k) {
-          const int sum = S + k - 2;
-          if (sum >= 4 && sum <= kMaxLoop && y <= sum - 1 && !(sum == 4 && y == 2))
-            rs[k] += gsel(K::gidx(y, sum), g0, g1, g2, g3, g4, g5, g6) * v;
+        for (int y = 1; y <= S + kTT - 4; ++y) {  // y = u1: source column t - 1 - u1
+          const real v = rowO[-y];
+#pragma unroll
+          for (int k = 0; k < kTT; ++k) {
+            const int sum = S + k - 2;
+            if (sum >= 4 && sum <= kMaxLoop && y <= sum - 1 && !(sum == 4 && y == 2))
+              rs[k] += gsel(K::gidx(y, sum), g0, g1, g2, g3, g4, g5, g6) * v;
+          }
         }
       }
 #pragma unroll
