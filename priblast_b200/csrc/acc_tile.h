@@ -714,6 +714,76 @@ struct BiTile {
     if constexpr (S < kMaxLoop) dense_rows<S + 1, COLS, ULO, DIR>(base, cols, dp0, cv, w, m);
   }
 
+#if defined(__CUDA_ARCH__)
+  // ---- packed FP32 variant of the dense pass (FFMA2): strand lengths (U, U + 1) share one accumulator pair ----
+  static __device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
+    unsigned long long p;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(p) : "f"(lo), "f"(hi));
+    return p;
+  }
+  static __device__ __forceinline__ void ffma2(unsigned long long &acc, unsigned long long a, unsigned long long b) {
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(a), "l"(b));
+  }
+  static PRIB_HD constexpr bool dn_use(int u, int S, int ULO) { return u >= ULO && u <= kMaxLoop && dn_any(u, S); }
+
+  // coefficient q of strand length U for source row S (see dense_cols), scalar
+  template <int S, int U>
+  static __device__ __forceinline__ float dense_q(const float *cv, const float (&w)[kTT], float qsat) {
+    if constexpr (dn_allsat(U, S)) {
+      return qsat;
+    } else {
+      float q = 0;
+#pragma unroll
+      for (int k = 0; k < kTT; ++k)
+        if (dn_valid(U, S + k)) q += w[k] * cv[U * 32 + (S + k - U)];
+      return q;
+    }
+  }
+
+  template <int S, int U, int ULO, int DIR>
+  static __device__ __forceinline__ void dense_cols2(const float *row, const float *cv, const float (&w)[kTT], float qsat,
+                                                     unsigned long long (&mp)[kMaxLoop / 2 + 1]) {
+    constexpr bool v0 = dn_use(U, S, ULO), v1 = dn_use(U + 1, S, ULO);
+    if constexpr (v0 || v1) {
+      unsigned long long qq;
+      if constexpr (v0 && v1 && !dn_allsat(U, S) && !dn_allsat(U + 1, S)) {
+        // both coefficients are 4-term sums over the targets: one FFMA2 per target, coefficient pairs from the
+        // constant bank
+        qq = 0;
+#pragma unroll
+        for (int k = 0; k < kTT; ++k) {
+          const bool a = dn_valid(U, S + k), b = dn_valid(U + 1, S + k);
+          if (a || b)
+            ffma2(qq, pack2(w[k], w[k]),
+                  pack2(a ? cv[U * 32 + (S + k - U)] : 0.f, b ? cv[(U + 1) * 32 + (S + k - U - 1)] : 0.f));
+        }
+      } else {
+        float q0 = 0, q1 = 0;
+        if constexpr (v0) q0 = dense_q<S, U>(cv, w, qsat);
+        if constexpr (v1) q1 = dense_q<S, U + 1>(cv, w, qsat);
+        qq = pack2(q0, q1);
+      }
+      ffma2(mp[U / 2], pack2(v0 ? row[DIR * U] : 0.f, v1 ? row[DIR * (U + 1)] : 0.f), qq);
+    }
+    if constexpr (U + 2 <= kMaxLoop) dense_cols2<S, U + 2, ULO, DIR>(row, cv, w, qsat, mp);
+  }
+
+  template <int S, int COLS, int ULO, int DIR>
+  static __device__ __forceinline__ void dense_rows2(const float *base, int cols, int dp0, const float *cv,
+                                                     const float (&w)[kTT], unsigned long long (&mp)[kMaxLoop / 2 + 1]) {
+    if (dp0 - S >= 5) {
+      const float *row = base - S * (COLS > 0 ? COLS : cols);
+      float qsat = 0;
+      if constexpr (dn_row_has_sat(S, ULO)) {
+#pragma unroll
+        for (int k = 0; k < kTT; ++k) qsat += w[k] * cv[(S + k - 1) * 32 + 1];
+      }
+      dense_cols2<S, (ULO / 2) * 2, ULO, DIR>(row, cv, w, qsat, mp);
+    }
+    if constexpr (S < kMaxLoop) dense_rows2<S + 1, COLS, ULO, DIR>(base, cols, dp0, cv, w, mp);
+  }
+#endif
+
   // Per-thread state carried from the generic pass (Alpha_stemI tile) to the bulge pass (Alpha_stemB tile).
   struct Strand {
     real w[kMaxLoop + 1];  // strand weights by strand length
@@ -769,14 +839,34 @@ struct BiTile {
       real wn[kTT];
 #pragma unroll
       for (int k = 0; k < kTT; ++k) wn[k] = (delta + 5 + k <= dpmax) ? c.ld(B_STEMO, delta + 5 + k + 2, g - 1) : (real)0;
+#if defined(__CUDA_ARCH__)
+      unsigned long long mp[kMaxLoop / 2 + 1];  // FP32 engine: packed accumulators (m[2j], m[2j + 1])
+#pragma unroll
+      for (int u = 0; u <= kMaxLoop / 2; ++u) mp[u] = 0;
+#endif
       for (int dp0 = delta + 5; dp0 <= dpmax; dp0 += kTT) {
         real w[kTT];
 #pragma unroll
         for (int k = 0; k < kTT; ++k) w[k] = wn[k];
 #pragma unroll
         for (int k = 0; k < kTT; ++k) wn[k] = (dp0 + kTT + k <= dpmax) ? c.ld(B_STEMO, dp0 + kTT + k + 2, g - 1) : (real)0;
-        dense_rows<1, COLS, ULO, 1>(tile + (dp0 - 5) * cols + t, cols, dp0, cv, w, ml);
+#if defined(__CUDA_ARCH__)
+        if constexpr (sizeof(real) == 4) dense_rows2<1, COLS, ULO, 1>(tile + (dp0 - 5) * cols + t, cols, dp0, cv, w, mp);
+        else
+#endif
+          dense_rows<1, COLS, ULO, 1>(tile + (dp0 - 5) * cols + t, cols, dp0, cv, w, ml);
       }
+#if defined(__CUDA_ARCH__)
+      if constexpr (sizeof(real) == 4) {
+#pragma unroll
+        for (int u = 0; u <= kMaxLoop / 2; ++u) {
+          float lo, hi;
+          unpack2(mp[u], lo, hi);
+          ml[2 * u] += lo;
+          if (2 * u + 1 <= kMaxLoop) ml[2 * u + 1] += hi;
+        }
+      }
+#endif
     }
     st.cnt = cnt;
   }
@@ -855,6 +945,11 @@ struct BiTile {
 #pragma unroll
       for (int k = 0; k < kTT; ++k)
         wn[k] = (delta + 5 + k <= dpmax) ? c.ld(B_STEMO, delta + 5 + k + 2, g2 - (delta + 5) - k - 1) : (real)0;
+#if defined(__CUDA_ARCH__)
+      unsigned long long mp[kMaxLoop / 2 + 1];
+#pragma unroll
+      for (int u = 0; u <= kMaxLoop / 2; ++u) mp[u] = 0;
+#endif
       for (int dp0 = delta + 5; dp0 <= dpmax; dp0 += kTT) {
         real w[kTT];
 #pragma unroll
@@ -862,8 +957,24 @@ struct BiTile {
 #pragma unroll
         for (int k = 0; k < kTT; ++k)
           wn[k] = (dp0 + kTT + k <= dpmax) ? c.ld(B_STEMO, dp0 + kTT + k + 2, g2 - dp0 - kTT - k - 1) : (real)0;
-        dense_rows<1, COLS, ULO, -1>(tile + (dp0 - 5) * cols + t + 31, cols, dp0, cv, w, mr);
+#if defined(__CUDA_ARCH__)
+        if constexpr (sizeof(real) == 4)
+          dense_rows2<1, COLS, ULO, -1>(tile + (dp0 - 5) * cols + t + 31, cols, dp0, cv, w, mp);
+        else
+#endif
+          dense_rows<1, COLS, ULO, -1>(tile + (dp0 - 5) * cols + t + 31, cols, dp0, cv, w, mr);
       }
+#if defined(__CUDA_ARCH__)
+      if constexpr (sizeof(real) == 4) {
+#pragma unroll
+        for (int u = 0; u <= kMaxLoop / 2; ++u) {
+          float lo, hi;
+          unpack2(mp[u], lo, hi);
+          mr[2 * u] += lo;
+          if (2 * u + 1 <= kMaxLoop) mr[2 * u + 1] += hi;
+        }
+      }
+#endif
     }
     st.cnt = cnt;
   }
