@@ -46,6 +46,23 @@ __device__ __forceinline__ void ffma2_bcast(unsigned long long &acc, float v, fl
 __device__ __forceinline__ void unpack2(unsigned long long p, float &lo, float &hi) {
   asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(p));
 }
+__device__ __forceinline__ unsigned long long pack2f(float lo, float hi) {
+  unsigned long long p;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(p) : "f"(lo), "f"(hi));
+  return p;
+}
+// (d0, d1) += (a0, a1) * (b0, b1) as one FFMA2
+__device__ __forceinline__ void fma2_into(float &d0, float &d1, float a0, float a1, float b0, float b1) {
+  unsigned long long acc = pack2f(d0, d1);
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(pack2f(a0, a1)), "l"(pack2f(b0, b1)));
+  unpack2(acc, d0, d1);
+}
+// (s0, s1) = (a0, a1) + (b, b) as one FADD2
+__device__ __forceinline__ void add2(float &s0, float &s1, float a0, float a1, float b) {
+  unsigned long long r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(pack2f(a0, a1)), "l"(pack2f(b, b)));
+  unpack2(r, s0, s1);
+}
 #endif
 
 // Called by the shallow steps right after their shared-memory / scratch stores: the CUDA kernels arrive at a
@@ -171,15 +188,31 @@ struct Tile {
           }
         }
       }
-#pragma unroll
-      for (int k = 0; k < kTT; ++k)
-        if (S + k >= 4 && S + k <= kMaxLoop) gs[k] += cf[S + k] * rs[k];
       // bulges of length u = S + k >= 4 out of the Alpha_stemB ring (same slot): inner cells (i + u, j) and (i, j - u)
       const real *rowB = row + kRingIn * (TCC > 0 ? TCC : TC);
       const real b0 = rowB[0];
+#if defined(__CUDA_ARCH__)
+      if constexpr (sizeof(real) == 4 && kTT == 4) {  // packed: targets in pairs, a target outside 4..30 gets factor 0
 #pragma unroll
-      for (int k = 0; k < kTT; ++k)
-        if (S + k >= 4 && S + k <= kMaxLoop) bs[k] += bu[S + k] * (rowB[S + k] + b0);
+        for (int k = 0; k < kTT; k += 2) {
+          const bool v0 = S + k >= 4 && S + k <= kMaxLoop, v1 = S + k + 1 >= 4 && S + k + 1 <= kMaxLoop;
+          if (v0 || v1) {
+            fma2_into(gs[k], gs[k + 1], rs[k], rs[k + 1], v0 ? cf[S + k] : 0.f, v1 ? cf[S + k + 1] : 0.f);
+            float t0, t1;
+            add2(t0, t1, v0 ? rowB[S + k] : 0.f, v1 ? rowB[S + k + 1] : 0.f, b0);
+            fma2_into(bs[k], bs[k + 1], t0, t1, v0 ? bu[S + k] : 0.f, v1 ? bu[S + k + 1] : 0.f);
+          }
+        }
+      } else
+#endif
+      {
+#pragma unroll
+        for (int k = 0; k < kTT; ++k)
+          if (S + k >= 4 && S + k <= kMaxLoop) gs[k] += cf[S + k] * rs[k];
+#pragma unroll
+        for (int k = 0; k < kTT; ++k)
+          if (S + k >= 4 && S + k <= kMaxLoop) bs[k] += bu[S + k] * (rowB[S + k] + b0);
+      }
     }
     if constexpr (S < kMaxLoop) in_rows<S + 1, TCC>(sm, TC, t, d0, cf, bu, g0, g1, g2, g3, g4, g5, g6, gs, bs);
   }
@@ -365,10 +398,26 @@ struct Tile {
       const real *rowB = sm.stemB + slot * (TCC > 0 ? TCC : TC) + t - 1;
       const real *rowO = sm.stemO + slot * (TCC > 0 ? TCC : TC) + t - 1;
       const real b0 = rowB[0];
+#if defined(__CUDA_ARCH__)
+      if constexpr (sizeof(real) == 4 && kTT == 4) {  // packed (see in_rows)
 #pragma unroll
-      for (int k = 0; k < kTT; ++k) {
-        const int u = S + k - 2;
-        if (u >= 2 && u <= kMaxLoop) o.bs[k] += bu[u] * (rowB[-u] + b0);
+        for (int k = 0; k < kTT; k += 2) {
+          const int u0 = S + k - 2, u1 = u0 + 1;
+          const bool v0 = u0 >= 2 && u0 <= kMaxLoop, v1 = u1 >= 2 && u1 <= kMaxLoop;
+          if (v0 || v1) {
+            float t0, t1;
+            add2(t0, t1, v0 ? rowB[-u0] : 0.f, v1 ? rowB[-u1] : 0.f, b0);
+            fma2_into(o.bs[k], o.bs[k + 1], t0, t1, v0 ? bu[u0] : 0.f, v1 ? bu[u1] : 0.f);
+          }
+        }
+      } else
+#endif
+      {
+#pragma unroll
+        for (int k = 0; k < kTT; ++k) {
+          const int u = S + k - 2;
+          if (u >= 2 && u <= kMaxLoop) o.bs[k] += bu[u] * (rowB[-u] + b0);
+        }
       }
       real rs[kTT];
 #pragma unroll
@@ -401,10 +450,22 @@ struct Tile {
           }
         }
       }
+#if defined(__CUDA_ARCH__)
+      if constexpr (sizeof(real) == 4 && kTT == 4) {
 #pragma unroll
-      for (int k = 0; k < kTT; ++k) {
-        const int sum = S + k - 2;
-        if (sum >= 4 && sum <= kMaxLoop) o.gs[k] += cf[sum] * rs[k];
+        for (int k = 0; k < kTT; k += 2) {
+          const int s0 = S + k - 2, s1 = s0 + 1;
+          const bool v0 = s0 >= 4 && s0 <= kMaxLoop, v1 = s1 >= 4 && s1 <= kMaxLoop;
+          if (v0 || v1) fma2_into(o.gs[k], o.gs[k + 1], rs[k], rs[k + 1], v0 ? cf[s0] : 0.f, v1 ? cf[s1] : 0.f);
+        }
+      } else
+#endif
+      {
+#pragma unroll
+        for (int k = 0; k < kTT; ++k) {
+          const int sum = S + k - 2;
+          if (sum >= 4 && sum <= kMaxLoop) o.gs[k] += cf[sum] * rs[k];
+        }
       }
     }
     if constexpr (S < kMaxLoop + 2) out_rows<S + 1, TCC>(sm, TC, t, d0, slot_d0, W, bu, cf, g0, g1, g2, g3, g4, g5, g6, o);
