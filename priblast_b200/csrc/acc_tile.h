@@ -493,16 +493,26 @@ struct Tile {
       const int shi = p >= 1 ? imin(L - p, W) - d0 : -1;
       const real *pa = scrBif + (long long)(d0 + 5 - (kTT - 1)) * TC + t;                  // bif row d0 + s
       const real *pb = c.arr[A_MULTI2] + (long long)(5 - (kTT - 1)) * nc + g + d0;          // row s, column q_0
+      {  // head: target k joins at s = 5 - k.  All operands are loaded first (one L2 latency instead of three).
+        real ha[kTT - 1], hb[kTT - 1][kTT];
 #pragma unroll
-      for (int s = 5 - (kTT - 1); s < 5; ++s) {  // head: target k joins at s = 5 - k
-        if (s <= shi) {
-          const real a = pa[0];
+        for (int h = 0; h < kTT - 1; ++h) {
+          const bool ok = 5 - (kTT - 1) + h <= shi;
+          ha[h] = ok ? pa[h * TC] : (real)0;
 #pragma unroll
           for (int k = 0; k < kTT; ++k)
-            if (s + k >= 5) o.bm1[k] += a * pb[(long long)k * (nc - 1)];
+            hb[h][k] = (ok && h + k >= kTT - 1) ? pb[(long long)h * nc + (long long)k * (nc - 1)] : (real)0;
         }
-        pa += TC;
-        pb += nc;
+#pragma unroll
+        for (int h = 0; h < kTT - 1; ++h) {
+          if (5 - (kTT - 1) + h <= shi) {
+#pragma unroll
+            for (int k = 0; k < kTT; ++k)
+              if (h + k >= kTT - 1) o.bm1[k] += ha[h] * hb[h][k];
+          }
+        }
+        pa += (kTT - 1) * TC;
+        pb += (long long)(kTT - 1) * nc;
       }
       int s = 5;
       for (; s + 1 <= shi; s += 2) {  // two rows per round, 10 independent loads in flight
@@ -554,16 +564,24 @@ struct Tile {
         for (int k = 0; k < kTT; ++k) o.ks[k] += pa[-k * TC] * b;
       }
       // tail: m = W - d0 + e, e = 1 .. kTT-1, exists only for the targets with k >= e
-      if (p >= 1) {
+      {  // (all operands loaded first: one L2 latency instead of three)
+        real tb[kTT - 1], tq[kTT - 1][kTT];
 #pragma unroll
         for (int e = 1; e < kTT; ++e) {
           const int mm = W - d0 + e;
-          if (mm >= 5 && mm <= p) {
-            const real *qa = scrBif + (long long)(d0 + mm) * TC + t - mm;
-            const real b = c.arr[A_MULTI1][(long long)mm * (nc - 1) + g];
+          const bool ok = p >= 1 && mm >= 5 && mm <= p;
+          tb[e - 1] = ok ? c.arr[A_MULTI1][(long long)mm * (nc - 1) + g] : (real)0;
+#pragma unroll
+          for (int k = 0; k < kTT; ++k)
+            tq[e - 1][k] = (ok && k >= e) ? scrBif[(long long)(d0 + mm - k) * TC + t - mm] : (real)0;
+        }
+#pragma unroll
+        for (int e = 1; e < kTT; ++e) {
+          const int mm = W - d0 + e;
+          if (p >= 1 && mm >= 5 && mm <= p) {
 #pragma unroll
             for (int k = 0; k < kTT; ++k)
-              if (k >= e) o.ks[k] += qa[-k * TC] * b;
+              if (k >= e) o.ks[k] += tq[e - 1][k] * tb[e - 1];
           }
         }
       }
