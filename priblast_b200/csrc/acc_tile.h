@@ -257,13 +257,24 @@ struct Tile {
         pa += 2 * TC;
         pb -= 2 * (TC - 1);
       }
-      for (; m <= d0 + kTT - 1 - 5; ++m) {  // tail: targets drop out one by one (rows below 5 do not exist)
-        const real a = pa[0];
+      {  // tail (<= kTT rows): targets drop out one by one (rows below 5 do not exist).  All operands are loaded
+         // first: one L2 latency instead of one per row.
+        real ta[kTT], tb[kTT][kTT];
 #pragma unroll
-        for (int k = 0; k < kTT; ++k)
-          if (m <= d0 + k - 5) mb[k] += a * pb[k * TC];
-        pa += TC;
-        pb -= TC - 1;
+        for (int j = 0; j < kTT; ++j) {
+          const bool ok = m + j <= d0 + kTT - 1 - 5;
+          ta[j] = ok ? pa[j * TC] : (real)0;
+#pragma unroll
+          for (int k = 0; k < kTT; ++k) tb[j][k] = (ok && m + j <= d0 + k - 5) ? pb[k * TC - j * (TC - 1)] : (real)0;
+        }
+#pragma unroll
+        for (int j = 0; j < kTT; ++j) {
+          if (m + j <= d0 + kTT - 1 - 5) {
+#pragma unroll
+            for (int k = 0; k < kTT; ++k)
+              if (m + j <= d0 + k - 5) mb[k] += ta[j] * tb[j][k];
+          }
+        }
       }
     }
   }
