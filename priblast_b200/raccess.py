@@ -13,7 +13,8 @@ from __future__ import annotations
 
 import ctypes
 import os
-from typing import Iterable, Sequence
+from collections.abc import Sequence
+from typing import Iterable
 
 import numpy as np
 
@@ -35,6 +36,27 @@ def packed_layout(lens: Sequence[int]):
     if len(lens):
         base[1:] = np.cumsum(2 * lens)[:-1]
     return base, base + lens, int((2 * lens).sum())
+
+
+class AccResults(Sequence):
+    """[(acc, cond), ...] as views into the one packed output buffer, made on demand (building thousands of numpy
+    views eagerly costs more than the device-to-host copy of their data)."""
+
+    def __init__(self, out, acc_off, cond_off, lens):
+        self.out, self._a, self._c, self._l = out, acc_off, cond_off, lens
+
+    def __len__(self):
+        return len(self._l)
+
+    def __getitem__(self, k):
+        if isinstance(k, slice):
+            return [self[i] for i in range(*k.indices(len(self)))]
+        if k < 0:
+            k += len(self)
+        if not 0 <= k < len(self):
+            raise IndexError(k)
+        a, c, l = int(self._a[k]), int(self._c[k]), int(self._l[k])
+        return self.out[a:a + l], self.out[c:c + l]
 
 
 class Raccess:
@@ -125,7 +147,7 @@ class Raccess:
                                            out.ctypes.data_as(ctypes.c_void_p),
                                            acc_off.ctypes.data_as(_capi.c_i64p),
                                            cond_off.ctypes.data_as(_capi.c_i64p)))
-        return [(out[a:a + l], out[c:c + l]) for a, c, l in zip(acc_off, cond_off, lens)]
+        return AccResults(out, acc_off, cond_off, lens)
 
     # -- split form: inputs resident on the device ---------------------------------------------------
     def stage(self, seqs: Iterable) -> int:
@@ -148,7 +170,7 @@ class Raccess:
         _capi.check(self._lib.prib_acc_fetch(self._ctx, out.ctypes.data_as(ctypes.c_void_p),
                                              acc_off.ctypes.data_as(_capi.c_i64p),
                                              cond_off.ctypes.data_as(_capi.c_i64p)))
-        return [(out[a:a + l], out[c:c + l]) for a, c, l in zip(acc_off, cond_off, lens)]
+        return AccResults(out, acc_off, cond_off, lens)
 
     def set_stream(self, cuda_stream_handle: int | None) -> None:
         _capi.check(self._lib.prib_acc_set_stream(self._ctx, ctypes.c_void_p(cuda_stream_handle or 0)))
