@@ -80,9 +80,13 @@ def load() -> ctypes.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    path = _build.LIB
-    if not os.path.exists(path):
-        _build.build_library()
+    path = os.environ.get("PRIB_ACC_LIB")  # experiment builds (profiles/build_variants.py); never set in production
+    if not path:
+        path = _build.LIB
+        # rebuilds when a source is newer than the library (returns at once otherwise); on a box without nvcc a
+        # stale library is an error, not something to load silently
+        if _build.is_stale():
+            _build.build_library()
     lib = ctypes.CDLL(path)
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)  # AttributeError if the symbol is not exported

@@ -36,7 +36,13 @@ constexpr int kScanWarps = 4;
 constexpr int kFp32MaxSpan = kMaxSpan;  // always try FP32 first: at W = 150 a quarter of random 2 kb sequences
                                          // is flagged and re-run in FP64, still 1.7x faster than FP64 for all (profiles/r1/sweep.json)
 // widest CTA of the tile kernels per precision (227 KB of rings / 80 rows): bounds the register budget
-template <typename real> struct TileMaxThreads { static constexpr int value = sizeof(real) == 4 ? 704 : 320; };
+#ifndef PRIB_TC32
+#define PRIB_TC32 704
+#endif
+#ifndef PRIB_TC64
+#define PRIB_TC64 320
+#endif
+template <typename real> struct TileMaxThreads { static constexpr int value = sizeof(real) == 4 ? PRIB_TC32 : PRIB_TC64; };
 
 // ---------------------------------------------------------------------------------------------
 // kernels
@@ -75,6 +81,50 @@ struct StepArrive {  // the hook of Tile::inside_shallow / outside_shallow
   __device__ __forceinline__ void operator()() const { *state = mbar_arrive(bar); }
 };
 
+// The kTT shallow steps of one group, each followed (between its barrier arrive and wait) by one chunk of the NEXT
+// group's deep sums (acc_tile.h, "software pipelining across groups").
+template <typename real, int K>
+__device__ __forceinline__ void inside_group_steps(const typename Core<real>::Ctx &c,
+                                                   const typename Core<real>::SmallTables &T,
+                                                   const typename Tile<real>::Geo &ge,
+                                                   const typename Tile<real>::InSmem &sm, real *scrM1, real *scrM2, int t,
+                                                   const typename Tile<real>::ColState &cs, int d0, bool more,
+                                                   const typename Tile<real>::InDeep &cur,
+                                                   typename Tile<real>::InDeep &nxt, unsigned long long *step_bar) {
+  typedef Tile<real> TL;
+  constexpr int TC = TileMaxThreads<real>::value;
+  const bool live = d0 + K >= kTurn;  // uniform
+  unsigned long long phase = 0;
+  if (live)
+    TL::template inside_shallow<TC>(c, T, ge, sm, scrM1, scrM2, t, cs, d0 + K, cur.gs[K], cur.mb[K], cur.bs[K],
+                                    StepArrive{step_bar, &phase});
+  if (more) TL::template inside_deep_chunk<K, TC>(T, ge, sm, scrM1, scrM2, t, d0 + kTT, nxt);
+  if (live) mbar_wait(step_bar, phase);
+  if constexpr (K + 1 < kTT) inside_group_steps<real, K + 1>(c, T, ge, sm, scrM1, scrM2, t, cs, d0, more, cur, nxt, step_bar);
+}
+
+template <typename real, int K>
+__device__ __forceinline__ void outside_group_steps(const typename Core<real>::Ctx &c,
+                                                    const typename Core<real>::SmallTables &T,
+                                                    const typename Tile<real>::Geo &ge,
+                                                    const typename Tile<real>::OutSmem &sm, real *scrBif, int t,
+                                                    const typename Tile<real>::ColState &cs, int d0, int slot_d0,
+                                                    bool more, const typename Tile<real>::OutDeep &cur,
+                                                    typename Tile<real>::OutDeep &nxt, unsigned long long *step_bar) {
+  typedef Tile<real> TL;
+  constexpr int TC = TileMaxThreads<real>::value;
+  const bool live = d0 - K >= kTurn;  // uniform
+  unsigned long long phase = 0;
+  if (live)
+    TL::template outside_shallow<TC>(c, T, ge, sm, scrBif, t, cs, d0 - K, TL::wrap_out(slot_d0 + kRingOut - K), cur.gs[K],
+                                     cur.bs[K], cur.bm1[K], cur.ks[K], StepArrive{step_bar, &phase});
+  if (more)
+    TL::template outside_deep_chunk<K, TC>(c, T, ge, sm, scrBif, t, cs, d0 - kTT, TL::wrap_out(slot_d0 + kRingOut - kTT), nxt);
+  if (live) mbar_wait(step_bar, phase);
+  if constexpr (K + 1 < kTT)
+    outside_group_steps<real, K + 1>(c, T, ge, sm, scrBif, t, cs, d0, slot_d0, more, cur, nxt, step_bar);
+}
+
 template <typename real>
 __global__ void __launch_bounds__(TileMaxThreads<real>::value, 1)
 k_inside_tile(typename Core<real>::Ctx c, int TX, long long ntiles, real *scratch) {
@@ -108,18 +158,13 @@ k_inside_tile(typename Core<real>::Ctx c, int TX, long long ntiles, real *scratc
     typename TL::ColState cs;
     TL::col_state(c, ge.g0 + t, cs);
     __syncthreads();
+    typename TL::InDeep cur, nxt;
+    TL::clear(cur);
     for (int d0 = dfirst; d0 <= W + 1; d0 += kTT) {
-      real gs[kTT], mb[kTT], bs[kTT];
-      TL::template inside_deep<TC>(T, ge, sm, scrM1, scrM2, t, d0, gs, mb, bs);
-#pragma unroll
-      for (int k = 0; k < kTT; ++k) {
-        if (d0 + k >= kTurn) {  // uniform
-          unsigned long long phase;
-          TL::template inside_shallow<TC>(c, T, ge, sm, scrM1, scrM2, t, cs, d0 + k, gs[k], mb[k], bs[k],
-                                          StepArrive{&step_bar, &phase});
-          mbar_wait(&step_bar, phase);
-        }
-      }
+      TL::template inside_deep_tail<TC>(T, ge, sm, scrM1, scrM2, t, d0, cur);
+      TL::clear(nxt);
+      inside_group_steps<real, 0>(c, T, ge, sm, scrM1, scrM2, t, cs, d0, d0 + kTT <= W + 1, cur, nxt, &step_bar);
+      cur = nxt;
     }
   }
 }
@@ -161,19 +206,14 @@ k_outside_tile(typename Core<real>::Ctx c, int TX, long long ntiles, real *scrat
     TL::col_state(c, ge.g0 - ge.H + t, cs);
     __syncthreads();
     int slot = (W + 1) % kRingOut;
+    typename TL::OutDeep cur, nxt;
+    TL::clear(cur);
     for (int d0 = W + 1; d0 >= dlast + kTT - 1; d0 -= kTT) {
-      typename TL::OutDeep o;
-      TL::template outside_deep<TC>(c, T, ge, sm, scrBif, t, cs, d0, slot, o);
-#pragma unroll
-      for (int k = 0; k < kTT; ++k) {
-        if (d0 - k >= kTurn) {  // uniform
-          unsigned long long phase;
-          TL::template outside_shallow<TC>(c, T, ge, sm, scrBif, t, cs, d0 - k, slot, o.gs[k], o.bs[k], o.bm1[k],
-                                           o.ks[k], StepArrive{&step_bar, &phase});
-          mbar_wait(&step_bar, phase);
-        }
-        slot = slot == 0 ? kRingOut - 1 : slot - 1;
-      }
+      TL::template outside_deep_tail<TC>(c, T, ge, sm, scrBif, t, cs, d0, slot, cur);
+      TL::clear(nxt);
+      outside_group_steps<real, 0>(c, T, ge, sm, scrBif, t, cs, d0, slot, d0 - kTT >= dlast + kTT - 1, cur, nxt, &step_bar);
+      cur = nxt;
+      slot = TL::wrap_out(slot + kRingOut - kTT);
     }
   }
 }

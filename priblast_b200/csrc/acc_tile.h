@@ -13,10 +13,19 @@
 // shared-memory load instead of one), then kTT "shallow" steps finish the cells span by span (stack,
 // 1-nt bulges, 1x1/1x2/2x1/2x2 loops, multiloop bookkeeping) with a __syncthreads in between.
 //
+// Software pipelining across groups.  A deep sum of the NEXT group only needs rows that are >= 5 spans away
+// from that group's first span — rows that are complete before the CURRENT group's shallow steps start.  So
+// the deep work of group n + 1 is cut into kTT "chunks" (source rows 5.., the middle of the multibranch
+// sums) that run between the barrier arrive and the barrier wait of the shallow steps of group n: the
+// latency-bound shallow steps (table gathers, ring round trips, barrier skew) overlap with the issue-bound
+// stencil work of other warps instead of idling the SM.  What is left for the start of a group (the "tail":
+// source rows 1..4 and the few multibranch terms that touch the previous group's rows) is small.
+//
 // The functions below are the per-thread bodies (thread t = local column t of the tile); the CUDA kernels
-// and the host emulation (tests/hostemu) both call them.  The order of additions inside a cell is
-// identical to acc_core.h's one-cell-at-a-time functions, so both give the same bits in the same
-// precision (checked by tests/test_hostemu.py).
+// and the host emulation (tests/hostemu) both call them in the same schedule.  Per cell the SET of terms is
+// the one of acc_core.h's one-cell-at-a-time functions; the order of additions differs (far rows first), so
+// the two agree to rounding, not bit for bit (tests/test_hostemu.py).  The order depends on the span only,
+// hence results do not depend on tile width, batch composition or the number of GPUs.
 #pragma once
 #include "acc_core.h"
 
@@ -150,7 +159,7 @@ struct Tile {
   // One source row of the inside stencils (row d0 - S of the Alpha_stemI / Alpha_stemB rings) for all kTT targets;
   // S is a template parameter so that every coefficient choice and column offset is resolved at compile
   // time (a plain `#pragma unroll` nest of this size is not unrolled by nvcc).
-  template <int S, int TCC>
+  template <int S, int SEND, int TCC>
   static PRIB_HD void in_rows(const InSmem &sm, int TC, int t, int d0, const real *cf, const real *bu, real g0, real g1,
                               real g2, real g3, real g4, real g5, real g6, real (&gs)[kTT], real (&bs)[kTT]) {
     if (d0 - S >= 5) {  // rows below span 5 hold no stems; same cut as `sum <= min(30, d - 5)` per target
@@ -214,69 +223,130 @@ struct Tile {
           if (S + k >= 4 && S + k <= kMaxLoop) bs[k] += bu[S + k] * (rowB[S + k] + b0);
       }
     }
-    if constexpr (S < kMaxLoop) in_rows<S + 1, TCC>(sm, TC, t, d0, cf, bu, g0, g1, g2, g3, g4, g5, g6, gs, bs);
+    if constexpr (S < SEND) in_rows<S + 1, SEND, TCC>(sm, TC, t, d0, cf, bu, g0, g1, g2, g3, g4, g5, g6, gs, bs);
   }
 
   // ---------------------------------------------------------------------------------------------
-  // inside, deep step: thread t = local column t; targets are the cells (i, i + d0 + k), k = 0..kTT-1.
+  // inside, deep sums: thread t = local column t; targets are the cells (i, i + d0 + k), k = 0..kTT-1.
   //   gs[k] = generic interior loops of Alpha_stemend (raccess.cpp:201-215, 808-812) as a stencil over the
   //           Alpha_stemI ring: source row d0 - s serves target k with loop size s + k;
   //   bs[k] = bulges of length >= 4 (:788-795) over the Alpha_stemB ring, same rows;
   //   mb[k] = Alpha_multibif (:131-143) from the per-CTA scratch rows scrM1 / scrM2 ([(W+4)][TC]).
   // Only rows <= d0 - 1 are read, so all kTT targets are legal at once.  TCC: compile-time tile width
   // (0 = ge.TC at run time, host emulation): every ring row offset becomes an immediate.
+  //
+  // The work is split for the software pipeline (see the top of the file):
+  //   inside_deep_chunk<C>: source rows S >= 5 (rows <= d0 - 5) in kTT chunks and the multibif terms whose two
+  //                         operands both lie in rows <= d0 - 5 (m = 8 .. d0 - 5); legal while the PREVIOUS
+  //                         group's shallow steps are still running;
+  //   inside_deep_tail:     source rows S = 1..4 and the multibif terms m = 5..7 and m >= d0 - 4, which read rows
+  //                         of the previous group; runs at the start of the group.
   // ---------------------------------------------------------------------------------------------
-  template <int TCC = 0>
-  static PRIB_HD void inside_deep(const ST &T, const Geo &ge, const InSmem &sm, const real *scrM1, const real *scrM2,
-                                  int t, int d0, real (&gs)[kTT], real (&mb)[kTT], real (&bs)[kTT]) {
+  struct InDeep {
+    real gs[kTT], mb[kTT], bs[kTT];
+  };
+  static PRIB_HD void clear(InDeep &a) {
+#pragma unroll
+    for (int k = 0; k < kTT; ++k) a.gs[k] = a.mb[k] = a.bs[k] = 0;
+  }
+  // source rows of chunk C: balanced by loads (S + 7 per row)
+  static PRIB_HD constexpr int in_chunk_lo(int C) { return C == 0 ? 5 : C == 1 ? 15 : C == 2 ? 21 : 26; }
+  static PRIB_HD constexpr int in_chunk_hi(int C) { return C == 0 ? 14 : C == 1 ? 20 : C == 2 ? 25 : kMaxLoop; }
+  enum { kBifEdge = 8 };  // multibif terms m < kBifEdge belong to the tail (their multi2 row may be of the previous group)
+
+  // mb[k] += sum over m = mlo..mhi of multi1[m][t] * multi2[d0 + k - m][t + m] for all kTT targets; the caller
+  // guarantees 5 <= mlo and mhi <= d0 - 5, so every operand exists.  A multi1 element serves all targets; two
+  // running pointers, every other offset is an immediate.
+  static PRIB_HD void in_bif_range(const real *scrM1, const real *scrM2, int TC, int t, int d0, int mlo, int mhi,
+                                   real (&mb)[kTT]) {
+    if (mlo > mhi) return;
+    const real *pa = scrM1 + mlo * TC + t;                       // multi1[m][t]
+    const real *pb = scrM2 + (long long)(d0 - mlo) * TC + t + mlo;  // multi2[d0 - m][t + m]; target k: pb[k * TC]
+    int m = mlo;
+    for (; m + 1 <= mhi; m += 2) {  // two m per round, 10 independent loads in flight
+      const real a0 = pa[0], a1 = pa[TC];
+      real b0[kTT], b1[kTT];
+#pragma unroll
+      for (int k = 0; k < kTT; ++k) {
+        b0[k] = pb[k * TC];
+        b1[k] = pb[k * TC - (TC - 1)];
+      }
+#pragma unroll
+      for (int k = 0; k < kTT; ++k) {
+        mb[k] += a0 * b0[k];
+        mb[k] += a1 * b1[k];
+      }
+      pa += 2 * TC;
+      pb -= 2 * (TC - 1);
+    }
+    if (m <= mhi) {
+      const real a0 = pa[0];
+      real b0[kTT];
+#pragma unroll
+      for (int k = 0; k < kTT; ++k) b0[k] = pb[k * TC];
+#pragma unroll
+      for (int k = 0; k < kTT; ++k) mb[k] += a0 * b0[k];
+    }
+  }
+
+  // multibif terms next to the two ends of the m range: (a) m = 5 .. kBifEdge - 1, (b) m = d0 - 4 .. d0 + kTT - 6
+  // (not below kBifEdge); target k takes m while m <= d0 + k - 5.  All operands are loaded first: one L2 latency.
+  static PRIB_HD void in_bif_edges(const real *scrM1, const real *scrM2, int TC, int t, int d0, real (&mb)[kTT]) {
+    constexpr int NA = kBifEdge - 5, NB = kTT - 1;
+    real ea[NA], eb[NA][kTT], ta[NB], tb[NB][kTT];
+#pragma unroll
+    for (int j = 0; j < NA; ++j) {
+      const int m = 5 + j;
+      ea[j] = (m <= d0 + kTT - 1 - 5) ? scrM1[m * TC + t] : (real)0;
+#pragma unroll
+      for (int k = 0; k < kTT; ++k) eb[j][k] = (m <= d0 + k - 5) ? scrM2[(long long)(d0 + k - m) * TC + t + m] : (real)0;
+    }
+#pragma unroll
+    for (int j = 0; j < NB; ++j) {
+      const int m = d0 - 4 + j;  // <= d0 + k - 5  <=>  k >= j + 1
+      const bool ok = m >= kBifEdge;
+      ta[j] = ok ? scrM1[m * TC + t] : (real)0;
+#pragma unroll
+      for (int k = 0; k < kTT; ++k) tb[j][k] = (ok && k >= j + 1) ? scrM2[(long long)(d0 + k - m) * TC + t + m] : (real)0;
+    }
+#pragma unroll
+    for (int j = 0; j < NA; ++j) {
+#pragma unroll
+      for (int k = 0; k < kTT; ++k)
+        if (5 + j <= d0 + k - 5) mb[k] += ea[j] * eb[j][k];
+    }
+#pragma unroll
+    for (int j = 0; j < NB; ++j) {
+      if (d0 - 4 + j >= kBifEdge) {
+#pragma unroll
+        for (int k = 0; k < kTT; ++k)
+          if (k >= j + 1) mb[k] += ta[j] * tb[j][k];
+      }
+    }
+  }
+
+  template <int C, int TCC = 0>
+  static PRIB_HD void inside_deep_chunk(const ST &T, const Geo &ge, const InSmem &sm, const real *scrM1,
+                                        const real *scrM2, int t, int d0, InDeep &a) {
     const int TC = TCC > 0 ? TCC : ge.TC;
     const real *cf = K::cf_tab(T), *bu = K::bulge_tab(T);
     const real g0 = T.cg[0], g1 = T.cg[1], g2 = T.cg[2], g3 = T.cg[3], g4 = T.cg[4], g5 = T.cg[5], g6 = T.cg[6];
-#pragma unroll
-    for (int k = 0; k < kTT; ++k) gs[k] = mb[k] = bs[k] = 0;
-    in_rows<1, TCC>(sm, TC, t, d0, cf, bu, g0, g1, g2, g3, g4, g5, g6, gs, bs);
-    // multibif: mb[k] = sum over m = 5 .. d0+k-5 of multi1[m][t] * multi2[d0+k-m][t+m]; a multi1 element
-    // serves all kTT targets.  Two running pointers, every other offset is an immediate.
-    {
-      const real *pa = scrM1 + 5 * TC + t;                       // multi1[m][t]
-      const real *pb = scrM2 + (long long)(d0 - 5) * TC + t + 5;  // multi2[d0 - m][t + m]; target k: pb[k * TC]
-      int m = 5;
-      for (; m + 1 <= d0 - 5; m += 2) {  // two m per round, 10 independent loads in flight
-        const real a0 = pa[0], a1 = pa[TC];
-        real b0[kTT], b1[kTT];
-#pragma unroll
-        for (int k = 0; k < kTT; ++k) {
-          b0[k] = pb[k * TC];
-          b1[k] = pb[k * TC - (TC - 1)];
-        }
-#pragma unroll
-        for (int k = 0; k < kTT; ++k) {
-          mb[k] += a0 * b0[k];
-          mb[k] += a1 * b1[k];
-        }
-        pa += 2 * TC;
-        pb -= 2 * (TC - 1);
-      }
-      {  // tail (<= kTT rows): targets drop out one by one (rows below 5 do not exist).  All operands are loaded
-         // first: one L2 latency instead of one per row.
-        real ta[kTT], tb[kTT][kTT];
-#pragma unroll
-        for (int j = 0; j < kTT; ++j) {
-          const bool ok = m + j <= d0 + kTT - 1 - 5;
-          ta[j] = ok ? pa[j * TC] : (real)0;
-#pragma unroll
-          for (int k = 0; k < kTT; ++k) tb[j][k] = (ok && m + j <= d0 + k - 5) ? pb[k * TC - j * (TC - 1)] : (real)0;
-        }
-#pragma unroll
-        for (int j = 0; j < kTT; ++j) {
-          if (m + j <= d0 + kTT - 1 - 5) {
-#pragma unroll
-            for (int k = 0; k < kTT; ++k)
-              if (m + j <= d0 + k - 5) mb[k] += ta[j] * tb[j][k];
-          }
-        }
-      }
+    {  // this chunk's quarter of the multibif terms m = kBifEdge .. d0 - 5 (first: their L2 latency is covered
+       // by the stencil rows of the other warps)
+      const int n = d0 - 5 - kBifEdge + 1, q = (n + kTT - 1) / kTT;
+      if (n > 0) in_bif_range(scrM1, scrM2, TC, t, d0, kBifEdge + C * q, imin(kBifEdge + (C + 1) * q - 1, d0 - 5), a.mb);
     }
+    in_rows<in_chunk_lo(C), in_chunk_hi(C), TCC>(sm, TC, t, d0, cf, bu, g0, g1, g2, g3, g4, g5, g6, a.gs, a.bs);
+  }
+
+  template <int TCC = 0>
+  static PRIB_HD void inside_deep_tail(const ST &T, const Geo &ge, const InSmem &sm, const real *scrM1,
+                                       const real *scrM2, int t, int d0, InDeep &a) {
+    const int TC = TCC > 0 ? TCC : ge.TC;
+    const real *cf = K::cf_tab(T), *bu = K::bulge_tab(T);
+    const real g0 = T.cg[0], g1 = T.cg[1], g2 = T.cg[2], g3 = T.cg[3], g4 = T.cg[4], g5 = T.cg[5], g6 = T.cg[6];
+    in_bif_edges(scrM1, scrM2, TC, t, d0, a.mb);
+    in_rows<1, 4, TCC>(sm, TC, t, d0, cf, bu, g0, g1, g2, g3, g4, g5, g6, a.gs, a.bs);
   }
 
   // ---------------------------------------------------------------------------------------------
@@ -400,7 +470,7 @@ struct Tile {
   };
 
   // One source row (d0 + S of the Beta_stemO / Beta_stemB rings) of the outside stencils for all kTT targets.
-  template <int S, int TCC>
+  template <int S, int SEND, int TCC>
   static PRIB_HD void out_rows(const OutSmem &sm, int TC, int t, int d0, int slot_d0, int W, const real *bu,
                                const real *cf, real g0, real g1, real g2, real g3, real g4, real g5, real g6,
                                OutDeep &o) {
@@ -479,122 +549,188 @@ struct Tile {
         }
       }
     }
-    if constexpr (S < kMaxLoop + 2) out_rows<S + 1, TCC>(sm, TC, t, d0, slot_d0, W, bu, cf, g0, g1, g2, g3, g4, g5, g6, o);
+    if constexpr (S < SEND) out_rows<S + 1, SEND, TCC>(sm, TC, t, d0, slot_d0, W, bu, cf, g0, g1, g2, g3, g4, g5, g6, o);
   }
 
-  template <int TCC = 0>
-  static PRIB_HD void outside_deep(const Ctx &c, const ST &T, const Geo &ge, const OutSmem &sm, const real *scrBif,
-                                   int t, const ColState &cs, int d0, int slot_d0 /* = d0 % kRingOut */, OutDeep &o) {
+  static PRIB_HD void clear(OutDeep &o) {
+#pragma unroll
+    for (int k = 0; k < kTT; ++k) o.gs[k] = o.bs[k] = o.bm1[k] = o.ks[k] = 0;
+  }
+  // Split of the deep sums of group d0 (targets d0 - k) for the software pipeline (see the top of the file):
+  //   outside_deep_chunk<C>: source rows S >= 5 (rows >= d0 + 5) in kTT chunks, Beta_multi1 terms s >= 5 and the
+  //                          k-loop terms m >= kBifEdge of Beta_multi2 — every bif row they read is >= d0 + 5, i.e.
+  //                          complete before the PREVIOUS group's shallow steps start;
+  //   outside_deep_tail:     source rows S = 1..4, the head of Beta_multi1 (s = 2..4), the k-loop terms m = 5..7 and
+  //                          m > W - d0, which read rows of the previous group; runs at the start of the group.
+  static PRIB_HD constexpr int out_chunk_lo(int C) { return C == 0 ? 5 : C == 1 ? 15 : C == 2 ? 22 : 28; }
+  static PRIB_HD constexpr int out_chunk_hi(int C) { return C == 0 ? 14 : C == 1 ? 21 : C == 2 ? 27 : kMaxLoop + 2; }
+
+  // Multiloop sums.  Only cells strictly inside the sequence (p >= 1, q < L) use them (outside_shallow
+  // ignores the sums of all others), and for those the term ranges of the kTT targets line up:
+  //   bm1[k]: m = 5 .. min(L - q_k, W - d_k)  <=>  bif row d0 + s with s = m - k = 5 - k .. min(L - p, W) - d0
+  //   ks[k] : m = 5 .. min(p, W - d_k)
+  // so the loops run on common bounds and every load stays inside the sequence / the scratch rows.
+
+  // bm1[k] += sum over s = slo..shi of bif[d0 + s][t] * Alpha_multi2[s + k][g + d0 - k] (slo >= 5: all targets take
+  // every s); a bif element serves all targets
+  static PRIB_HD void out_bm1_range(const Ctx &c, const real *scrBif, int TC, int t, long long g, int d0, int slo,
+                                    int shi, real (&bm1)[kTT]) {
+    if (slo > shi) return;
+    const long long nc = c.NC;
+    const real *pa = scrBif + (long long)(d0 + slo) * TC + t;      // bif row d0 + s
+    const real *pb = c.arr[A_MULTI2] + (long long)slo * nc + g + d0;  // row s, column q_0; target k: pb[k * (nc - 1)]
+    int s = slo;
+    for (; s + 1 <= shi; s += 2) {  // two rows per round, 10 independent loads in flight
+      const real a0 = pa[0], a1 = pa[TC];
+      real b0[kTT], b1[kTT];
+#pragma unroll
+      for (int k = 0; k < kTT; ++k) {
+        b0[k] = pb[(long long)k * (nc - 1)];
+        b1[k] = pb[(long long)k * (nc - 1) + nc];
+      }
+#pragma unroll
+      for (int k = 0; k < kTT; ++k) {
+        bm1[k] += a0 * b0[k];
+        bm1[k] += a1 * b1[k];
+      }
+      pa += 2 * TC;
+      pb += 2 * nc;
+    }
+    if (s <= shi) {
+      const real a = pa[0];
+      real b0[kTT];
+#pragma unroll
+      for (int k = 0; k < kTT; ++k) b0[k] = pb[(long long)k * (nc - 1)];
+#pragma unroll
+      for (int k = 0; k < kTT; ++k) bm1[k] += a * b0[k];
+    }
+  }
+
+  // ks[k] += sum over m = mlo..mhi of bif[d0 - k + m][t - m] * Alpha_multi1[m][g - m]; an Alpha element serves all
+  // targets (the caller guarantees mhi <= W - d0: all targets take every m)
+  static PRIB_HD void out_ks_range(const Ctx &c, const real *scrBif, int TC, int t, long long g, int d0, int mlo,
+                                   int mhi, real (&ks)[kTT]) {
+    if (mlo > mhi) return;
+    const long long nc = c.NC;
+    const real *pa = scrBif + (long long)(d0 + mlo) * TC + t - mlo;  // bif[d0 + m][t - m]; target k: pa[-k * TC]
+    const real *pb = c.arr[A_MULTI1] + (long long)mlo * (nc - 1) + g;  // Alpha_multi1[m][g - m]
+    int m = mlo;
+    for (; m + 1 <= mhi; m += 2) {
+      const real b0 = pb[0], b1 = pb[nc - 1];
+      real a0[kTT], a1[kTT];
+#pragma unroll
+      for (int k = 0; k < kTT; ++k) {
+        a0[k] = pa[-k * TC];
+        a1[k] = pa[-k * TC + (TC - 1)];
+      }
+#pragma unroll
+      for (int k = 0; k < kTT; ++k) {
+        ks[k] += a0[k] * b0;
+        ks[k] += a1[k] * b1;
+      }
+      pa += 2 * (TC - 1);
+      pb += 2 * (nc - 1);
+    }
+    if (m <= mhi) {
+      const real b = pb[0];
+      real a0[kTT];
+#pragma unroll
+      for (int k = 0; k < kTT; ++k) a0[k] = pa[-k * TC];
+#pragma unroll
+      for (int k = 0; k < kTT; ++k) ks[k] += a0[k] * b;
+    }
+  }
+
+  template <int C, int TCC = 0>
+  static PRIB_HD void outside_deep_chunk(const Ctx &c, const ST &T, const Geo &ge, const OutSmem &sm,
+                                         const real *scrBif, int t, const ColState &cs, int d0,
+                                         int slot_d0 /* = d0 % kRingOut */, OutDeep &o) {
     const int TC = TCC > 0 ? TCC : ge.TC, W = c.W;
     const real *bu = K::bulge_tab(T), *cf = K::cf_tab(T);
     const real g0 = T.cg[0], g1 = T.cg[1], g2 = T.cg[2], g3 = T.cg[3], g4 = T.cg[4], g5 = T.cg[5], g6 = T.cg[6];
-#pragma unroll
-    for (int k = 0; k < kTT; ++k) o.gs[k] = o.bs[k] = o.bm1[k] = o.ks[k] = 0;
-    // stencils: source row d0 + s; target k: bulge length / loop size s + k - 2
-    out_rows<1, TCC>(sm, TC, t, d0, slot_d0, W, bu, cf, g0, g1, g2, g3, g4, g5, g6, o);
-    // Multiloop sums.  Only cells strictly inside the sequence (p >= 1, q < L) use them (outside_shallow
-    // ignores the sums of all others), and for those the term ranges of the kTT targets line up:
-    //   bm1[k]: m = 5 .. min(L - q_k, W - d_k)  <=>  bif row d0 + s with s = m - k = 5 - k .. min(L - p, W) - d0
-    //   ks[k] : m = 5 .. min(p, W - d_k)
-    // so the loops run on common bounds and every load stays inside the sequence / the scratch rows.
+    const long long g = ge.g0 - ge.H + t;
+    const int L = cs.L, p = cs.i;
+    {  // this chunk's quarter of the multiloop terms (first: their L2 latency is covered by the stencil rows of
+       // the other warps)
+      const int shi = p >= 1 ? imin(L - p, W) - d0 : -1;
+      const int n1 = W - d0 - 4, q1 = (n1 + kTT - 1) / kTT;  // s = 5 .. W - d0, uniform split
+      if (n1 > 0) out_bm1_range(c, scrBif, TC, t, g, d0, 5 + C * q1, imin(5 + (C + 1) * q1 - 1, shi), o.bm1);
+      const int mhi = p >= 1 ? imin(p, W - d0) : -1;
+      const int n2 = W - d0 - kBifEdge + 1, q2 = (n2 + kTT - 1) / kTT;  // m = kBifEdge .. W - d0
+      if (n2 > 0) out_ks_range(c, scrBif, TC, t, g, d0, kBifEdge + C * q2, imin(kBifEdge + (C + 1) * q2 - 1, mhi), o.ks);
+    }
+    out_rows<out_chunk_lo(C), out_chunk_hi(C), TCC>(sm, TC, t, d0, slot_d0, W, bu, cf, g0, g1, g2, g3, g4, g5, g6, o);
+  }
+
+  template <int TCC = 0>
+  static PRIB_HD void outside_deep_tail(const Ctx &c, const ST &T, const Geo &ge, const OutSmem &sm, const real *scrBif,
+                                        int t, const ColState &cs, int d0, int slot_d0 /* = d0 % kRingOut */,
+                                        OutDeep &o) {
+    const int TC = TCC > 0 ? TCC : ge.TC, W = c.W;
+    const real *bu = K::bulge_tab(T), *cf = K::cf_tab(T);
+    const real g0 = T.cg[0], g1 = T.cg[1], g2 = T.cg[2], g3 = T.cg[3], g4 = T.cg[4], g5 = T.cg[5], g6 = T.cg[6];
     const long long g = ge.g0 - ge.H + t;
     const int L = cs.L, p = cs.i;
     const long long nc = c.NC;
-    {  // bm1[k] += bif[d0 + s][t] * Alpha_multi2[s + k][g + d0 - k]; a bif element serves all targets
-      const int shi = p >= 1 ? imin(L - p, W) - d0 : -1;
-      const real *pa = scrBif + (long long)(d0 + 5 - (kTT - 1)) * TC + t;                  // bif row d0 + s
-      const real *pb = c.arr[A_MULTI2] + (long long)(5 - (kTT - 1)) * nc + g + d0;          // row s, column q_0
-      {  // head: target k joins at s = 5 - k.  All operands are loaded first (one L2 latency instead of three).
-        real ha[kTT - 1], hb[kTT - 1][kTT];
+    // All global operands of the tail are loaded first (one L2 latency), the stencil rows 1..4 run while they fly.
+    const int shi = p >= 1 ? imin(L - p, W) - d0 : -1;
+    const int mhi = p >= 1 ? imin(p, W - d0) : -1;
+    real ha[kTT - 1], hb[kTT - 1][kTT];  // head of bm1: target k joins at s = 5 - k
+    {
+      const real *pa = scrBif + (long long)(d0 + 5 - (kTT - 1)) * TC + t;          // bif row d0 + s
+      const real *pb = c.arr[A_MULTI2] + (long long)(5 - (kTT - 1)) * nc + g + d0;  // row s, column q_0
 #pragma unroll
-        for (int h = 0; h < kTT - 1; ++h) {
-          const bool ok = 5 - (kTT - 1) + h <= shi;
-          ha[h] = ok ? pa[h * TC] : (real)0;
+      for (int h = 0; h < kTT - 1; ++h) {
+        const bool ok = 5 - (kTT - 1) + h <= shi;
+        ha[h] = ok ? pa[h * TC] : (real)0;
 #pragma unroll
-          for (int k = 0; k < kTT; ++k)
-            hb[h][k] = (ok && h + k >= kTT - 1) ? pb[(long long)h * nc + (long long)k * (nc - 1)] : (real)0;
-        }
-#pragma unroll
-        for (int h = 0; h < kTT - 1; ++h) {
-          if (5 - (kTT - 1) + h <= shi) {
-#pragma unroll
-            for (int k = 0; k < kTT; ++k)
-              if (h + k >= kTT - 1) o.bm1[k] += ha[h] * hb[h][k];
-          }
-        }
-        pa += (kTT - 1) * TC;
-        pb += (long long)(kTT - 1) * nc;
-      }
-      int s = 5;
-      for (; s + 1 <= shi; s += 2) {  // two rows per round, 10 independent loads in flight
-        const real a0 = pa[0], a1 = pa[TC];
-        real b0[kTT], b1[kTT];
-#pragma unroll
-        for (int k = 0; k < kTT; ++k) {
-          b0[k] = pb[(long long)k * (nc - 1)];
-          b1[k] = pb[(long long)k * (nc - 1) + nc];
-        }
-#pragma unroll
-        for (int k = 0; k < kTT; ++k) {
-          o.bm1[k] += a0 * b0[k];
-          o.bm1[k] += a1 * b1[k];
-        }
-        pa += 2 * TC;
-        pb += 2 * nc;
-      }
-      if (s <= shi) {
-        const real a = pa[0];
-#pragma unroll
-        for (int k = 0; k < kTT; ++k) o.bm1[k] += a * pb[(long long)k * (nc - 1)];
+        for (int k = 0; k < kTT; ++k)
+          hb[h][k] = (ok && h + k >= kTT - 1) ? pb[(long long)h * nc + (long long)k * (nc - 1)] : (real)0;
       }
     }
-    {  // ks[k] += bif[d0 - k + m][t - m] * Alpha_multi1[m][g - m]; an Alpha element serves all targets
-      const int mhi = p >= 1 ? imin(p, W - d0) : -1;  // common part: all targets take m <= W - d0
-      const real *pa = scrBif + (long long)(d0 + 5) * TC + t - 5;  // bif[d0 + m][t - m]; target k: pa[-k * TC]
-      const real *pb = c.arr[A_MULTI1] + 5 * (nc - 1) + g;         // Alpha_multi1[m][g - m]
-      int m = 5;
-      for (; m + 1 <= mhi; m += 2) {
-        const real b0 = pb[0], b1 = pb[nc - 1];
-        real a0[kTT], a1[kTT];
+    constexpr int NE = kBifEdge - 5;
+    real eb[NE], ea[NE][kTT];  // k-loop terms m = 5 .. kBifEdge - 1 (all targets)
 #pragma unroll
-        for (int k = 0; k < kTT; ++k) {
-          a0[k] = pa[-k * TC];
-          a1[k] = pa[-k * TC + (TC - 1)];
-        }
+    for (int j = 0; j < NE; ++j) {
+      const int m = 5 + j;
+      const bool ok = m <= mhi;
+      eb[j] = ok ? c.arr[A_MULTI1][(long long)m * (nc - 1) + g] : (real)0;
 #pragma unroll
-        for (int k = 0; k < kTT; ++k) {
-          o.ks[k] += a0[k] * b0;
-          o.ks[k] += a1[k] * b1;
-        }
-        pa += 2 * (TC - 1);
-        pb += 2 * (nc - 1);
+      for (int k = 0; k < kTT; ++k) ea[j][k] = ok ? scrBif[(long long)(d0 - k + m) * TC + t - m] : (real)0;
+    }
+    real tb[kTT - 1], tq[kTT - 1][kTT];  // k-loop terms m = W - d0 + e, e = 1 .. kTT-1: only the targets with k >= e
+#pragma unroll
+    for (int e = 1; e < kTT; ++e) {
+      const int mm = W - d0 + e;
+      const bool ok = p >= 1 && mm >= 5 && mm <= p;
+      tb[e - 1] = ok ? c.arr[A_MULTI1][(long long)mm * (nc - 1) + g] : (real)0;
+#pragma unroll
+      for (int k = 0; k < kTT; ++k)
+        tq[e - 1][k] = (ok && k >= e) ? scrBif[(long long)(d0 + mm - k) * TC + t - mm] : (real)0;
+    }
+    out_rows<1, 4, TCC>(sm, TC, t, d0, slot_d0, W, bu, cf, g0, g1, g2, g3, g4, g5, g6, o);
+#pragma unroll
+    for (int h = 0; h < kTT - 1; ++h) {
+      if (5 - (kTT - 1) + h <= shi) {
+#pragma unroll
+        for (int k = 0; k < kTT; ++k)
+          if (h + k >= kTT - 1) o.bm1[k] += ha[h] * hb[h][k];
       }
-      if (m <= mhi) {
-        const real b = pb[0];
+    }
 #pragma unroll
-        for (int k = 0; k < kTT; ++k) o.ks[k] += pa[-k * TC] * b;
+    for (int j = 0; j < NE; ++j) {
+      if (5 + j <= mhi) {
+#pragma unroll
+        for (int k = 0; k < kTT; ++k) o.ks[k] += ea[j][k] * eb[j];
       }
-      // tail: m = W - d0 + e, e = 1 .. kTT-1, exists only for the targets with k >= e
-      {  // (all operands loaded first: one L2 latency instead of three)
-        real tb[kTT - 1], tq[kTT - 1][kTT];
+    }
 #pragma unroll
-        for (int e = 1; e < kTT; ++e) {
-          const int mm = W - d0 + e;
-          const bool ok = p >= 1 && mm >= 5 && mm <= p;
-          tb[e - 1] = ok ? c.arr[A_MULTI1][(long long)mm * (nc - 1) + g] : (real)0;
+    for (int e = 1; e < kTT; ++e) {
+      const int mm = W - d0 + e;
+      if (p >= 1 && mm >= 5 && mm <= p) {
 #pragma unroll
-          for (int k = 0; k < kTT; ++k)
-            tq[e - 1][k] = (ok && k >= e) ? scrBif[(long long)(d0 + mm - k) * TC + t - mm] : (real)0;
-        }
-#pragma unroll
-        for (int e = 1; e < kTT; ++e) {
-          const int mm = W - d0 + e;
-          if (p >= 1 && mm >= 5 && mm <= p) {
-#pragma unroll
-            for (int k = 0; k < kTT; ++k)
-              if (k >= e) o.ks[k] += tq[e - 1][k] * tb[e - 1];
-          }
-        }
+        for (int k = 0; k < kTT; ++k)
+          if (k >= e) o.ks[k] += tq[e - 1][k] * tb[e - 1];
       }
     }
   }
