@@ -37,10 +37,10 @@ constexpr int kFp32MaxSpan = kMaxSpan;  // always try FP32 first: at W = 150 a q
                                          // is flagged and re-run in FP64, still 1.7x faster than FP64 for all (profiles/r1/sweep.json)
 // widest CTA of the tile kernels per precision (227 KB of rings / 80 rows): bounds the register budget
 #ifndef PRIB_TC32
-#define PRIB_TC32 704
+#define PRIB_TC32 640
 #endif
 #ifndef PRIB_TC64
-#define PRIB_TC64 320
+#define PRIB_TC64 288
 #endif
 template <typename real> struct TileMaxThreads { static constexpr int value = sizeof(real) == 4 ? PRIB_TC32 : PRIB_TC64; };
 
@@ -49,81 +49,38 @@ template <typename real> struct TileMaxThreads { static constexpr int value = si
 // ---------------------------------------------------------------------------------------------
 // grid = resident CTAs (one per SM: the rings take ~all shared memory), blockDim = TC, tiles round-robin.
 // dynamic smem: (kTilePad + kTileRows * TC) reals + hot tables + (TC + 16) base codes.
+constexpr int kProgBytes = 128;  // 32 per-warp progress counters (warp-to-warp synchronisation of the tile kernels)
 template <typename real>
 __host__ __device__ constexpr size_t tile_smem_bytes() {
   return ((size_t)kTilePad + (size_t)kTileRows * TileMaxThreads<real>::value) * sizeof(real) +
          (Core<real>::kHotBytes + TileMaxThreads<real>::value + kMaxSpan + 16 + 15) / 16 * 16  // + base codes (outside: TC + W + 8)
-         + 16;                                                                                   // + the step barrier (last 16 bytes)
+         + kProgBytes;                                                                           // + the per-warp progress counters
 }
 
-// Split CTA barrier (mbarrier): arrive after the stores other threads will read, wait before reading theirs.
-__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+// Warp-to-warp synchronisation of the tile kernels (acc_tile.h, "Synchronisation"): one progress counter per warp in
+// shared memory.  A warp publishes the number of events it has completed (per group of kTT spans: 1 for the deep step,
+// 1 per shallow step) with release semantics and polls its neighbours' counters with acquire semantics.
+// Slack (in events) a warp may run ahead of the neighbour that READS its columns, from the ring sizes of acc_tile.h:
+// inside: the 4-row multi rings are read one row back (3 steps); outside: the 8-row Beta_stem ring is read up to 6
+// rows back (2 steps).  Both also cover the 32/34-row stencil rings (the deep step of a group reads 30/32 rows back).
+enum { kEvSlackIn = 3, kEvSlackOut = 2 };
+__device__ __forceinline__ void prog_signal(int *prog, int warp, int lane, int value) {
+  __syncwarp();  // every lane's ring / scratch stores (and ring reads) are ordered before lane 0's release
+  if (lane == 0)
+    asm volatile("st.release.cta.shared.b32 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(prog + warp)), "r"(value) : "memory");
 }
-__device__ __forceinline__ unsigned long long mbar_arrive(unsigned long long *bar) {
-  unsigned long long state;
-  asm volatile("mbarrier.arrive.shared::cta.b64 %0, [%1];" : "=l"(state) : "r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
-  return state;
+__device__ __forceinline__ void prog_wait(const int *prog, int warp, int need) {
+  const unsigned addr = (unsigned)__cvta_generic_to_shared(prog + warp);
+  int v;
+  do {
+    asm volatile("ld.acquire.cta.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  } while (v < need);
 }
-__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned long long state) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "MBAR_WAIT:\n"
-      "mbarrier.try_wait.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra MBAR_DONE;\n"
-      "bra MBAR_WAIT;\n"
-      "MBAR_DONE:\n"
-      "}" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "l"(state) : "memory");
-}
-struct StepArrive {  // the hook of Tile::inside_shallow / outside_shallow
-  unsigned long long *bar, *state;
-  __device__ __forceinline__ void operator()() const { *state = mbar_arrive(bar); }
+struct StepSignal {  // the hook of Tile::inside_shallow / outside_shallow: runs right after the ring / scratch stores
+  int *prog;
+  int warp, lane, value;
+  __device__ __forceinline__ void operator()() const { prog_signal(prog, warp, lane, value); }
 };
-
-// The kTT shallow steps of one group, each followed (between its barrier arrive and wait) by one chunk of the NEXT
-// group's deep sums (acc_tile.h, "software pipelining across groups").
-template <typename real, int K>
-__device__ __forceinline__ void inside_group_steps(const typename Core<real>::Ctx &c,
-                                                   const typename Core<real>::SmallTables &T,
-                                                   const typename Tile<real>::Geo &ge,
-                                                   const typename Tile<real>::InSmem &sm, real *scrM1, real *scrM2, int t,
-                                                   const typename Tile<real>::ColState &cs, int d0, bool more,
-                                                   const typename Tile<real>::InDeep &cur,
-                                                   typename Tile<real>::InDeep &nxt, unsigned long long *step_bar) {
-  typedef Tile<real> TL;
-  constexpr int TC = TileMaxThreads<real>::value;
-  const bool live = d0 + K >= kTurn;  // uniform
-  unsigned long long phase = 0;
-  if (live)
-    TL::template inside_shallow<TC>(c, T, ge, sm, scrM1, scrM2, t, cs, d0 + K, cur.gs[K], cur.mb[K], cur.bs[K],
-                                    StepArrive{step_bar, &phase});
-  if (more) TL::template inside_deep_chunk<K, TC>(T, ge, sm, scrM1, scrM2, t, d0 + kTT, nxt);
-  if (live) mbar_wait(step_bar, phase);
-  if constexpr (K + 1 < kTT) inside_group_steps<real, K + 1>(c, T, ge, sm, scrM1, scrM2, t, cs, d0, more, cur, nxt, step_bar);
-}
-
-template <typename real, int K>
-__device__ __forceinline__ void outside_group_steps(const typename Core<real>::Ctx &c,
-                                                    const typename Core<real>::SmallTables &T,
-                                                    const typename Tile<real>::Geo &ge,
-                                                    const typename Tile<real>::OutSmem &sm, real *scrBif, int t,
-                                                    const typename Tile<real>::ColState &cs, int d0, int slot_d0,
-                                                    bool more, const typename Tile<real>::OutDeep &cur,
-                                                    typename Tile<real>::OutDeep &nxt, unsigned long long *step_bar) {
-  typedef Tile<real> TL;
-  constexpr int TC = TileMaxThreads<real>::value;
-  const bool live = d0 - K >= kTurn;  // uniform
-  unsigned long long phase = 0;
-  if (live)
-    TL::template outside_shallow<TC>(c, T, ge, sm, scrBif, t, cs, d0 - K, TL::wrap_out(slot_d0 + kRingOut - K), cur.gs[K],
-                                     cur.bs[K], cur.bm1[K], cur.ks[K], StepArrive{step_bar, &phase});
-  if (more)
-    TL::template outside_deep_chunk<K, TC>(c, T, ge, sm, scrBif, t, cs, d0 - kTT, TL::wrap_out(slot_d0 + kRingOut - kTT), nxt);
-  if (live) mbar_wait(step_bar, phase);
-  if constexpr (K + 1 < kTT)
-    outside_group_steps<real, K + 1>(c, T, ge, sm, scrBif, t, cs, d0, slot_d0, more, cur, nxt, step_bar);
-}
 
 template <typename real>
 __global__ void __launch_bounds__(TileMaxThreads<real>::value, 1)
@@ -131,7 +88,8 @@ k_inside_tile(typename Core<real>::Ctx c, int TX, long long ntiles, real *scratc
   typedef Tile<real> TL;
   constexpr int TC = TileMaxThreads<real>::value;  // compile-time row stride
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int t = threadIdx.x, W = c.W;
+  const int t = threadIdx.x, W = c.W, warp = t >> 5, lane = t & 31;
+  constexpr int NW = TC / 32;
   real *base = reinterpret_cast<real *>(smem_raw) + kTilePad;
   unsigned char *stab = smem_raw + ((size_t)kTilePad + (size_t)kTileRows * TC) * sizeof(real);  // 16-byte aligned
   uint8_t *sS = stab + Core<real>::kHotBytes;
@@ -142,9 +100,9 @@ k_inside_tile(typename Core<real>::Ctx c, int TX, long long ntiles, real *scratc
   real *scrM2 = scrM1 + (size_t)(W + 4) * TC;
   const typename TL::InSmem sm = TL::carve_in(base, TC, sS);
   const int dfirst = TL::first_group(W);
-  constexpr size_t bar_off = tile_smem_bytes<real>() - 16;
-  unsigned long long &step_bar = *reinterpret_cast<unsigned long long *>(smem_raw + bar_off);
-  if (t == 0) mbar_init(&step_bar, TC);
+  int *prog = reinterpret_cast<int *>(smem_raw + tile_smem_bytes<real>() - kProgBytes);
+  if (t < 32) prog[t] = 0;
+  int ebase = 0;  // events completed by every warp before this tile
   __syncthreads();
   for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     typename TL::Geo ge;
@@ -158,14 +116,27 @@ k_inside_tile(typename Core<real>::Ctx c, int TX, long long ntiles, real *scratc
     typename TL::ColState cs;
     TL::col_state(c, ge.g0 + t, cs);
     __syncthreads();
-    typename TL::InDeep cur, nxt;
-    TL::clear(cur);
+    // Inside: a cell reads columns t .. t + 29 -> forward neighbour = warp + 1, back-pressure from warp - 1.
+    int ev = ebase;
     for (int d0 = dfirst; d0 <= W + 1; d0 += kTT) {
-      TL::template inside_deep_tail<TC>(T, ge, sm, scrM1, scrM2, t, d0, cur);
-      TL::clear(nxt);
-      inside_group_steps<real, 0>(c, T, ge, sm, scrM1, scrM2, t, cs, d0, d0 + kTT <= W + 1, cur, nxt, &step_bar);
-      cur = nxt;
+      real gs[kTT], mb[kTT], bs[kTT];
+      if (warp + 1 < NW) prog_wait(prog, warp + 1, ev);  // the neighbour has finished the previous group
+      TL::template inside_deep<TC>(T, ge, sm, scrM1, scrM2, t, d0, gs, mb, bs);
+      prog_signal(prog, warp, lane, ++ev);
+#pragma unroll
+      for (int k = 0; k < kTT; ++k) {
+        ++ev;  // this step's event
+        if (d0 + k >= kTurn) {  // uniform
+          if (k > 0 && warp + 1 < NW) prog_wait(prog, warp + 1, ev - 1);
+          if (warp > 0) prog_wait(prog, warp - 1, ev - kEvSlackIn);
+          TL::template inside_shallow<TC>(c, T, ge, sm, scrM1, scrM2, t, cs, d0 + k, gs[k], mb[k], bs[k],
+                                          StepSignal{prog, warp, lane, ev});
+        } else {
+          prog_signal(prog, warp, lane, ev);
+        }
+      }
     }
+    ebase = ev;
   }
 }
 
@@ -175,7 +146,8 @@ k_outside_tile(typename Core<real>::Ctx c, int TX, long long ntiles, real *scrat
   typedef Tile<real> TL;
   constexpr int TC = TileMaxThreads<real>::value;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int t = threadIdx.x, W = c.W;
+  const int t = threadIdx.x, W = c.W, warp = t >> 5, lane = t & 31;
+  constexpr int NW = TC / 32;
   real *pad = reinterpret_cast<real *>(smem_raw);
   real *base = pad + kTilePad;
   unsigned char *stab = smem_raw + ((size_t)kTilePad + (size_t)kTileRows * TC) * sizeof(real);
@@ -186,9 +158,9 @@ k_outside_tile(typename Core<real>::Ctx c, int TX, long long ntiles, real *scrat
   real *scrBif = scratch + (size_t)blockIdx.x * 2 * (W + 4) * TC;
   const typename TL::OutSmem sm = TL::carve_out(base, TC, sS);
   const int dlast = TL::first_group(W);  // the groups of the inside pass, walked downwards
-  constexpr size_t bar_off = tile_smem_bytes<real>() - 16;
-  unsigned long long &step_bar = *reinterpret_cast<unsigned long long *>(smem_raw + bar_off);
-  if (t == 0) mbar_init(&step_bar, TC);
+  int *prog = reinterpret_cast<int *>(smem_raw + tile_smem_bytes<real>() - kProgBytes);
+  if (t < 32) prog[t] = 0;
+  int ebase = 0;
   __syncthreads();
   for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     typename TL::Geo ge;
@@ -205,16 +177,29 @@ k_outside_tile(typename Core<real>::Ctx c, int TX, long long ntiles, real *scrat
     typename TL::ColState cs;
     TL::col_state(c, ge.g0 - ge.H + t, cs);
     __syncthreads();
+    // Outside: a cell reads columns t - 30 .. t -> forward neighbour = warp - 1, back-pressure from warp + 1.
     int slot = (W + 1) % kRingOut;
-    typename TL::OutDeep cur, nxt;
-    TL::clear(cur);
+    int ev = ebase;
     for (int d0 = W + 1; d0 >= dlast + kTT - 1; d0 -= kTT) {
-      TL::template outside_deep_tail<TC>(c, T, ge, sm, scrBif, t, cs, d0, slot, cur);
-      TL::clear(nxt);
-      outside_group_steps<real, 0>(c, T, ge, sm, scrBif, t, cs, d0, slot, d0 - kTT >= dlast + kTT - 1, cur, nxt, &step_bar);
-      cur = nxt;
-      slot = TL::wrap_out(slot + kRingOut - kTT);
+      typename TL::OutDeep o;
+      if (warp > 0) prog_wait(prog, warp - 1, ev);
+      TL::template outside_deep<TC>(c, T, ge, sm, scrBif, t, cs, d0, slot, o);
+      prog_signal(prog, warp, lane, ++ev);
+#pragma unroll
+      for (int k = 0; k < kTT; ++k) {
+        ++ev;
+        if (d0 - k >= kTurn) {  // uniform
+          if (k > 0 && warp > 0) prog_wait(prog, warp - 1, ev - 1);
+          if (warp + 1 < NW) prog_wait(prog, warp + 1, ev - kEvSlackOut);
+          TL::template outside_shallow<TC>(c, T, ge, sm, scrBif, t, cs, d0 - k, slot, o.gs[k], o.bs[k], o.bm1[k],
+                                           o.ks[k], StepSignal{prog, warp, lane, ev});
+        } else {
+          prog_signal(prog, warp, lane, ev);
+        }
+        slot = slot == 0 ? kRingOut - 1 : slot - 1;
+      }
     }
+    ebase = ev;
   }
 }
 

@@ -13,19 +13,18 @@
 // shared-memory load instead of one), then kTT "shallow" steps finish the cells span by span (stack,
 // 1-nt bulges, 1x1/1x2/2x1/2x2 loops, multiloop bookkeeping) with a __syncthreads in between.
 //
-// Software pipelining across groups.  A deep sum of the NEXT group only needs rows that are >= 5 spans away
-// from that group's first span — rows that are complete before the CURRENT group's shallow steps start.  So
-// the deep work of group n + 1 is cut into kTT "chunks" (source rows 5.., the middle of the multibranch
-// sums) that run between the barrier arrive and the barrier wait of the shallow steps of group n: the
-// latency-bound shallow steps (table gathers, ring round trips, barrier skew) overlap with the issue-bound
-// stencil work of other warps instead of idling the SM.  What is left for the start of a group (the "tail":
-// source rows 1..4 and the few multibranch terms that touch the previous group's rows) is small.
+// Synchronisation.  A cell only reads ring rows of its own warp's columns and of the columns of ONE neighbouring
+// warp (inside: up to 29 columns to the right; outside: up to 30 to the left), so the kernels do not use a
+// CTA-wide barrier per span: every warp publishes a progress counter and waits only for its neighbour
+// ("forward": the neighbour has produced the rows I read; "back-pressure": the other neighbour has finished
+// reading the ring slots I am about to overwrite).  The ring sizes below leave 3 steps of slack between
+// neighbouring warps, so the warps drift apart and the latency-bound shallow steps of one warp overlap with the
+// issue-bound deep steps of others.  The order of additions per cell is not affected.
 //
 // The functions below are the per-thread bodies (thread t = local column t of the tile); the CUDA kernels
-// and the host emulation (tests/hostemu) both call them in the same schedule.  Per cell the SET of terms is
-// the one of acc_core.h's one-cell-at-a-time functions; the order of additions differs (far rows first), so
-// the two agree to rounding, not bit for bit (tests/test_hostemu.py).  The order depends on the span only,
-// hence results do not depend on tile width, batch composition or the number of GPUs.
+// and the host emulation (tests/hostemu) both call them.  The order of additions inside a cell is
+// identical to acc_core.h's one-cell-at-a-time functions, so both give the same bits in the same
+// precision (checked by tests/test_hostemu.py).
 #pragma once
 #include "acc_core.h"
 
@@ -36,8 +35,10 @@ enum {
   kRingIn = 32,    // inside: source rows d-30..d-1 plus the row being written
   kRingOut = 34,   // outside: source rows d+1..d+32 plus the row being written
   kRingStem = 8,
-  kRingSE = 4,
-  kTileRows = 80,  // shared-memory rows of TC reals per CTA (both passes)
+  kRingSE = 8,
+  kRingMu = 4,     // Alpha/Beta_multi and _multi2: the previous row is read, 4 slots leave 3 steps of slack between
+                   // neighbouring warps (the kernels synchronise warp to warp, not CTA-wide)
+  kTileRows = 88,  // shared-memory rows of TC reals per CTA (both passes)
   kTilePad = 64,   // zeroed reals in front of the rings: the outside stencils look up to 33 columns to the left
   kOutBaseLead = 2,  // outside pass: base codes staged in shared memory start 2 columns left of the tile ...
   kOutBaseTail = 8,  // ... and reach W + 4 columns past its right edge (s[d + 3] of the last column)
@@ -137,7 +138,7 @@ struct Tile {
     s.stem = s.stemB + kRingIn * TC;
     s.se = s.stem + kRingStem * TC;
     s.mu = s.se + kRingSE * TC;
-    s.m2 = s.mu + 2 * TC;
+    s.m2 = s.mu + kRingMu * TC;
     s.S = S;
     return s;
   }
@@ -152,14 +153,14 @@ struct Tile {
     s.stemB = s.stemO + kRingOut * TC;
     s.stem = s.stemB + kRingOut * TC;
     s.mu = s.stem + kRingStem * TC;
-    s.m2 = s.mu + 2 * TC;
+    s.m2 = s.mu + kRingMu * TC;
     return s;
   }
 
   // One source row of the inside stencils (row d0 - S of the Alpha_stemI / Alpha_stemB rings) for all kTT targets;
   // S is a template parameter so that every coefficient choice and column offset is resolved at compile
   // time (a plain `#pragma unroll` nest of this size is not unrolled by nvcc).
-  template <int S, int SEND, int TCC>
+  template <int S, int TCC>
   static PRIB_HD void in_rows(const InSmem &sm, int TC, int t, int d0, const real *cf, const real *bu, real g0, real g1,
                               real g2, real g3, real g4, real g5, real g6, real (&gs)[kTT], real (&bs)[kTT]) {
     if (d0 - S >= 5) {  // rows below span 5 hold no stems; same cut as `sum <= min(30, d - 5)` per target
@@ -174,10 +175,16 @@ struct Tile {
         unsigned long long r01 = 0, r23 = 0;
 #pragma unroll
         for (int x = 1; x <= S + kTT - 2; ++x) {
+#if defined(PRIB_EXP_HALFLDS)
+          const float v = row[x | 1];
+#else
           const float v = row[x];
+#endif
           const int a0 = in_cidx(x, S), a1 = in_cidx(x, S + 1), a2 = in_cidx(x, S + 2), a3 = in_cidx(x, S + 3);
           if (a0 != 7 || a1 != 7) ffma2_bcast(r01, v, g_cgpair_f[a0 * 8 + a1]);
+#if !defined(PRIB_EXP_HALFFMA)
           if (a2 != 7 || a3 != 7) ffma2_bcast(r23, v, g_cgpair_f[a2 * 8 + a3]);
+#endif
         }
         float q0, q1, q2, q3;
         unpack2(r01, q0, q1);
@@ -223,130 +230,72 @@ struct Tile {
           if (S + k >= 4 && S + k <= kMaxLoop) bs[k] += bu[S + k] * (rowB[S + k] + b0);
       }
     }
-    if constexpr (S < SEND) in_rows<S + 1, SEND, TCC>(sm, TC, t, d0, cf, bu, g0, g1, g2, g3, g4, g5, g6, gs, bs);
+    if constexpr (S < kMaxLoop) in_rows<S + 1, TCC>(sm, TC, t, d0, cf, bu, g0, g1, g2, g3, g4, g5, g6, gs, bs);
   }
 
   // ---------------------------------------------------------------------------------------------
-  // inside, deep sums: thread t = local column t; targets are the cells (i, i + d0 + k), k = 0..kTT-1.
+  // inside, deep step: thread t = local column t; targets are the cells (i, i + d0 + k), k = 0..kTT-1.
   //   gs[k] = generic interior loops of Alpha_stemend (raccess.cpp:201-215, 808-812) as a stencil over the
   //           Alpha_stemI ring: source row d0 - s serves target k with loop size s + k;
   //   bs[k] = bulges of length >= 4 (:788-795) over the Alpha_stemB ring, same rows;
   //   mb[k] = Alpha_multibif (:131-143) from the per-CTA scratch rows scrM1 / scrM2 ([(W+4)][TC]).
   // Only rows <= d0 - 1 are read, so all kTT targets are legal at once.  TCC: compile-time tile width
   // (0 = ge.TC at run time, host emulation): every ring row offset becomes an immediate.
-  //
-  // The work is split for the software pipeline (see the top of the file):
-  //   inside_deep_chunk<C>: source rows S >= 5 (rows <= d0 - 5) in kTT chunks and the multibif terms whose two
-  //                         operands both lie in rows <= d0 - 5 (m = 8 .. d0 - 5); legal while the PREVIOUS
-  //                         group's shallow steps are still running;
-  //   inside_deep_tail:     source rows S = 1..4 and the multibif terms m = 5..7 and m >= d0 - 4, which read rows
-  //                         of the previous group; runs at the start of the group.
   // ---------------------------------------------------------------------------------------------
-  struct InDeep {
-    real gs[kTT], mb[kTT], bs[kTT];
-  };
-  static PRIB_HD void clear(InDeep &a) {
-#pragma unroll
-    for (int k = 0; k < kTT; ++k) a.gs[k] = a.mb[k] = a.bs[k] = 0;
-  }
-  // source rows of chunk C: balanced by loads (S + 7 per row)
-  static PRIB_HD constexpr int in_chunk_lo(int C) { return C == 0 ? 5 : C == 1 ? 15 : C == 2 ? 21 : 26; }
-  static PRIB_HD constexpr int in_chunk_hi(int C) { return C == 0 ? 14 : C == 1 ? 20 : C == 2 ? 25 : kMaxLoop; }
-  enum { kBifEdge = 8 };  // multibif terms m < kBifEdge belong to the tail (their multi2 row may be of the previous group)
-
-  // mb[k] += sum over m = mlo..mhi of multi1[m][t] * multi2[d0 + k - m][t + m] for all kTT targets; the caller
-  // guarantees 5 <= mlo and mhi <= d0 - 5, so every operand exists.  A multi1 element serves all targets; two
-  // running pointers, every other offset is an immediate.
-  static PRIB_HD void in_bif_range(const real *scrM1, const real *scrM2, int TC, int t, int d0, int mlo, int mhi,
-                                   real (&mb)[kTT]) {
-    if (mlo > mhi) return;
-    const real *pa = scrM1 + mlo * TC + t;                       // multi1[m][t]
-    const real *pb = scrM2 + (long long)(d0 - mlo) * TC + t + mlo;  // multi2[d0 - m][t + m]; target k: pb[k * TC]
-    int m = mlo;
-    for (; m + 1 <= mhi; m += 2) {  // two m per round, 10 independent loads in flight
-      const real a0 = pa[0], a1 = pa[TC];
-      real b0[kTT], b1[kTT];
-#pragma unroll
-      for (int k = 0; k < kTT; ++k) {
-        b0[k] = pb[k * TC];
-        b1[k] = pb[k * TC - (TC - 1)];
-      }
-#pragma unroll
-      for (int k = 0; k < kTT; ++k) {
-        mb[k] += a0 * b0[k];
-        mb[k] += a1 * b1[k];
-      }
-      pa += 2 * TC;
-      pb -= 2 * (TC - 1);
-    }
-    if (m <= mhi) {
-      const real a0 = pa[0];
-      real b0[kTT];
-#pragma unroll
-      for (int k = 0; k < kTT; ++k) b0[k] = pb[k * TC];
-#pragma unroll
-      for (int k = 0; k < kTT; ++k) mb[k] += a0 * b0[k];
-    }
-  }
-
-  // multibif terms next to the two ends of the m range: (a) m = 5 .. kBifEdge - 1, (b) m = d0 - 4 .. d0 + kTT - 6
-  // (not below kBifEdge); target k takes m while m <= d0 + k - 5.  All operands are loaded first: one L2 latency.
-  static PRIB_HD void in_bif_edges(const real *scrM1, const real *scrM2, int TC, int t, int d0, real (&mb)[kTT]) {
-    constexpr int NA = kBifEdge - 5, NB = kTT - 1;
-    real ea[NA], eb[NA][kTT], ta[NB], tb[NB][kTT];
-#pragma unroll
-    for (int j = 0; j < NA; ++j) {
-      const int m = 5 + j;
-      ea[j] = (m <= d0 + kTT - 1 - 5) ? scrM1[m * TC + t] : (real)0;
-#pragma unroll
-      for (int k = 0; k < kTT; ++k) eb[j][k] = (m <= d0 + k - 5) ? scrM2[(long long)(d0 + k - m) * TC + t + m] : (real)0;
-    }
-#pragma unroll
-    for (int j = 0; j < NB; ++j) {
-      const int m = d0 - 4 + j;  // <= d0 + k - 5  <=>  k >= j + 1
-      const bool ok = m >= kBifEdge;
-      ta[j] = ok ? scrM1[m * TC + t] : (real)0;
-#pragma unroll
-      for (int k = 0; k < kTT; ++k) tb[j][k] = (ok && k >= j + 1) ? scrM2[(long long)(d0 + k - m) * TC + t + m] : (real)0;
-    }
-#pragma unroll
-    for (int j = 0; j < NA; ++j) {
-#pragma unroll
-      for (int k = 0; k < kTT; ++k)
-        if (5 + j <= d0 + k - 5) mb[k] += ea[j] * eb[j][k];
-    }
-#pragma unroll
-    for (int j = 0; j < NB; ++j) {
-      if (d0 - 4 + j >= kBifEdge) {
-#pragma unroll
-        for (int k = 0; k < kTT; ++k)
-          if (k >= j + 1) mb[k] += ta[j] * tb[j][k];
-      }
-    }
-  }
-
-  template <int C, int TCC = 0>
-  static PRIB_HD void inside_deep_chunk(const ST &T, const Geo &ge, const InSmem &sm, const real *scrM1,
-                                        const real *scrM2, int t, int d0, InDeep &a) {
-    const int TC = TCC > 0 ? TCC : ge.TC;
-    const real *cf = K::cf_tab(T), *bu = K::bulge_tab(T);
-    const real g0 = T.cg[0], g1 = T.cg[1], g2 = T.cg[2], g3 = T.cg[3], g4 = T.cg[4], g5 = T.cg[5], g6 = T.cg[6];
-    {  // this chunk's quarter of the multibif terms m = kBifEdge .. d0 - 5 (first: their L2 latency is covered
-       // by the stencil rows of the other warps)
-      const int n = d0 - 5 - kBifEdge + 1, q = (n + kTT - 1) / kTT;
-      if (n > 0) in_bif_range(scrM1, scrM2, TC, t, d0, kBifEdge + C * q, imin(kBifEdge + (C + 1) * q - 1, d0 - 5), a.mb);
-    }
-    in_rows<in_chunk_lo(C), in_chunk_hi(C), TCC>(sm, TC, t, d0, cf, bu, g0, g1, g2, g3, g4, g5, g6, a.gs, a.bs);
-  }
-
   template <int TCC = 0>
-  static PRIB_HD void inside_deep_tail(const ST &T, const Geo &ge, const InSmem &sm, const real *scrM1,
-                                       const real *scrM2, int t, int d0, InDeep &a) {
+  static PRIB_HD void inside_deep(const ST &T, const Geo &ge, const InSmem &sm, const real *scrM1, const real *scrM2,
+                                  int t, int d0, real (&gs)[kTT], real (&mb)[kTT], real (&bs)[kTT]) {
     const int TC = TCC > 0 ? TCC : ge.TC;
     const real *cf = K::cf_tab(T), *bu = K::bulge_tab(T);
     const real g0 = T.cg[0], g1 = T.cg[1], g2 = T.cg[2], g3 = T.cg[3], g4 = T.cg[4], g5 = T.cg[5], g6 = T.cg[6];
-    in_bif_edges(scrM1, scrM2, TC, t, d0, a.mb);
-    in_rows<1, 4, TCC>(sm, TC, t, d0, cf, bu, g0, g1, g2, g3, g4, g5, g6, a.gs, a.bs);
+#pragma unroll
+    for (int k = 0; k < kTT; ++k) gs[k] = mb[k] = bs[k] = 0;
+    in_rows<1, TCC>(sm, TC, t, d0, cf, bu, g0, g1, g2, g3, g4, g5, g6, gs, bs);
+    // multibif: mb[k] = sum over m = 5 .. d0+k-5 of multi1[m][t] * multi2[d0+k-m][t+m]; a multi1 element
+    // serves all kTT targets.  Two running pointers, every other offset is an immediate.
+    {
+      const real *pa = scrM1 + 5 * TC + t;                       // multi1[m][t]
+      const real *pb = scrM2 + (long long)(d0 - 5) * TC + t + 5;  // multi2[d0 - m][t + m]; target k: pb[k * TC]
+      int m = 5;
+#if defined(PRIB_EXP_NOBIF)
+      if (d0 == 1000)
+#endif
+      for (; m + 1 <= d0 - 5; m += 2) {  // two m per round, 10 independent loads in flight
+        const real a0 = pa[0], a1 = pa[TC];
+        real b0[kTT], b1[kTT];
+#pragma unroll
+        for (int k = 0; k < kTT; ++k) {
+          b0[k] = pb[k * TC];
+          b1[k] = pb[k * TC - (TC - 1)];
+        }
+#pragma unroll
+        for (int k = 0; k < kTT; ++k) {
+          mb[k] += a0 * b0[k];
+          mb[k] += a1 * b1[k];
+        }
+        pa += 2 * TC;
+        pb -= 2 * (TC - 1);
+      }
+      {  // tail (<= kTT rows): targets drop out one by one (rows below 5 do not exist).  All operands are loaded
+         // first: one L2 latency instead of one per row.
+        real ta[kTT], tb[kTT][kTT];
+#pragma unroll
+        for (int j = 0; j < kTT; ++j) {
+          const bool ok = m + j <= d0 + kTT - 1 - 5;
+          ta[j] = ok ? pa[j * TC] : (real)0;
+#pragma unroll
+          for (int k = 0; k < kTT; ++k) tb[j][k] = (ok && m + j <= d0 + k - 5) ? pb[k * TC - j * (TC - 1)] : (real)0;
+        }
+#pragma unroll
+        for (int j = 0; j < kTT; ++j) {
+          if (m + j <= d0 + kTT - 1 - 5) {
+#pragma unroll
+            for (int k = 0; k < kTT; ++k)
+              if (m + j <= d0 + k - 5) mb[k] += ta[j] * tb[j][k];
+          }
+        }
+      }
+    }
   }
 
   // ---------------------------------------------------------------------------------------------
@@ -369,7 +318,11 @@ struct Tile {
       // Special-loop table entries (1x1, 1x2, 2x1, 2x2: 6.4 KB + 32 KB + 160 KB tables, L2-resident) are fetched
       // first: their indices depend on the bases only, and the rest of the step hides the L2 latency.
       real p11 = 0, p21a = 0, p21b = 0, p22 = 0;
+#if defined(PRIB_EXP_NOTAB)
+      if (te && d == 1000) {
+#else
       if (te) {
+#endif
         const int sd1 = s[d - 1], sd2 = s[d - 2], s2 = s[2], s3 = s[3];
         if (smax >= 2) p11 = c.e_int11[idx11(te, T.rt[T.bp[s2][sd1]], si1, sj)];
         if (smax >= 3) {
@@ -386,9 +339,9 @@ struct Tile {
       }
       mb *= T.inv_cA;
       stemD = tp ? stem * K::e_dangle(T, tp, i > 0, si, j < L, sj1) : 0;
-      m2 = stemD * T.e_mlintern + sm.m2[((d - 1) & 1) * TC + t] * T.e_mlbase;
+      m2 = stemD * T.e_mlintern + sm.m2[((d - 1) & (kRingMu - 1)) * TC + t] * T.e_mlbase;
       m1 = m2 + mb;
-      mu = sm.mu[((d - 1) & 1) * TC + t + 1] * T.e_mlbase + mb;
+      mu = sm.mu[((d - 1) & (kRingMu - 1)) * TC + t + 1] * T.e_mlbase + mb;
       if (tp) {
         stemI = stem * T.e_mmI[T.rt[tp]][sj1][si];
         stemB = stem * T.tau[tp];
@@ -433,13 +386,17 @@ struct Tile {
     sm.stemB[(d & (kRingIn - 1)) * TC + t] = stemB;
     sm.stem[(d & (kRingStem - 1)) * TC + t] = stem;
     sm.se[(d & (kRingSE - 1)) * TC + t] = se;
-    sm.mu[(d & 1) * TC + t] = mu;
-    sm.m2[(d & 1) * TC + t] = m2;
+    sm.mu[(d & (kRingMu - 1)) * TC + t] = mu;
+    sm.m2[(d & (kRingMu - 1)) * TC + t] = m2;
     scrM1[d * TC + t] = m1;
     scrM2[d * TC + t] = m2;
     stores_done();
     // persistent outputs: owned columns only
+#if defined(PRIB_EXP_NOSTG)
+    if (t < ge.TX && i >= 0 && j <= L && d == 1000) {
+#else
     if (t < ge.TX && i >= 0 && j <= L) {
+#endif
       const long long g = ge.g0 + t;
       if (c.delta == 2) c.at(A_STEM, d, g) = stem;  // only the 2x1 / 2x2 loops of delta == 2 read it (BiTile)
       c.at(A_STEMI, d, g) = stemI;
@@ -470,7 +427,7 @@ struct Tile {
   };
 
   // One source row (d0 + S of the Beta_stemO / Beta_stemB rings) of the outside stencils for all kTT targets.
-  template <int S, int SEND, int TCC>
+  template <int S, int TCC>
   static PRIB_HD void out_rows(const OutSmem &sm, int TC, int t, int d0, int slot_d0, int W, const real *bu,
                                const real *cf, real g0, real g1, real g2, real g3, real g4, real g5, real g6,
                                OutDeep &o) {
@@ -508,10 +465,16 @@ struct Tile {
         unsigned long long r01 = 0, r23 = 0;
 #pragma unroll
         for (int y = 1; y <= S + kTT - 4; ++y) {
+#if defined(PRIB_EXP_HALFLDS)
+          const float v = rowO[-(y | 1)];
+#else
           const float v = rowO[-y];
+#endif
           const int a0 = in_cidx(y, S - 2), a1 = in_cidx(y, S - 1), a2 = in_cidx(y, S), a3 = in_cidx(y, S + 1);
           if (a0 != 7 || a1 != 7) ffma2_bcast(r01, v, g_cgpair_f[a0 * 8 + a1]);
+#if !defined(PRIB_EXP_HALFFMA)
           if (a2 != 7 || a3 != 7) ffma2_bcast(r23, v, g_cgpair_f[a2 * 8 + a3]);
+#endif
         }
         float q0, q1, q2, q3;
         unpack2(r01, q0, q1);
@@ -549,188 +512,128 @@ struct Tile {
         }
       }
     }
-    if constexpr (S < SEND) out_rows<S + 1, SEND, TCC>(sm, TC, t, d0, slot_d0, W, bu, cf, g0, g1, g2, g3, g4, g5, g6, o);
-  }
-
-  static PRIB_HD void clear(OutDeep &o) {
-#pragma unroll
-    for (int k = 0; k < kTT; ++k) o.gs[k] = o.bs[k] = o.bm1[k] = o.ks[k] = 0;
-  }
-  // Split of the deep sums of group d0 (targets d0 - k) for the software pipeline (see the top of the file):
-  //   outside_deep_chunk<C>: source rows S >= 5 (rows >= d0 + 5) in kTT chunks, Beta_multi1 terms s >= 5 and the
-  //                          k-loop terms m >= kBifEdge of Beta_multi2 — every bif row they read is >= d0 + 5, i.e.
-  //                          complete before the PREVIOUS group's shallow steps start;
-  //   outside_deep_tail:     source rows S = 1..4, the head of Beta_multi1 (s = 2..4), the k-loop terms m = 5..7 and
-  //                          m > W - d0, which read rows of the previous group; runs at the start of the group.
-  static PRIB_HD constexpr int out_chunk_lo(int C) { return C == 0 ? 5 : C == 1 ? 15 : C == 2 ? 22 : 28; }
-  static PRIB_HD constexpr int out_chunk_hi(int C) { return C == 0 ? 14 : C == 1 ? 21 : C == 2 ? 27 : kMaxLoop + 2; }
-
-  // Multiloop sums.  Only cells strictly inside the sequence (p >= 1, q < L) use them (outside_shallow
-  // ignores the sums of all others), and for those the term ranges of the kTT targets line up:
-  //   bm1[k]: m = 5 .. min(L - q_k, W - d_k)  <=>  bif row d0 + s with s = m - k = 5 - k .. min(L - p, W) - d0
-  //   ks[k] : m = 5 .. min(p, W - d_k)
-  // so the loops run on common bounds and every load stays inside the sequence / the scratch rows.
-
-  // bm1[k] += sum over s = slo..shi of bif[d0 + s][t] * Alpha_multi2[s + k][g + d0 - k] (slo >= 5: all targets take
-  // every s); a bif element serves all targets
-  static PRIB_HD void out_bm1_range(const Ctx &c, const real *scrBif, int TC, int t, long long g, int d0, int slo,
-                                    int shi, real (&bm1)[kTT]) {
-    if (slo > shi) return;
-    const long long nc = c.NC;
-    const real *pa = scrBif + (long long)(d0 + slo) * TC + t;      // bif row d0 + s
-    const real *pb = c.arr[A_MULTI2] + (long long)slo * nc + g + d0;  // row s, column q_0; target k: pb[k * (nc - 1)]
-    int s = slo;
-    for (; s + 1 <= shi; s += 2) {  // two rows per round, 10 independent loads in flight
-      const real a0 = pa[0], a1 = pa[TC];
-      real b0[kTT], b1[kTT];
-#pragma unroll
-      for (int k = 0; k < kTT; ++k) {
-        b0[k] = pb[(long long)k * (nc - 1)];
-        b1[k] = pb[(long long)k * (nc - 1) + nc];
-      }
-#pragma unroll
-      for (int k = 0; k < kTT; ++k) {
-        bm1[k] += a0 * b0[k];
-        bm1[k] += a1 * b1[k];
-      }
-      pa += 2 * TC;
-      pb += 2 * nc;
-    }
-    if (s <= shi) {
-      const real a = pa[0];
-      real b0[kTT];
-#pragma unroll
-      for (int k = 0; k < kTT; ++k) b0[k] = pb[(long long)k * (nc - 1)];
-#pragma unroll
-      for (int k = 0; k < kTT; ++k) bm1[k] += a * b0[k];
-    }
-  }
-
-  // ks[k] += sum over m = mlo..mhi of bif[d0 - k + m][t - m] * Alpha_multi1[m][g - m]; an Alpha element serves all
-  // targets (the caller guarantees mhi <= W - d0: all targets take every m)
-  static PRIB_HD void out_ks_range(const Ctx &c, const real *scrBif, int TC, int t, long long g, int d0, int mlo,
-                                   int mhi, real (&ks)[kTT]) {
-    if (mlo > mhi) return;
-    const long long nc = c.NC;
-    const real *pa = scrBif + (long long)(d0 + mlo) * TC + t - mlo;  // bif[d0 + m][t - m]; target k: pa[-k * TC]
-    const real *pb = c.arr[A_MULTI1] + (long long)mlo * (nc - 1) + g;  // Alpha_multi1[m][g - m]
-    int m = mlo;
-    for (; m + 1 <= mhi; m += 2) {
-      const real b0 = pb[0], b1 = pb[nc - 1];
-      real a0[kTT], a1[kTT];
-#pragma unroll
-      for (int k = 0; k < kTT; ++k) {
-        a0[k] = pa[-k * TC];
-        a1[k] = pa[-k * TC + (TC - 1)];
-      }
-#pragma unroll
-      for (int k = 0; k < kTT; ++k) {
-        ks[k] += a0[k] * b0;
-        ks[k] += a1[k] * b1;
-      }
-      pa += 2 * (TC - 1);
-      pb += 2 * (nc - 1);
-    }
-    if (m <= mhi) {
-      const real b = pb[0];
-      real a0[kTT];
-#pragma unroll
-      for (int k = 0; k < kTT; ++k) a0[k] = pa[-k * TC];
-#pragma unroll
-      for (int k = 0; k < kTT; ++k) ks[k] += a0[k] * b;
-    }
-  }
-
-  template <int C, int TCC = 0>
-  static PRIB_HD void outside_deep_chunk(const Ctx &c, const ST &T, const Geo &ge, const OutSmem &sm,
-                                         const real *scrBif, int t, const ColState &cs, int d0,
-                                         int slot_d0 /* = d0 % kRingOut */, OutDeep &o) {
-    const int TC = TCC > 0 ? TCC : ge.TC, W = c.W;
-    const real *bu = K::bulge_tab(T), *cf = K::cf_tab(T);
-    const real g0 = T.cg[0], g1 = T.cg[1], g2 = T.cg[2], g3 = T.cg[3], g4 = T.cg[4], g5 = T.cg[5], g6 = T.cg[6];
-    const long long g = ge.g0 - ge.H + t;
-    const int L = cs.L, p = cs.i;
-    {  // this chunk's quarter of the multiloop terms (first: their L2 latency is covered by the stencil rows of
-       // the other warps)
-      const int shi = p >= 1 ? imin(L - p, W) - d0 : -1;
-      const int n1 = W - d0 - 4, q1 = (n1 + kTT - 1) / kTT;  // s = 5 .. W - d0, uniform split
-      if (n1 > 0) out_bm1_range(c, scrBif, TC, t, g, d0, 5 + C * q1, imin(5 + (C + 1) * q1 - 1, shi), o.bm1);
-      const int mhi = p >= 1 ? imin(p, W - d0) : -1;
-      const int n2 = W - d0 - kBifEdge + 1, q2 = (n2 + kTT - 1) / kTT;  // m = kBifEdge .. W - d0
-      if (n2 > 0) out_ks_range(c, scrBif, TC, t, g, d0, kBifEdge + C * q2, imin(kBifEdge + (C + 1) * q2 - 1, mhi), o.ks);
-    }
-    out_rows<out_chunk_lo(C), out_chunk_hi(C), TCC>(sm, TC, t, d0, slot_d0, W, bu, cf, g0, g1, g2, g3, g4, g5, g6, o);
+    if constexpr (S < kMaxLoop + 2) out_rows<S + 1, TCC>(sm, TC, t, d0, slot_d0, W, bu, cf, g0, g1, g2, g3, g4, g5, g6, o);
   }
 
   template <int TCC = 0>
-  static PRIB_HD void outside_deep_tail(const Ctx &c, const ST &T, const Geo &ge, const OutSmem &sm, const real *scrBif,
-                                        int t, const ColState &cs, int d0, int slot_d0 /* = d0 % kRingOut */,
-                                        OutDeep &o) {
+  static PRIB_HD void outside_deep(const Ctx &c, const ST &T, const Geo &ge, const OutSmem &sm, const real *scrBif,
+                                   int t, const ColState &cs, int d0, int slot_d0 /* = d0 % kRingOut */, OutDeep &o) {
     const int TC = TCC > 0 ? TCC : ge.TC, W = c.W;
     const real *bu = K::bulge_tab(T), *cf = K::cf_tab(T);
     const real g0 = T.cg[0], g1 = T.cg[1], g2 = T.cg[2], g3 = T.cg[3], g4 = T.cg[4], g5 = T.cg[5], g6 = T.cg[6];
+#pragma unroll
+    for (int k = 0; k < kTT; ++k) o.gs[k] = o.bs[k] = o.bm1[k] = o.ks[k] = 0;
+    // stencils: source row d0 + s; target k: bulge length / loop size s + k - 2
+    out_rows<1, TCC>(sm, TC, t, d0, slot_d0, W, bu, cf, g0, g1, g2, g3, g4, g5, g6, o);
+    // Multiloop sums.  Only cells strictly inside the sequence (p >= 1, q < L) use them (outside_shallow
+    // ignores the sums of all others), and for those the term ranges of the kTT targets line up:
+    //   bm1[k]: m = 5 .. min(L - q_k, W - d_k)  <=>  bif row d0 + s with s = m - k = 5 - k .. min(L - p, W) - d0
+    //   ks[k] : m = 5 .. min(p, W - d_k)
+    // so the loops run on common bounds and every load stays inside the sequence / the scratch rows.
     const long long g = ge.g0 - ge.H + t;
     const int L = cs.L, p = cs.i;
     const long long nc = c.NC;
-    // All global operands of the tail are loaded first (one L2 latency), the stencil rows 1..4 run while they fly.
-    const int shi = p >= 1 ? imin(L - p, W) - d0 : -1;
-    const int mhi = p >= 1 ? imin(p, W - d0) : -1;
-    real ha[kTT - 1], hb[kTT - 1][kTT];  // head of bm1: target k joins at s = 5 - k
-    {
-      const real *pa = scrBif + (long long)(d0 + 5 - (kTT - 1)) * TC + t;          // bif row d0 + s
-      const real *pb = c.arr[A_MULTI2] + (long long)(5 - (kTT - 1)) * nc + g + d0;  // row s, column q_0
+    {  // bm1[k] += bif[d0 + s][t] * Alpha_multi2[s + k][g + d0 - k]; a bif element serves all targets
+      const int shi = p >= 1 ? imin(L - p, W) - d0 : -1;
+      const real *pa = scrBif + (long long)(d0 + 5 - (kTT - 1)) * TC + t;                  // bif row d0 + s
+      const real *pb = c.arr[A_MULTI2] + (long long)(5 - (kTT - 1)) * nc + g + d0;          // row s, column q_0
+      {  // head: target k joins at s = 5 - k.  All operands are loaded first (one L2 latency instead of three).
+        real ha[kTT - 1], hb[kTT - 1][kTT];
 #pragma unroll
-      for (int h = 0; h < kTT - 1; ++h) {
-        const bool ok = 5 - (kTT - 1) + h <= shi;
-        ha[h] = ok ? pa[h * TC] : (real)0;
+        for (int h = 0; h < kTT - 1; ++h) {
+          const bool ok = 5 - (kTT - 1) + h <= shi;
+          ha[h] = ok ? pa[h * TC] : (real)0;
 #pragma unroll
-        for (int k = 0; k < kTT; ++k)
-          hb[h][k] = (ok && h + k >= kTT - 1) ? pb[(long long)h * nc + (long long)k * (nc - 1)] : (real)0;
+          for (int k = 0; k < kTT; ++k)
+            hb[h][k] = (ok && h + k >= kTT - 1) ? pb[(long long)h * nc + (long long)k * (nc - 1)] : (real)0;
+        }
+#pragma unroll
+        for (int h = 0; h < kTT - 1; ++h) {
+          if (5 - (kTT - 1) + h <= shi) {
+#pragma unroll
+            for (int k = 0; k < kTT; ++k)
+              if (h + k >= kTT - 1) o.bm1[k] += ha[h] * hb[h][k];
+          }
+        }
+        pa += (kTT - 1) * TC;
+        pb += (long long)(kTT - 1) * nc;
+      }
+      int s = 5;
+#if defined(PRIB_EXP_NOBIF)
+      if (d0 == 1000)
+#endif
+      for (; s + 1 <= shi; s += 2) {  // two rows per round, 10 independent loads in flight
+        const real a0 = pa[0], a1 = pa[TC];
+        real b0[kTT], b1[kTT];
+#pragma unroll
+        for (int k = 0; k < kTT; ++k) {
+          b0[k] = pb[(long long)k * (nc - 1)];
+          b1[k] = pb[(long long)k * (nc - 1) + nc];
+        }
+#pragma unroll
+        for (int k = 0; k < kTT; ++k) {
+          o.bm1[k] += a0 * b0[k];
+          o.bm1[k] += a1 * b1[k];
+        }
+        pa += 2 * TC;
+        pb += 2 * nc;
+      }
+      if (s <= shi) {
+        const real a = pa[0];
+#pragma unroll
+        for (int k = 0; k < kTT; ++k) o.bm1[k] += a * pb[(long long)k * (nc - 1)];
       }
     }
-    constexpr int NE = kBifEdge - 5;
-    real eb[NE], ea[NE][kTT];  // k-loop terms m = 5 .. kBifEdge - 1 (all targets)
+    {  // ks[k] += bif[d0 - k + m][t - m] * Alpha_multi1[m][g - m]; an Alpha element serves all targets
+      const int mhi = p >= 1 ? imin(p, W - d0) : -1;  // common part: all targets take m <= W - d0
+      const real *pa = scrBif + (long long)(d0 + 5) * TC + t - 5;  // bif[d0 + m][t - m]; target k: pa[-k * TC]
+      const real *pb = c.arr[A_MULTI1] + 5 * (nc - 1) + g;         // Alpha_multi1[m][g - m]
+      int m = 5;
+#if defined(PRIB_EXP_NOBIF)
+      if (d0 == 1000)
+#endif
+      for (; m + 1 <= mhi; m += 2) {
+        const real b0 = pb[0], b1 = pb[nc - 1];
+        real a0[kTT], a1[kTT];
 #pragma unroll
-    for (int j = 0; j < NE; ++j) {
-      const int m = 5 + j;
-      const bool ok = m <= mhi;
-      eb[j] = ok ? c.arr[A_MULTI1][(long long)m * (nc - 1) + g] : (real)0;
+        for (int k = 0; k < kTT; ++k) {
+          a0[k] = pa[-k * TC];
+          a1[k] = pa[-k * TC + (TC - 1)];
+        }
 #pragma unroll
-      for (int k = 0; k < kTT; ++k) ea[j][k] = ok ? scrBif[(long long)(d0 - k + m) * TC + t - m] : (real)0;
-    }
-    real tb[kTT - 1], tq[kTT - 1][kTT];  // k-loop terms m = W - d0 + e, e = 1 .. kTT-1: only the targets with k >= e
-#pragma unroll
-    for (int e = 1; e < kTT; ++e) {
-      const int mm = W - d0 + e;
-      const bool ok = p >= 1 && mm >= 5 && mm <= p;
-      tb[e - 1] = ok ? c.arr[A_MULTI1][(long long)mm * (nc - 1) + g] : (real)0;
-#pragma unroll
-      for (int k = 0; k < kTT; ++k)
-        tq[e - 1][k] = (ok && k >= e) ? scrBif[(long long)(d0 + mm - k) * TC + t - mm] : (real)0;
-    }
-    out_rows<1, 4, TCC>(sm, TC, t, d0, slot_d0, W, bu, cf, g0, g1, g2, g3, g4, g5, g6, o);
-#pragma unroll
-    for (int h = 0; h < kTT - 1; ++h) {
-      if (5 - (kTT - 1) + h <= shi) {
-#pragma unroll
-        for (int k = 0; k < kTT; ++k)
-          if (h + k >= kTT - 1) o.bm1[k] += ha[h] * hb[h][k];
+        for (int k = 0; k < kTT; ++k) {
+          o.ks[k] += a0[k] * b0;
+          o.ks[k] += a1[k] * b1;
+        }
+        pa += 2 * (TC - 1);
+        pb += 2 * (nc - 1);
       }
-    }
+      if (m <= mhi) {
+        const real b = pb[0];
 #pragma unroll
-    for (int j = 0; j < NE; ++j) {
-      if (5 + j <= mhi) {
-#pragma unroll
-        for (int k = 0; k < kTT; ++k) o.ks[k] += ea[j][k] * eb[j];
+        for (int k = 0; k < kTT; ++k) o.ks[k] += pa[-k * TC] * b;
       }
-    }
+      // tail: m = W - d0 + e, e = 1 .. kTT-1, exists only for the targets with k >= e
+      {  // (all operands loaded first: one L2 latency instead of three)
+        real tb[kTT - 1], tq[kTT - 1][kTT];
 #pragma unroll
-    for (int e = 1; e < kTT; ++e) {
-      const int mm = W - d0 + e;
-      if (p >= 1 && mm >= 5 && mm <= p) {
+        for (int e = 1; e < kTT; ++e) {
+          const int mm = W - d0 + e;
+          const bool ok = p >= 1 && mm >= 5 && mm <= p;
+          tb[e - 1] = ok ? c.arr[A_MULTI1][(long long)mm * (nc - 1) + g] : (real)0;
 #pragma unroll
-        for (int k = 0; k < kTT; ++k)
-          if (k >= e) o.ks[k] += tq[e - 1][k] * tb[e - 1];
+          for (int k = 0; k < kTT; ++k)
+            tq[e - 1][k] = (ok && k >= e) ? scrBif[(long long)(d0 + mm - k) * TC + t - mm] : (real)0;
+        }
+#pragma unroll
+        for (int e = 1; e < kTT; ++e) {
+          const int mm = W - d0 + e;
+          if (p >= 1 && mm >= 5 && mm <= p) {
+#pragma unroll
+            for (int k = 0; k < kTT; ++k)
+              if (k >= e) o.ks[k] += tq[e - 1][k] * tb[e - 1];
+          }
+        }
       }
     }
   }
@@ -758,7 +661,11 @@ struct Tile {
       double la = 0, lb = 0, lz = 0;  // loaded here, combined where the base term is formed (in-order issue: a
                                       // dependent add up here would stall the warp on the loads right away)
       real p11 = 0, p21a = 0, p21b = 0, p22 = 0;
+#if defined(PRIB_EXP_NOTAB)
+      if (t2_ && d == 1000) {
+#else
       if (t2_) {
+#endif
         la = c.lao[g];
         lb = c.lbo[g + d];
         lz = c.lao[cs.zcol];
@@ -775,10 +682,10 @@ struct Tile {
       const real bse = (inner && d + 2 <= W + 1) ? b2[-1] : 0;  // Beta_stemend(p,q), :277-279
       if (inner) {
         const int tt = T.rt[te];
-        bmulti = (d + 1 <= W + 1 ? sm.mu[((d + 1) & 1) * TC + t - 1] * T.e_mlbase : (real)0) +
+        bmulti = (d + 1 <= W + 1 ? sm.mu[((d + 1) & (kRingMu - 1)) * TC + t - 1] * T.e_mlbase : (real)0) +
                  T.k2 * bse * T.e_mlclose * T.e_d3[tt][sp1] * T.e_d5[tt][sq_];
         bm1 *= T.inv_cA;
-        bmulti2 = bm1 + sm.m2[((d + 1) & 1) * TC + t] * T.e_mlbase + ks * T.inv_cA;
+        bmulti2 = bm1 + sm.m2[((d + 1) & (kRingMu - 1)) * TC + t] * T.e_mlbase + ks * T.inv_cA;
         bmbif = bm1 + bmulti;
       }
       const int t2 = T.bp[sp1][sq_];
@@ -817,11 +724,15 @@ struct Tile {
     sm.stemO[slot_d * TC + t] = bstemO;
     sm.stemB[slot_d * TC + t] = bstemB;
     sm.stem[(d & (kRingStem - 1)) * TC + t] = bstem;
-    sm.mu[(d & 1) * TC + t] = bmulti;
-    sm.m2[(d & 1) * TC + t] = bmulti2;
+    sm.mu[(d & (kRingMu - 1)) * TC + t] = bmulti;
+    sm.m2[(d & (kRingMu - 1)) * TC + t] = bmulti2;
     scrBif[d * TC + t] = bmbif;
     stores_done();
+#if defined(PRIB_EXP_NOSTG)
+    if (t >= ge.H && p >= 0 && q <= L && d == 1000) {
+#else
     if (t >= ge.H && p >= 0 && q <= L) {
+#endif
       c.at(B_STEM, d, g) = bstem;
       c.at(B_STEMO, d, g) = bstemO;
       c.at(B_STEMB, d, g) = bstemB;

@@ -100,20 +100,10 @@ void run_dp_tiled(EmuT<real> &e, int TC) {
   std::vector<typename TL::ColState> cs(TC);
   real *base = smem.data() + kTilePad;
   const int dfirst = TL::first_group(W);
-  std::vector<typename TL::InDeep> din(TC), din_next(TC);
-  std::vector<typename TL::OutDeep> dout(TC), dout_next(TC);
+  struct InDeep { real gs[kTT], mb[kTT], bs[kTT]; };
+  std::vector<InDeep> din(TC);
+  std::vector<typename TL::OutDeep> dout(TC);
   real *scrM1 = scr.data(), *scrM2 = scr.data() + (size_t)(W + 4) * TC;
-  // The schedule of the CUDA kernels (software pipelining across groups): the tail of the group's deep sums, then
-  // per span the shallow step of every thread ("barrier arrive"), then chunk k of the NEXT group's deep sums
-  // ("barrier wait" comes after it on the device; a chunk only reads rows that were complete before the group started).
-  auto in_chunk = [&](int k, const typename TL::Geo &ge, const typename TL::InSmem &sm, int t, int d0) {
-    switch (k) {
-      case 0: TL::template inside_deep_chunk<0, 0>(*c.T, ge, sm, scrM1, scrM2, t, d0, din_next[t]); break;
-      case 1: TL::template inside_deep_chunk<1, 0>(*c.T, ge, sm, scrM1, scrM2, t, d0, din_next[t]); break;
-      case 2: TL::template inside_deep_chunk<2, 0>(*c.T, ge, sm, scrM1, scrM2, t, d0, din_next[t]); break;
-      default: TL::template inside_deep_chunk<3, 0>(*c.T, ge, sm, scrM1, scrM2, t, d0, din_next[t]); break;
-    }
-  };
   for (long long tile = 0; tile < ntiles; tile++) {
     typename TL::Geo ge{tile * TX, TC, TX, H};
     std::fill(smem.begin(), smem.end(), (real)0);
@@ -121,21 +111,14 @@ void run_dp_tiled(EmuT<real> &e, int TC) {
     for (int k = 0; k < TC + 8; k++) sS[k] = (ge.g0 + k < c.NC) ? c.S[ge.g0 + k] : 0;
     for (int t = 0; t < TC; t++) TL::col_state(c, ge.g0 + t, cs[t]);
     typename TL::InSmem sm = TL::carve_in(base, TC, sS.data());
-    for (int t = 0; t < TC; t++) TL::clear(din[t]);
     for (int d0 = dfirst; d0 <= W + 1; d0 += kTT) {
-      for (int t = 0; t < TC; t++) {
-        TL::template inside_deep_tail<0>(*c.T, ge, sm, scrM1, scrM2, t, d0, din[t]);
-        TL::clear(din_next[t]);
-      }
+      for (int t = 0; t < TC; t++) TL::template inside_deep<0>(*c.T, ge, sm, scrM1, scrM2, t, d0, din[t].gs, din[t].mb, din[t].bs);
       for (int k = 0; k < kTT; k++) {
-        if (d0 + k >= kTurn)
-          for (int t = 0; t < TC; t++)
-            TL::template inside_shallow<0>(c, *c.T, ge, sm, scrM1, scrM2, t, cs[t], d0 + k, din[t].gs[k], din[t].mb[k],
-                                           din[t].bs[k]);
-        if (d0 + kTT <= W + 1)
-          for (int t = 0; t < TC; t++) in_chunk(k, ge, sm, t, d0 + kTT);
+        if (d0 + k < kTurn) continue;
+        for (int t = 0; t < TC; t++)
+          TL::template inside_shallow<0>(c, *c.T, ge, sm, scrM1, scrM2, t, cs[t], d0 + k, din[t].gs[k], din[t].mb[k],
+                                         din[t].bs[k]);
       }
-      din.swap(din_next);
     }
   }
   double ring[256];
@@ -143,7 +126,6 @@ void run_dp_tiled(EmuT<real> &e, int TC) {
     K::scan_alpha_outer(c, k, ring);
     K::scan_beta_outer(c, k, ring);
   }
-  auto slot_of = [](int d) { return ((d % kRingOut) + kRingOut) % kRingOut; };
   for (long long tile = 0; tile < ntiles; tile++) {
     typename TL::Geo ge{tile * TX, TC, TX, H};
     std::fill(smem.begin(), smem.end(), (real)0);
@@ -155,31 +137,17 @@ void run_dp_tiled(EmuT<real> &e, int TC) {
       sSo[k] = (col >= 0 && col < c.NC) ? c.S[col] : 0;
     }
     typename TL::OutSmem sm = TL::carve_out(base, TC, sSo.data());
-    auto out_chunk = [&](int k, int t, int d0) {
-      switch (k) {
-        case 0: TL::template outside_deep_chunk<0, 0>(c, *c.T, ge, sm, scr.data(), t, cs[t], d0, slot_of(d0), dout_next[t]); break;
-        case 1: TL::template outside_deep_chunk<1, 0>(c, *c.T, ge, sm, scr.data(), t, cs[t], d0, slot_of(d0), dout_next[t]); break;
-        case 2: TL::template outside_deep_chunk<2, 0>(c, *c.T, ge, sm, scr.data(), t, cs[t], d0, slot_of(d0), dout_next[t]); break;
-        default: TL::template outside_deep_chunk<3, 0>(c, *c.T, ge, sm, scr.data(), t, cs[t], d0, slot_of(d0), dout_next[t]); break;
-      }
-    };
-    for (int t = 0; t < TC; t++) TL::clear(dout[t]);
-    const int dlast = dfirst + kTT - 1;
-    for (int d0 = W + 1; d0 >= dlast; d0 -= kTT) {
-      for (int t = 0; t < TC; t++) {
-        TL::template outside_deep_tail<0>(c, *c.T, ge, sm, scr.data(), t, cs[t], d0, slot_of(d0), dout[t]);
-        TL::clear(dout_next[t]);
-      }
+    for (int d0 = W + 1; d0 >= dfirst + kTT - 1; d0 -= kTT) {
+      for (int t = 0; t < TC; t++)
+        TL::template outside_deep<0>(c, *c.T, ge, sm, scr.data(), t, cs[t], d0, ((d0 % kRingOut) + kRingOut) % kRingOut,
+                                     dout[t]);
       for (int k = 0; k < kTT; k++) {
         const int d = d0 - k;
-        if (d >= kTurn)
-          for (int t = 0; t < TC; t++)
-            TL::template outside_shallow<0>(c, *c.T, ge, sm, scr.data(), t, cs[t], d, slot_of(d), dout[t].gs[k],
-                                            dout[t].bs[k], dout[t].bm1[k], dout[t].ks[k]);
-        if (d0 - kTT >= dlast)
-          for (int t = 0; t < TC; t++) out_chunk(k, t, d0 - kTT);
+        if (d < kTurn) continue;
+        for (int t = 0; t < TC; t++)
+          TL::template outside_shallow<0>(c, *c.T, ge, sm, scr.data(), t, cs[t], d, d % kRingOut, dout[t].gs[k],
+                                          dout[t].bs[k], dout[t].bm1[k], dout[t].ks[k]);
       }
-      dout.swap(dout_next);
     }
   }
 }
