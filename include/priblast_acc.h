@@ -27,6 +27,8 @@ extern "C" {
 #define PRIB_ECUDA (-2)   /* CUDA runtime/driver error, no device, or out of device memory */
 #define PRIB_ESTATE (-3)  /* call order violated (e.g. compute before stage) */
 #define PRIB_ENOMEM (-4)  /* host allocation failed */
+#define PRIB_ENUMERIC (-5) /* an output value is not finite (partition function out of the double range); the
+                              reference's log-domain sums cannot do this, so the result is refused, not returned */
 
 typedef struct prib_ctx prib_ctx;
 

@@ -78,16 +78,21 @@ static __constant__ float g_cf_f[32];
 // (cg[a], cg[b]) for a, b = 0..7 (index 7 = 0): coefficient pairs of the packed FP32 stencils (FFMA2 takes the pair
 // as a 64-bit uniform-register operand, so the coefficients cost no vector registers)
 static __constant__ float2 g_cgpair_f[64];
+// cg[0..6] for the centre-line chain of the tile kernels (acc_tile.h)
+static __constant__ double g_cg_d[8];
+static __constant__ float g_cg_f[8];
 template <typename real> struct ConstTab;
 template <> struct ConstTab<double> {
   static __device__ __forceinline__ const double *conv() { return g_conv_d; }
   static __device__ __forceinline__ const double *bulge() { return g_bulge_d; }
   static __device__ __forceinline__ const double *cf() { return g_cf_d; }
+  static __device__ __forceinline__ const double *cg() { return g_cg_d; }
 };
 template <> struct ConstTab<float> {
   static __device__ __forceinline__ const float *conv() { return g_conv_f; }
   static __device__ __forceinline__ const float *bulge() { return g_bulge_f; }
   static __device__ __forceinline__ const float *cf() { return g_cf_f; }
+  static __device__ __forceinline__ const float *cg() { return g_cg_f; }
 };
 #endif
 
@@ -149,6 +154,7 @@ struct Ctx {
   const long long *acc_off, *cond_off;  // float offsets per sequence into out
   float *out;
   int32_t *flags;          // per sequence: set when a stored value leaves the safe range (FP32 build)
+  int32_t *bad;            // one counter per batch: outputs that are not finite (0 = all good); may be null
 
   PRIB_HD real &at(int a, int d, long long g) const { return arr[a][(long long)d * NC + g]; }
   PRIB_HD real ld(int a, int d, long long g) const { return arr[a][(long long)d * NC + g]; }
@@ -169,6 +175,13 @@ static PRIB_HD const real *cf_tab(const SmallTables &T) {
   return ConstTab<real>::cf();
 #else
   return T.cf;
+#endif
+}
+static PRIB_HD const real *cg_tab(const SmallTables &T) {
+#if defined(__CUDA_ARCH__)
+  return ConstTab<real>::cg();
+#else
+  return T.cg;
 #endif
 }
 // ninio step of a generic loop, compile-time after unrolling
@@ -300,21 +313,27 @@ static PRIB_HD void inside_cell(const Ctx &c, long long g, int d) {
 // Outer arrays (raccess.cpp:230-241 and :260-271) as scaled linear recurrences; results stored as logs.
 // ring: 256 doubles of scratch.  One caller per sequence.
 // ------------------------------------------------------------------------------------------------
+// Rescaling: the scaled values stay below kScanBig = 2^256 at every check; between two checks a value can grow by at
+// most one un-normalised Alpha_stem weight (<= e^405 ~ 2^584 for a perfect 75-bp GC helix at W <= 200, DESIGN.md
+// §2.1) times the weight of a short structure, so nothing overflows 2^1024; the rescale repeats until the value is
+// back under the threshold.
+static constexpr double kScanBig = 1.157920892373162e77;  // 2^256
+static constexpr int kScanBigLog2 = 256;
+
 static PRIB_HD void scan_alpha_outer(const Ctx &c, int sq, double *ring) {
   const int L = c.seq_len[sq], W = c.W;
   const long long off = c.seq_off[sq];
-  const double kBig = 1.3407807929942597e154;  // 2^512
-  long long e2 = 0;                            // true value = ring value * 2^e2
+  long long e2 = 0;  // true value = ring value * 2^e2
   ring[0] = 1.0;
   c.lao[off] = 0.0;
   for (int i = 1; i <= L; ++i) {
     double v = ring[(i - 1) & 255];
     const int dmax = imin(W + 1, i);
     for (int d = 5; d <= dmax; ++d) v += (double)c.ld(A_STEMD, d, off + i - d) * c.T->us[d] * ring[(i - d) & 255];
-    if (v > kBig) {
-      for (int k = imax(0, i - W - 2); k < i; ++k) ring[k & 255] *= 1.0 / kBig;
-      v *= 1.0 / kBig;
-      e2 += 512;
+    for (int it = 0; it < 4 && v > kScanBig; ++it) {  // bounded: an infinite v (overflowed FP32 weights of a flagged sequence) must not spin
+      for (int k = imax(0, i - W - 2); k < i; ++k) ring[k & 255] *= 1.0 / kScanBig;
+      v *= 1.0 / kScanBig;
+      e2 += kScanBigLog2;
     }
     ring[i & 255] = v;
     c.lao[off + i] = log(v) + (double)e2 * 0.6931471805599453094;
@@ -324,7 +343,6 @@ static PRIB_HD void scan_alpha_outer(const Ctx &c, int sq, double *ring) {
 static PRIB_HD void scan_beta_outer(const Ctx &c, int sq, double *ring) {
   const int L = c.seq_len[sq], W = c.W;
   const long long off = c.seq_off[sq];
-  const double kBig = 1.3407807929942597e154;
   long long e2 = 0;
   ring[L & 255] = 1.0;
   c.lbo[off + L] = 0.0;
@@ -332,10 +350,10 @@ static PRIB_HD void scan_beta_outer(const Ctx &c, int sq, double *ring) {
     double v = ring[(i + 1) & 255];
     const int dmax = imin(W + 1, L - i);
     for (int d = 5; d <= dmax; ++d) v += (double)c.ld(A_STEMD, d, off + i) * c.T->us[d] * ring[(i + d) & 255];
-    if (v > kBig) {
-      for (int k = i + 1; k <= imin(L, i + W + 2); ++k) ring[k & 255] *= 1.0 / kBig;
-      v *= 1.0 / kBig;
-      e2 += 512;
+    for (int it = 0; it < 4 && v > kScanBig; ++it) {  // bounded: an infinite v (overflowed FP32 weights of a flagged sequence) must not spin
+      for (int k = i + 1; k <= imin(L, i + W + 2); ++k) ring[k & 255] *= 1.0 / kScanBig;
+      v *= 1.0 / kScanBig;
+      e2 += kScanBigLog2;
     }
     ring[i & 255] = v;
     c.lbo[off + i] = log(v) + (double)e2 * 0.6931471805599453094;
@@ -682,13 +700,25 @@ static PRIB_HD void finalize_position(const Ctx &c, long long g) {
   prob += mp0;
   const float a = (float)((-(double)fmath_logf(c, (float)prob) * kT) / 1000);
   acc[x - 1] = a;
+  bool finite = a == a && a - a == 0.f;  // neither NaN nor inf
   if (has_cond) {
     double pc = 0.0;
     pc += exp(c.lao[off + x - 1] + c.lbo[off + x + w] - Z);
     pc += hairpin_prob(c, off, x, w + 1);
     pc += cbp;
     pc += mp1;
-    cond[x + w - 1] = (float)((-(double)fmath_logf(c, (float)pc) * kT) / 1000 - a);
+    const float cv = (float)((-(double)fmath_logf(c, (float)pc) * kT) / 1000 - a);
+    cond[x + w - 1] = cv;
+    finite = finite && cv == cv && cv - cv == 0.f;
+  }
+  // The reference cannot produce a non-finite value here (its log-domain sums saturate); if this path ever does
+  // (overflowed partition function), the caller must hear about it instead of finding NaN in <db>.acc.
+  if (!finite && c.bad) {
+#if defined(__CUDA_ARCH__)
+    atomicAdd(c.bad, 1);
+#else
+    ++*c.bad;
+#endif
   }
 }
 

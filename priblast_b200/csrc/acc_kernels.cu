@@ -42,6 +42,7 @@ constexpr int kFp32MaxSpan = kMaxSpan;  // always try FP32 first: at W = 150 a q
 #ifndef PRIB_TC64
 #define PRIB_TC64 288
 #endif
+template <typename real> struct TileChain { static constexpr bool value = sizeof(real) == 4 && PRIB_CHAIN != 0; };
 template <typename real> struct TileMaxThreads { static constexpr int value = sizeof(real) == 4 ? PRIB_TC32 : PRIB_TC64; };
 
 // ---------------------------------------------------------------------------------------------
@@ -63,7 +64,7 @@ __host__ __device__ constexpr size_t tile_smem_bytes() {
 // Slack (in events) a warp may run ahead of the neighbour that READS its columns, from the ring sizes of acc_tile.h:
 // inside: the 4-row multi rings are read one row back (3 steps); outside: the 8-row Beta_stem ring is read up to 6
 // rows back (2 steps).  Both also cover the 32/34-row stencil rings (the deep step of a group reads 30/32 rows back).
-enum { kEvSlackIn = 3, kEvSlackOut = 2 };
+enum { kEvPerGroup = kTT + 1, kEvSlackIn = 3, kEvSlackOut = 2 };
 __device__ __forceinline__ void prog_signal(int *prog, int warp, int lane, int value) {
   __syncwarp();  // every lane's ring / scratch stores (and ring reads) are ordered before lane 0's release
   if (lane == 0)
@@ -82,9 +83,10 @@ struct StepSignal {  // the hook of Tile::inside_shallow / outside_shallow: runs
   __device__ __forceinline__ void operator()() const { prog_signal(prog, warp, lane, value); }
 };
 
-template <typename real>
+template <typename real, int PAR /* parity of the first span of every group (chain formulation) */>
 __global__ void __launch_bounds__(TileMaxThreads<real>::value, 1)
 k_inside_tile(typename Core<real>::Ctx c, int TX, long long ntiles, real *scratch) {
+  constexpr bool CH = TileChain<real>::value;
   typedef Tile<real> TL;
   constexpr int TC = TileMaxThreads<real>::value;  // compile-time row stride
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -117,20 +119,31 @@ k_inside_tile(typename Core<real>::Ctx c, int TX, long long ntiles, real *scratc
     TL::col_state(c, ge.g0 + t, cs);
     __syncthreads();
     // Inside: a cell reads columns t .. t + 29 -> forward neighbour = warp + 1, back-pressure from warp - 1.
-    int ev = ebase;
-    for (int d0 = dfirst; d0 <= W + 1; d0 += kTT) {
+    // Chain formulation: the generic sums of column x come from the centre-line threads x .. x + (W + 1) / 2 (warps
+    // w .. w + 2) through the double-buffered exchange rows.
+    int ev = ebase, grp = 0;
+    typename TL::Chain ch;
+    if constexpr (CH) TL::clear(ch);
+    for (int d0 = dfirst; d0 <= W + 1; d0 += kTT, ++grp) {
       real gs[kTT], mb[kTT], bs[kTT];
+      real *xch = sm.xch + (grp & 1) * kTT * TC;
       if (warp + 1 < NW) prog_wait(prog, warp + 1, ev);  // the neighbour has finished the previous group
-      TL::template inside_deep<TC>(T, ge, sm, scrM1, scrM2, t, d0, gs, mb, bs);
+      if constexpr (CH) {
+        if (warp >= 2) prog_wait(prog, warp - 2, ev - kEvPerGroup);  // readers of this exchange buffer (group - 2) are done
+        TL::template inside_deep_chain<PAR, TC>(T, ge, sm, scrM1, scrM2, t, d0, ch, xch, mb, bs);
+      } else {
+        TL::template inside_deep<TC>(T, ge, sm, scrM1, scrM2, t, d0, gs, mb, bs);
+      }
       prog_signal(prog, warp, lane, ++ev);
 #pragma unroll
       for (int k = 0; k < kTT; ++k) {
         ++ev;  // this step's event
         if (d0 + k >= kTurn) {  // uniform
-          if (k > 0 && warp + 1 < NW) prog_wait(prog, warp + 1, ev - 1);
+          if ((k > 0 || CH) && warp + 1 < NW) prog_wait(prog, warp + 1, ev - 1);
+          if (CH && warp + 2 < NW) prog_wait(prog, warp + 2, ev - 1 - k);  // its deep step of this group wrote my columns
           if (warp > 0) prog_wait(prog, warp - 1, ev - kEvSlackIn);
-          TL::template inside_shallow<TC>(c, T, ge, sm, scrM1, scrM2, t, cs, d0 + k, gs[k], mb[k], bs[k],
-                                          StepSignal{prog, warp, lane, ev});
+          TL::template inside_shallow<TC>(c, T, ge, sm, scrM1, scrM2, t, cs, d0 + k, CH ? xch[k * TC + t] : gs[k], mb[k],
+                                          bs[k], StepSignal{prog, warp, lane, ev});
         } else {
           prog_signal(prog, warp, lane, ev);
         }
@@ -143,6 +156,7 @@ k_inside_tile(typename Core<real>::Ctx c, int TX, long long ntiles, real *scratc
 template <typename real>
 __global__ void __launch_bounds__(TileMaxThreads<real>::value, 1)
 k_outside_tile(typename Core<real>::Ctx c, int TX, long long ntiles, real *scratch) {
+  constexpr bool CH = TileChain<real>::value;
   typedef Tile<real> TL;
   constexpr int TC = TileMaxThreads<real>::value;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -178,21 +192,32 @@ k_outside_tile(typename Core<real>::Ctx c, int TX, long long ntiles, real *scrat
     TL::col_state(c, ge.g0 - ge.H + t, cs);
     __syncthreads();
     // Outside: a cell reads columns t - 30 .. t -> forward neighbour = warp - 1, back-pressure from warp + 1.
+    // Chain formulation: the generic sums of column x come from the centre-line threads x - (W + 1) / 2 .. x (warps
+    // w - 2 .. w).
     int slot = (W + 1) % kRingOut;
-    int ev = ebase;
-    for (int d0 = W + 1; d0 >= dlast + kTT - 1; d0 -= kTT) {
+    int ev = ebase, grp = 0;
+    typename TL::Chain ch;
+    if constexpr (CH) TL::clear(ch);
+    for (int d0 = W + 1; d0 >= dlast + kTT - 1; d0 -= kTT, ++grp) {
       typename TL::OutDeep o;
+      real *xch = sm.xch + (grp & 1) * kTT * TC;
       if (warp > 0) prog_wait(prog, warp - 1, ev);
-      TL::template outside_deep<TC>(c, T, ge, sm, scrBif, t, cs, d0, slot, o);
+      if constexpr (CH) {
+        if (warp + 2 < NW) prog_wait(prog, warp + 2, ev - kEvPerGroup);
+        TL::template outside_deep_chain<TC>(c, T, ge, sm, scrBif, t, cs, d0, slot, ch, xch, o);
+      } else {
+        TL::template outside_deep<TC>(c, T, ge, sm, scrBif, t, cs, d0, slot, o);
+      }
       prog_signal(prog, warp, lane, ++ev);
 #pragma unroll
       for (int k = 0; k < kTT; ++k) {
         ++ev;
         if (d0 - k >= kTurn) {  // uniform
-          if (k > 0 && warp > 0) prog_wait(prog, warp - 1, ev - 1);
+          if ((k > 0 || CH) && warp > 0) prog_wait(prog, warp - 1, ev - 1);
+          if (CH && warp >= 2) prog_wait(prog, warp - 2, ev - 1 - k);
           if (warp + 1 < NW) prog_wait(prog, warp + 1, ev - kEvSlackOut);
-          TL::template outside_shallow<TC>(c, T, ge, sm, scrBif, t, cs, d0 - k, slot, o.gs[k], o.bs[k], o.bm1[k],
-                                           o.ks[k], StepSignal{prog, warp, lane, ev});
+          TL::template outside_shallow<TC>(c, T, ge, sm, scrBif, t, cs, d0 - k, slot, CH ? xch[k * TC + t] : o.gs[k],
+                                           o.bs[k], o.bm1[k], o.ks[k], StepSignal{prog, warp, lane, ev});
         } else {
           prog_signal(prog, warp, lane, ev);
         }
@@ -227,7 +252,7 @@ __device__ void warp_scan(const typename Core<real>::Ctx &c, int sq, double *rin
                           int lane) {
   const int L = c.seq_len[sq], W = c.W;
   const long long off = c.seq_off[sq];
-  const double kBig = 1.3407807929942597e154, kLn2 = 0.6931471805599453094;
+  const double kBig = Core<real>::kScanBig, kLn2 = 0.6931471805599453094;  // see scan_alpha_outer (acc_core.h)
   double *dst = ALPHA ? c.lao : c.lbo;
   const real *src = c.arr[A_STEMD];  // cell (st - d, st) sits at column st - d: row stride NC - 1 for Alpha_outer
   const int half = (W + 2) * 32;
@@ -278,10 +303,11 @@ __device__ void warp_scan(const typename Core<real>::Ctx &c, int sq, double *rin
       dst[off + i] = log(myv) + (double)e2 * kLn2;
     }
     __syncwarp();
-    if (vprev > kBig) {  // uniform (vprev was broadcast): exact power-of-two rescale of the live window
+    for (int it = 0; it < 4 && vprev > kBig; ++it) {  // uniform (vprev was broadcast): exact power-of-two rescale of the live window
       const int hi = imin(L, st0 + 31), lo = imax(0, hi - W - 2);
       for (int k = lo + lane; k <= hi; k += 32) ring[k & 255] *= 1.0 / kBig;
-      e2 += 512;
+      vprev *= 1.0 / kBig;
+      e2 += Core<real>::kScanBigLog2;
       __syncwarp();
     }
     cur ^= 1;
@@ -551,6 +577,8 @@ struct prib_ctx {
   size_t h_in_cap = 0;
   int32_t *h_flags = nullptr;
   long long h_flags_cap = 0;
+  int32_t *d_bad = nullptr;       // number of non-finite outputs of the current compute (finalize_position)
+  int32_t *h_bad = nullptr;
   prib_acc_counters cnt{};
 };
 
@@ -620,6 +648,7 @@ typename Core<real>::Ctx make_ctx(prib_ctx *c, const Batch &b) {
   k.cond_off = b.d_cond_off;
   k.out = c->d_out;
   k.flags = b.d_flags;
+  k.bad = c->d_bad;
   return k;
 }
 
@@ -802,7 +831,8 @@ int run_batch(prib_ctx *c, const Batch &b, bool timed) {
   const long long ntiles = (b.NC + TX - 1) / TX;
   const int tgrid = (int)std::min<long long>(ntiles, c->grid_tiles);
   real *scratch = reinterpret_cast<real *>(c->d_tile_scratch);
-  k_inside_tile<real><<<tgrid, e.TC, e.tile_smem, st>>>(k, TX, ntiles, scratch);
+  if (Tile<real>::first_group(c->W) & 1) k_inside_tile<real, 1><<<tgrid, e.TC, e.tile_smem, st>>>(k, TX, ntiles, scratch);
+  else k_inside_tile<real, 0><<<tgrid, e.TC, e.tile_smem, st>>>(k, TX, ntiles, scratch);
   if (timed) CU(cudaEventRecord(c->evp[2], st));
   k_outer_scans_warp<real><<<(2 * b.n + e.scan_warps - 1) / e.scan_warps, 32 * e.scan_warps,
                              (size_t)e.scan_warps * 2 * (c->W + 2) * 32 * sizeof(real), st>>>(k);
@@ -867,10 +897,12 @@ int setup_engine(prib_ctx *c, const ScaleSpec &spec, size_t smem_max, std::strin
     CU(cudaMemcpyToSymbol(g_conv_d, &tab.small.conv[0][0], sizeof(real) * 32 * 32));
     CU(cudaMemcpyToSymbol(g_bulge_d, tab.small.e_bulge, sizeof(real) * 32));
     CU(cudaMemcpyToSymbol(g_cf_d, tab.small.cf, sizeof(real) * 32));
+    CU(cudaMemcpyToSymbol(g_cg_d, tab.small.cg, sizeof(real) * 8));
   } else {
     CU(cudaMemcpyToSymbol(g_conv_f, &tab.small.conv[0][0], sizeof(real) * 32 * 32));
     CU(cudaMemcpyToSymbol(g_bulge_f, tab.small.e_bulge, sizeof(real) * 32));
     CU(cudaMemcpyToSymbol(g_cf_f, tab.small.cf, sizeof(real) * 32));
+    CU(cudaMemcpyToSymbol(g_cg_f, tab.small.cg, sizeof(real) * 8));
     float2 pairs[64];
     for (int a = 0; a < 8; a++)
       for (int b = 0; b < 8; b++)
@@ -892,7 +924,8 @@ int setup_engine(prib_ctx *c, const ScaleSpec &spec, size_t smem_max, std::strin
   if (TC < c->W + 34) return fail(PRIB_ECUDA, "tile narrower than the span halo");
   e.TC = TC;
   e.tile_smem = tile_smem_bytes<real>();
-  CU(cudaFuncSetAttribute(k_inside_tile<real>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+  CU(cudaFuncSetAttribute((k_inside_tile<real, 0>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+  CU(cudaFuncSetAttribute((k_inside_tile<real, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
   CU(cudaFuncSetAttribute(k_outside_tile<real>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
   // interior-loop tiles: the widest block (<= 512 threads) whose Alpha_stemI tile + span lists fit
   const int rows = c->W - 5 > 0 ? c->W - 5 : 0;
@@ -987,6 +1020,9 @@ int prib_acc_create(prib_ctx **out, const prib_acc_params *params) {
   CUB(cudaEventCreate(&c->evk0));
   CUB(cudaEventCreate(&c->evk1));
   for (auto &e : c->evp) CUB(cudaEventCreate(&e));
+  CUB(cudaMalloc(&c->d_bad, sizeof(int32_t)));
+  CUB(cudaMallocHost(&c->h_bad, sizeof(int32_t)));
+  *c->h_bad = 0;
   cudaDeviceProp prop;
   CUB(cudaGetDeviceProperties(&prop, params->device));
   c->grid_tiles = prop.multiProcessorCount;
@@ -1032,6 +1068,8 @@ void prib_acc_destroy(prib_ctx *c) {
   if (c->h_stage) cudaFreeHost(c->h_stage);
   if (c->h_in) cudaFreeHost(c->h_in);
   if (c->h_flags) cudaFreeHost(c->h_flags);
+  if (c->h_bad) cudaFreeHost(c->h_bad);
+  cudaFree(c->d_bad);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
   if (c->evk0) cudaEventDestroy(c->evk0);
@@ -1096,6 +1134,7 @@ int prib_acc_compute(prib_ctx *c) {
   CU(cudaEventRecord(c->evk0, c->stream));
   // entries the kernels never write (acc tail, cond head) must read 0: raccess.cpp:487-488
   CU(cudaMemsetAsync(c->d_out, 0, (size_t)std::max<long long>(c->out_floats, 1) * sizeof(float), c->stream));
+  CU(cudaMemsetAsync(c->d_bad, 0, sizeof(int32_t), c->stream));
   std::vector<int> flagged;
   for (size_t bi = 0; bi < c->n_batches; ++bi) {
     const Batch &b = c->batches[bi];
@@ -1189,8 +1228,12 @@ int prib_acc_fetch(prib_ctx *c, float *out, const int64_t *acc_off, const int64_
     CU(cudaMemcpyAsync(dst, c->d_out, (size_t)c->out_floats * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaEventRecord(c->ev1, c->stream));
   }
+  CU(cudaMemcpyAsync(c->h_bad, c->d_bad, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
   if (settle_kernel_time(c) != PRIB_OK) return PRIB_ECUDA;
+  if (*c->h_bad != 0)
+    return fail(PRIB_ENUMERIC, std::to_string(*c->h_bad) + " accessibility value(s) are not finite: the partition function "
+                               "left the double range (span too wide for this sequence); nothing was written");
   if (c->out_floats > 0) {
     float ms = 0;
     CU(cudaEventElapsedTime(&ms, c->ev0, c->ev1));

@@ -28,6 +28,13 @@
 #pragma once
 #include "acc_core.h"
 
+// 1 = the FP32 tile kernels evaluate the generic interior-loop sums by the centre-line chain (below); needs 8 more
+// shared-memory rows and ~54 more registers per thread, which forces a narrower tile — measured on B200: no net gain
+// (DESIGN.md §8), so the product build leaves it off; tests/hostemu builds with 1 to keep the formulation tested.
+#ifndef PRIB_CHAIN
+#define PRIB_CHAIN 0
+#endif
+
 namespace prib {
 
 enum {
@@ -38,7 +45,8 @@ enum {
   kRingSE = 8,
   kRingMu = 4,     // Alpha/Beta_multi and _multi2: the previous row is read, 4 slots leave 3 steps of slack between
                    // neighbouring warps (the kernels synchronise warp to warp, not CTA-wide)
-  kTileRows = 88,  // shared-memory rows of TC reals per CTA (both passes)
+  kXchRows = 2 * 4, // generic-loop sums handed from the centre-line chain to the column threads, double buffered
+  kTileRows = 88 + (PRIB_CHAIN ? kXchRows : 0),  // shared-memory rows of TC reals per CTA (both passes)
   kTilePad = 64,   // zeroed reals in front of the rings: the outside stencils look up to 33 columns to the left
   kOutBaseLead = 2,  // outside pass: base codes staged in shared memory start 2 columns left of the tile ...
   kOutBaseTail = 8,  // ... and reach W + 4 columns past its right edge (s[d + 3] of the last column)
@@ -128,7 +136,7 @@ struct Tile {
 
   // ---- shared-memory carve-up (same kTileRows rows for both passes; base points past the zero pad) ----
   struct InSmem {
-    real *stemI, *stemB, *stem, *se, *mu, *m2;
+    real *stemI, *stemB, *stem, *se, *mu, *m2, *xch;
     const uint8_t *S;  // bases of local columns 0 .. TC+3
   };
   static PRIB_HD InSmem carve_in(real *base, int TC, const uint8_t *S) {
@@ -139,11 +147,12 @@ struct Tile {
     s.se = s.stem + kRingStem * TC;
     s.mu = s.se + kRingSE * TC;
     s.m2 = s.mu + kRingMu * TC;
+    s.xch = s.m2 + kRingMu * TC;
     s.S = S;
     return s;
   }
   struct OutSmem {
-    real *stemO, *stemB, *stem, *mu, *m2;
+    real *stemO, *stemB, *stem, *mu, *m2, *xch;
     const uint8_t *S;  // bases of global columns g0 - H - kOutBaseLead .. (TC + W + kOutBaseTail of them): S[kOutBaseLead + t] = column of thread t
   };
   static PRIB_HD OutSmem carve_out(real *base, int TC, const uint8_t *S) {
@@ -154,7 +163,53 @@ struct Tile {
     s.stem = s.stemB + kRingOut * TC;
     s.mu = s.stem + kRingStem * TC;
     s.m2 = s.mu + kRingMu * TC;
+    s.xch = s.m2 + kRingMu * TC;
     return s;
+  }
+
+  // ---------------------------------------------------------------------------------------------
+  // Centre-line chain for the generic interior-loop sums (FP32 engine).
+  //
+  // For a target cell (i, j) and loop size s the deep steps need the row sum
+  //     H_s(i, j) = sum over u1 = 1 .. s-1 of cg[|2 u1 - s|] * X[r][i + u1]        (r = source row, X = the ...I / ...O ring)
+  // The cell (i - 1, j + 1) with loop size s + 2 reads the SAME source row, the same elements with the same
+  // coefficients (u1 and u2 both grow by one, |u1 - u2| stays), plus the two new end elements u1 = 1 and u1 = s + 1:
+  //     H_{s+2}(i - 1, j + 1) = H_s(i, j) + cg[min(s, 6)] * (two end elements).
+  // So a thread that follows one CENTRE LINE (cells (x, d), (x - 1, d + 2), ... in the inside pass; (x, d),
+  // (x + 1, d - 2), ... in the outside pass) keeps the 27 running row sums of each span parity in registers and pays
+  // 2 loads + 2 flops per (target, loop size) instead of s - 1 of each: ~60 loads + ~100 flops per cell instead of
+  // ~130 loads + ~520 FMA slots with the time-tiled direct sums.  All terms are positive, so the chained sums carry no
+  // cancellation; the 2x2 loop (s = 4, u1 = 2) is excluded from the target's sum but kept in the chain state.
+  // Thread tau owns the centre line of column tau - floor(d / 2) (inside) / tau + floor((W + 1 - d) / 2) (outside);
+  // every exact cell of the rectangular tile has its centre thread inside the CTA.  The finished sums gs[k] go to the
+  // column-mapped shallow steps through a double-buffered [kTT][TC] exchange array in shared memory.
+  // ---------------------------------------------------------------------------------------------
+  enum { kChainN = kMaxLoop - 4 + 1 };  // loop sizes 4 .. 30
+  struct Chain {
+    real f[2][kChainN];  // [parity of the target's step][s - 4]
+  };
+  static PRIB_HD void clear(Chain &ch) {
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int b = 0; b < kChainN; ++b) ch.f[a][b] = 0;
+  }
+  // e[u1] = ring element of the loop with left strand u1 (DIR = +1: inside, column x + u1; DIR = -1: outside, column
+  // x - 1 - u1, the caller passes e = row + x - 1); returns H_s and updates the chain state
+  template <int s, int FILE_, int DIR>
+  static PRIB_HD real chain_step(const real *e, const real *cg, Chain &ch) {
+    real v;
+    if constexpr (s == 4) {
+      v = cg[2] * (e[DIR * 1] + e[DIR * 3]);
+      ch.f[FILE_][0] = v + cg[0] * e[DIR * 2];
+    } else if constexpr (s == 5) {
+      v = cg[3] * (e[DIR * 1] + e[DIR * 4]) + cg[1] * (e[DIR * 2] + e[DIR * 3]);
+      ch.f[FILE_][1] = v;
+    } else {
+      v = ch.f[FILE_][s - 6] + cg[s - 2 < 6 ? s - 2 : 6] * (e[DIR * 1] + e[DIR * (s - 1)]);
+      ch.f[FILE_][s - 4] = v;
+    }
+    return v;
   }
 
   // One source row of the inside stencils (row d0 - S of the Alpha_stemI / Alpha_stemB rings) for all kTT targets;
@@ -233,26 +288,9 @@ struct Tile {
     if constexpr (S < kMaxLoop) in_rows<S + 1, TCC>(sm, TC, t, d0, cf, bu, g0, g1, g2, g3, g4, g5, g6, gs, bs);
   }
 
-  // ---------------------------------------------------------------------------------------------
-  // inside, deep step: thread t = local column t; targets are the cells (i, i + d0 + k), k = 0..kTT-1.
-  //   gs[k] = generic interior loops of Alpha_stemend (raccess.cpp:201-215, 808-812) as a stencil over the
-  //           Alpha_stemI ring: source row d0 - s serves target k with loop size s + k;
-  //   bs[k] = bulges of length >= 4 (:788-795) over the Alpha_stemB ring, same rows;
-  //   mb[k] = Alpha_multibif (:131-143) from the per-CTA scratch rows scrM1 / scrM2 ([(W+4)][TC]).
-  // Only rows <= d0 - 1 are read, so all kTT targets are legal at once.  TCC: compile-time tile width
-  // (0 = ge.TC at run time, host emulation): every ring row offset becomes an immediate.
-  // ---------------------------------------------------------------------------------------------
-  template <int TCC = 0>
-  static PRIB_HD void inside_deep(const ST &T, const Geo &ge, const InSmem &sm, const real *scrM1, const real *scrM2,
-                                  int t, int d0, real (&gs)[kTT], real (&mb)[kTT], real (&bs)[kTT]) {
-    const int TC = TCC > 0 ? TCC : ge.TC;
-    const real *cf = K::cf_tab(T), *bu = K::bulge_tab(T);
-    const real g0 = T.cg[0], g1 = T.cg[1], g2 = T.cg[2], g3 = T.cg[3], g4 = T.cg[4], g5 = T.cg[5], g6 = T.cg[6];
-#pragma unroll
-    for (int k = 0; k < kTT; ++k) gs[k] = mb[k] = bs[k] = 0;
-    in_rows<1, TCC>(sm, TC, t, d0, cf, bu, g0, g1, g2, g3, g4, g5, g6, gs, bs);
-    // multibif: mb[k] = sum over m = 5 .. d0+k-5 of multi1[m][t] * multi2[d0+k-m][t+m]; a multi1 element
-    // serves all kTT targets.  Two running pointers, every other offset is an immediate.
+  // multibif: mb[k] = sum over m = 5 .. d0+k-5 of multi1[m][t] * multi2[d0+k-m][t+m]; a multi1 element
+  // serves all kTT targets.  Two running pointers, every other offset is an immediate.
+  static PRIB_HD void in_bif_all(const real *scrM1, const real *scrM2, int TC, int t, int d0, real (&mb)[kTT]) {
     {
       const real *pa = scrM1 + 5 * TC + t;                       // multi1[m][t]
       const real *pb = scrM2 + (long long)(d0 - 5) * TC + t + 5;  // multi2[d0 - m][t + m]; target k: pb[k * TC]
@@ -299,6 +337,81 @@ struct Tile {
   }
 
   // ---------------------------------------------------------------------------------------------
+  // inside, deep step: thread t = local column t; targets are the cells (i, i + d0 + k), k = 0..kTT-1.
+  //   gs[k] = generic interior loops of Alpha_stemend (raccess.cpp:201-215, 808-812) as a stencil over the
+  //           Alpha_stemI ring: source row d0 - s serves target k with loop size s + k;
+  //   bs[k] = bulges of length >= 4 (:788-795) over the Alpha_stemB ring, same rows;
+  //   mb[k] = Alpha_multibif (:131-143) from the per-CTA scratch rows scrM1 / scrM2 ([(W+4)][TC]).
+  // Only rows <= d0 - 1 are read, so all kTT targets are legal at once.  TCC: compile-time tile width
+  // (0 = ge.TC at run time, host emulation): every ring row offset becomes an immediate.
+  // ---------------------------------------------------------------------------------------------
+  template <int TCC = 0>
+  static PRIB_HD void inside_deep(const ST &T, const Geo &ge, const InSmem &sm, const real *scrM1, const real *scrM2,
+                                  int t, int d0, real (&gs)[kTT], real (&mb)[kTT], real (&bs)[kTT]) {
+    const int TC = TCC > 0 ? TCC : ge.TC;
+    const real *cf = K::cf_tab(T), *bu = K::bulge_tab(T);
+    const real g0 = T.cg[0], g1 = T.cg[1], g2 = T.cg[2], g3 = T.cg[3], g4 = T.cg[4], g5 = T.cg[5], g6 = T.cg[6];
+#pragma unroll
+    for (int k = 0; k < kTT; ++k) gs[k] = mb[k] = bs[k] = 0;
+#if defined(PRIB_EXP_NODEEP)
+    if (d0 == 1000)
+#endif
+    in_rows<1, TCC>(sm, TC, t, d0, cf, bu, g0, g1, g2, g3, g4, g5, g6, gs, bs);
+    in_bif_all(scrM1, scrM2, TC, t, d0, mb);
+  }
+
+  // One source row (d0 - S) in the chain formulation: generic sums through chain_step (thread = centre line, column
+  // xb - ((PAR + k) >> 1) for target k), bulges >= 4 as in in_rows (thread = column t).  Rows are walked from S = 30
+  // DOWN to 1: target k reads the chain entry s - 2 that target k - 2 (or the previous group) left for the same row.
+  template <int S, int K, int PAR>
+  static PRIB_HD void in_chain_cell(const real *rowI, int xb, const real *cf, const real *cg, Chain &ch, real (&gs)[kTT]) {
+    constexpr int s = S + K;
+    if constexpr (s >= 4 && s <= kMaxLoop) {
+      const real v = chain_step<s, (PAR + K) & 1, 1>(rowI + xb - ((PAR + K) >> 1), cg, ch);
+      gs[K] += cf[s] * v;
+    }
+  }
+  template <int S, int PAR, int TCC>
+  static PRIB_HD void in_chain_rows(const InSmem &sm, int TC, int t, int xb, int d0, const real *cf, const real *bu,
+                                    const real *cg, Chain &ch, real (&gs)[kTT], real (&bs)[kTT]) {
+    if (d0 - S >= 5) {  // rows below span 5 hold no stems (their chain entries are still zero)
+      const real *rowI = sm.stemI + ((d0 - S) & (kRingIn - 1)) * (TCC > 0 ? TCC : TC);
+      in_chain_cell<S, 0, PAR>(rowI, xb, cf, cg, ch, gs);
+      in_chain_cell<S, 1, PAR>(rowI, xb, cf, cg, ch, gs);
+      in_chain_cell<S, 2, PAR>(rowI, xb, cf, cg, ch, gs);
+      in_chain_cell<S, 3, PAR>(rowI, xb, cf, cg, ch, gs);
+      const real *rowB = rowI + kRingIn * (TCC > 0 ? TCC : TC) + t;
+      const real b0 = rowB[0];
+#pragma unroll
+      for (int k = 0; k < kTT; ++k)
+        if (S + k >= 4 && S + k <= kMaxLoop) bs[k] += bu[S + k] * (rowB[S + k] + b0);
+    }
+    if constexpr (S > 1) in_chain_rows<S - 1, PAR, TCC>(sm, TC, t, xb, d0, cf, bu, cg, ch, gs, bs);
+  }
+
+  // Deep step in the chain formulation; PAR = d0 & 1 (the same for every group of a kernel launch).  The generic sums
+  // of the kTT targets are written to xch[k * TC + column] (one group's half of the exchange array); mb / bs come back
+  // to the caller as in inside_deep.
+  template <int PAR, int TCC = 0>
+  static PRIB_HD void inside_deep_chain(const ST &T, const Geo &ge, const InSmem &sm, const real *scrM1,
+                                        const real *scrM2, int t, int d0, Chain &ch, real *xch, real (&mb)[kTT],
+                                        real (&bs)[kTT]) {
+    const int TC = TCC > 0 ? TCC : ge.TC;
+    const real *cf = K::cf_tab(T), *bu = K::bulge_tab(T), *cg = K::cg_tab(T);
+    real gs[kTT];
+#pragma unroll
+    for (int k = 0; k < kTT; ++k) gs[k] = mb[k] = bs[k] = 0;
+    const int xb = t - ((d0 - PAR) >> 1);
+    in_chain_rows<kMaxLoop, PAR, TCC>(sm, TC, t, xb, d0, cf, bu, cg, ch, gs, bs);
+#pragma unroll
+    for (int k = 0; k < kTT; ++k) {
+      const int x = xb - ((PAR + k) >> 1);
+      if (x >= 0) xch[k * TC + x] = gs[k];
+    }
+    in_bif_all(scrM1, scrM2, TC, t, d0, mb);
+  }
+
+  // ---------------------------------------------------------------------------------------------
   // inside, shallow step: finishes cell (i, i + d) of column t given its deep sums gs / mb.
   // ---------------------------------------------------------------------------------------------
   template <int TCC = 0, typename Hook = NoStepHook>
@@ -310,7 +423,11 @@ struct Tile {
     real stem = 0, stemI = 0, stemB = 0, stemD = 0, se = 0, mu = 0, m1 = 0, m2 = 0;
     const int smax = imin(kMaxLoop, d - 5);  // u1 + u2 <= smax keeps the inner span >= 5
     const int L = cs.L, i = cs.i, j = i + d;
+#if defined(PRIB_EXP_NOSHALLOW)
+    const bool live = i >= 0 && j <= L && t + d <= TC - 1 && d == 1000;
+#else
     const bool live = i >= 0 && j <= L && t + d <= TC - 1;
+#endif
     if (live) {
       const uint8_t *s = sm.S + t;
       const int si = s[0], si1 = s[1], sj = s[d], sj1 = s[d + 1];
@@ -388,9 +505,18 @@ struct Tile {
     sm.se[(d & (kRingSE - 1)) * TC + t] = se;
     sm.mu[(d & (kRingMu - 1)) * TC + t] = mu;
     sm.m2[(d & (kRingMu - 1)) * TC + t] = m2;
+#if defined(PRIB_SCR_BEFORE)
     scrM1[d * TC + t] = m1;
     scrM2[d * TC + t] = m2;
+#endif
     stores_done();
+#if !defined(PRIB_SCR_BEFORE)
+    // The multibranch scratch rows go to global memory AFTER the release of this step's progress counter: the first
+    // reader of row d is a deep step that waits for a LATER event of this warp (it reads rows <= its d0 - 2), and that
+    // event's release covers these stores; a release right behind them would wait for their L2 round trip every step.
+    scrM1[d * TC + t] = m1;
+    scrM2[d * TC + t] = m2;
+#endif
     // persistent outputs: owned columns only
 #if defined(PRIB_EXP_NOSTG)
     if (t < ge.TX && i >= 0 && j <= L && d == 1000) {
@@ -515,16 +641,11 @@ struct Tile {
     if constexpr (S < kMaxLoop + 2) out_rows<S + 1, TCC>(sm, TC, t, d0, slot_d0, W, bu, cf, g0, g1, g2, g3, g4, g5, g6, o);
   }
 
-  template <int TCC = 0>
-  static PRIB_HD void outside_deep(const Ctx &c, const ST &T, const Geo &ge, const OutSmem &sm, const real *scrBif,
-                                   int t, const ColState &cs, int d0, int slot_d0 /* = d0 % kRingOut */, OutDeep &o) {
-    const int TC = TCC > 0 ? TCC : ge.TC, W = c.W;
-    const real *bu = K::bulge_tab(T), *cf = K::cf_tab(T);
-    const real g0 = T.cg[0], g1 = T.cg[1], g2 = T.cg[2], g3 = T.cg[3], g4 = T.cg[4], g5 = T.cg[5], g6 = T.cg[6];
-#pragma unroll
-    for (int k = 0; k < kTT; ++k) o.gs[k] = o.bs[k] = o.bm1[k] = o.ks[k] = 0;
-    // stencils: source row d0 + s; target k: bulge length / loop size s + k - 2
-    out_rows<1, TCC>(sm, TC, t, d0, slot_d0, W, bu, cf, g0, g1, g2, g3, g4, g5, g6, o);
+  // Multiloop sums of the outside deep step (see outside_deep): bm1[k] and ks[k] from the per-CTA Beta_multibif
+  // scratch and the Alpha arrays in HBM.
+  static PRIB_HD void out_multi_all(const Ctx &c, const Geo &ge, const real *scrBif, int TC, int t, const ColState &cs,
+                                    int d0, OutDeep &o) {
+    const int W = c.W;
     // Multiloop sums.  Only cells strictly inside the sequence (p >= 1, q < L) use them (outside_shallow
     // ignores the sums of all others), and for those the term ranges of the kTT targets line up:
     //   bm1[k]: m = 5 .. min(L - q_k, W - d_k)  <=>  bif row d0 + s with s = m - k = 5 - k .. min(L - p, W) - d0
@@ -638,6 +759,70 @@ struct Tile {
     }
   }
 
+  template <int TCC = 0>
+  static PRIB_HD void outside_deep(const Ctx &c, const ST &T, const Geo &ge, const OutSmem &sm, const real *scrBif,
+                                   int t, const ColState &cs, int d0, int slot_d0 /* = d0 % kRingOut */, OutDeep &o) {
+    const int TC = TCC > 0 ? TCC : ge.TC, W = c.W;
+    const real *bu = K::bulge_tab(T), *cf = K::cf_tab(T);
+    const real g0 = T.cg[0], g1 = T.cg[1], g2 = T.cg[2], g3 = T.cg[3], g4 = T.cg[4], g5 = T.cg[5], g6 = T.cg[6];
+#pragma unroll
+    for (int k = 0; k < kTT; ++k) o.gs[k] = o.bs[k] = o.bm1[k] = o.ks[k] = 0;
+    // stencils: source row d0 + s; target k: bulge length / loop size s + k - 2
+    out_rows<1, TCC>(sm, TC, t, d0, slot_d0, W, bu, cf, g0, g1, g2, g3, g4, g5, g6, o);
+    out_multi_all(c, ge, scrBif, TC, t, cs, d0, o);
+  }
+
+  // One source row (d0 + S) of the outside pass in the chain formulation (see "Centre-line chain"): target k has
+  // span d0 - k and loop size S + k - 2; its centre-line thread sits at column xb + (k >> 1) (the groups start at
+  // W + 1 and have kTT = 4 spans, so the step parity of target k is k & 1).  Bulges as in out_rows (thread = column).
+  template <int S, int K>
+  static PRIB_HD void out_chain_cell(const real *rowO, int xb, const real *cf, const real *cg, Chain &ch, real (&gs)[kTT]) {
+    constexpr int s = S + K - 2;
+    if constexpr (s >= 4 && s <= kMaxLoop) {
+      const real v = chain_step<s, K & 1, -1>(rowO + xb + (K >> 1) - 1, cg, ch);
+      gs[K] += cf[s] * v;
+    }
+  }
+  template <int S, int TCC>
+  static PRIB_HD void out_chain_rows(const OutSmem &sm, int TC, int t, int xb, int d0, int slot_d0, int W, const real *bu,
+                                     const real *cf, const real *cg, Chain &ch, OutDeep &o) {
+    if (d0 + S <= W + 1) {  // rows above W + 1 do not exist (their chain entries are still zero)
+      const int slot = wrap_out(slot_d0 + S);
+      const real *rowO = sm.stemO + slot * (TCC > 0 ? TCC : TC);
+      out_chain_cell<S, 0>(rowO, xb, cf, cg, ch, o.gs);
+      out_chain_cell<S, 1>(rowO, xb, cf, cg, ch, o.gs);
+      out_chain_cell<S, 2>(rowO, xb, cf, cg, ch, o.gs);
+      out_chain_cell<S, 3>(rowO, xb, cf, cg, ch, o.gs);
+      const real *rowB = sm.stemB + slot * (TCC > 0 ? TCC : TC) + t - 1;
+      const real b0 = rowB[0];
+#pragma unroll
+      for (int k = 0; k < kTT; ++k) {
+        const int u = S + k - 2;
+        if (u >= 2 && u <= kMaxLoop) o.bs[k] += bu[u] * (rowB[-u] + b0);
+      }
+    }
+    if constexpr (S > 1) out_chain_rows<S - 1, TCC>(sm, TC, t, xb, d0, slot_d0, W, bu, cf, cg, ch, o);
+  }
+
+  // Deep step in the chain formulation: o.gs is written to xch[k * TC + column] instead of being returned.
+  template <int TCC = 0>
+  static PRIB_HD void outside_deep_chain(const Ctx &c, const ST &T, const Geo &ge, const OutSmem &sm, const real *scrBif,
+                                         int t, const ColState &cs, int d0, int slot_d0, Chain &ch, real *xch,
+                                         OutDeep &o) {
+    const int TC = TCC > 0 ? TCC : ge.TC, W = c.W;
+    const real *bu = K::bulge_tab(T), *cf = K::cf_tab(T), *cg = K::cg_tab(T);
+#pragma unroll
+    for (int k = 0; k < kTT; ++k) o.gs[k] = o.bs[k] = o.bm1[k] = o.ks[k] = 0;
+    const int xb = t + ((W + 1 - d0) >> 1);
+    out_chain_rows<kMaxLoop + 2, TCC>(sm, TC, t, xb, d0, slot_d0, W, bu, cf, cg, ch, o);
+#pragma unroll
+    for (int k = 0; k < kTT; ++k) {
+      const int x = xb + (k >> 1);
+      if (x < TC) xch[k * TC + x] = o.gs[k];
+    }
+    out_multi_all(c, ge, scrBif, TC, t, cs, d0, o);
+  }
+
   template <int TCC = 0, typename Hook = NoStepHook>
   static PRIB_HD void outside_shallow(const Ctx &c, const ST &T, const Geo &ge, const OutSmem &sm, real *scrBif, int t,
                                       const ColState &cs, int d, int slot_d /* = d % kRingOut */, real gs, real bs,
@@ -649,7 +834,11 @@ struct Tile {
     const long long g = ge.g0 - ge.H + t;
     const int L = cs.L, p = cs.i, q = p + d;
     // a halo cell is exact iff its end reaches the owned region (all its super-intervals are in the tile)
+#if defined(PRIB_EXP_NOSHALLOW)
+    const bool live = p >= 0 && q <= L && t + d >= ge.H && d == 1000;
+#else
     const bool live = p >= 0 && q <= L && t + d >= ge.H;
+#endif
     if (live) {
       const uint8_t *s = sm.S + kOutBaseLead + t;  // staged for columns g0-H-2 .. g0-H+TC+W+5 (the right end q = p + d lies beyond the tile)
       const int sp = s[0], sp1 = s[1], sq_ = s[d], sq1 = s[d + 1];
@@ -726,8 +915,13 @@ struct Tile {
     sm.stem[(d & (kRingStem - 1)) * TC + t] = bstem;
     sm.mu[(d & (kRingMu - 1)) * TC + t] = bmulti;
     sm.m2[(d & (kRingMu - 1)) * TC + t] = bmulti2;
+#if defined(PRIB_SCR_BEFORE)
     scrBif[d * TC + t] = bmbif;
+#endif
     stores_done();
+#if !defined(PRIB_SCR_BEFORE)
+    scrBif[d * TC + t] = bmbif;  // after the release, see inside_shallow (deep steps read bif rows >= their d0 + 2)
+#endif
 #if defined(PRIB_EXP_NOSTG)
     if (t >= ge.H && p >= 0 && q <= L && d == 1000) {
 #else

@@ -18,6 +18,7 @@
 
 using namespace prib;
 static int g_poison = 0;
+static int g_chain = 0;  // 1: the tile emulation uses the centre-line chain formulation of the deep steps (FP32 device engine)
 
 namespace {
 
@@ -103,6 +104,7 @@ void run_dp_tiled(EmuT<real> &e, int TC) {
   struct InDeep { real gs[kTT], mb[kTT], bs[kTT]; };
   std::vector<InDeep> din(TC);
   std::vector<typename TL::OutDeep> dout(TC);
+  std::vector<typename TL::Chain> chains(TC);
   real *scrM1 = scr.data(), *scrM2 = scr.data() + (size_t)(W + 4) * TC;
   for (long long tile = 0; tile < ntiles; tile++) {
     typename TL::Geo ge{tile * TX, TC, TX, H};
@@ -111,13 +113,20 @@ void run_dp_tiled(EmuT<real> &e, int TC) {
     for (int k = 0; k < TC + 8; k++) sS[k] = (ge.g0 + k < c.NC) ? c.S[ge.g0 + k] : 0;
     for (int t = 0; t < TC; t++) TL::col_state(c, ge.g0 + t, cs[t]);
     typename TL::InSmem sm = TL::carve_in(base, TC, sS.data());
-    for (int d0 = dfirst; d0 <= W + 1; d0 += kTT) {
-      for (int t = 0; t < TC; t++) TL::template inside_deep<0>(*c.T, ge, sm, scrM1, scrM2, t, d0, din[t].gs, din[t].mb, din[t].bs);
+    for (auto &ch : chains) TL::clear(ch);
+    int grp = 0;
+    for (int d0 = dfirst; d0 <= W + 1; d0 += kTT, ++grp) {
+      real *xch = sm.xch + (size_t)(grp & 1) * kTT * TC;
+      for (int t = 0; t < TC; t++) {
+        if (!g_chain) TL::template inside_deep<0>(*c.T, ge, sm, scrM1, scrM2, t, d0, din[t].gs, din[t].mb, din[t].bs);
+        else if (dfirst & 1) TL::template inside_deep_chain<1, 0>(*c.T, ge, sm, scrM1, scrM2, t, d0, chains[t], xch, din[t].mb, din[t].bs);
+        else TL::template inside_deep_chain<0, 0>(*c.T, ge, sm, scrM1, scrM2, t, d0, chains[t], xch, din[t].mb, din[t].bs);
+      }
       for (int k = 0; k < kTT; k++) {
         if (d0 + k < kTurn) continue;
         for (int t = 0; t < TC; t++)
-          TL::template inside_shallow<0>(c, *c.T, ge, sm, scrM1, scrM2, t, cs[t], d0 + k, din[t].gs[k], din[t].mb[k],
-                                         din[t].bs[k]);
+          TL::template inside_shallow<0>(c, *c.T, ge, sm, scrM1, scrM2, t, cs[t], d0 + k,
+                                         g_chain ? xch[(size_t)k * TC + t] : din[t].gs[k], din[t].mb[k], din[t].bs[k]);
       }
     }
   }
@@ -137,16 +146,22 @@ void run_dp_tiled(EmuT<real> &e, int TC) {
       sSo[k] = (col >= 0 && col < c.NC) ? c.S[col] : 0;
     }
     typename TL::OutSmem sm = TL::carve_out(base, TC, sSo.data());
-    for (int d0 = W + 1; d0 >= dfirst + kTT - 1; d0 -= kTT) {
-      for (int t = 0; t < TC; t++)
-        TL::template outside_deep<0>(c, *c.T, ge, sm, scr.data(), t, cs[t], d0, ((d0 % kRingOut) + kRingOut) % kRingOut,
-                                     dout[t]);
+    for (auto &ch : chains) TL::clear(ch);
+    int grp = 0;
+    for (int d0 = W + 1; d0 >= dfirst + kTT - 1; d0 -= kTT, ++grp) {
+      real *xch = sm.xch + (size_t)(grp & 1) * kTT * TC;
+      const int slot0 = ((d0 % kRingOut) + kRingOut) % kRingOut;
+      for (int t = 0; t < TC; t++) {
+        if (!g_chain) TL::template outside_deep<0>(c, *c.T, ge, sm, scr.data(), t, cs[t], d0, slot0, dout[t]);
+        else TL::template outside_deep_chain<0>(c, *c.T, ge, sm, scr.data(), t, cs[t], d0, slot0, chains[t], xch, dout[t]);
+      }
       for (int k = 0; k < kTT; k++) {
         const int d = d0 - k;
         if (d < kTurn) continue;
         for (int t = 0; t < TC; t++)
-          TL::template outside_shallow<0>(c, *c.T, ge, sm, scr.data(), t, cs[t], d, d % kRingOut, dout[t].gs[k],
-                                          dout[t].bs[k], dout[t].bm1[k], dout[t].ks[k]);
+          TL::template outside_shallow<0>(c, *c.T, ge, sm, scr.data(), t, cs[t], d, d % kRingOut,
+                                          g_chain ? xch[(size_t)k * TC + t] : dout[t].gs[k], dout[t].bs[k], dout[t].bm1[k],
+                                          dout[t].ks[k]);
       }
     }
   }
@@ -259,6 +274,8 @@ extern "C" {
 // poison = 1: fill every DP array with NaN before the run (emulates a device that does not zero its state):
 // any read of a never-written cell then shows up in the output
 void hostemu_set_poison(int on) { g_poison = on; }
+// chain = 1: deep steps in the centre-line chain formulation (what the FP32 device engine runs)
+void hostemu_set_chain(int on) { g_chain = on; }
 
 // FP32 band arithmetic with span scaling; flags_out[k] != 0 marks sequences whose stored values left
 // the safe range (the product re-runs those in FP64).

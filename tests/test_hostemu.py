@@ -130,3 +130,43 @@ def test_no_kernel_reads_a_cell_it_did_not_write(emu, W, TC, delta):
     assert np.all(np.isfinite(got))
     assert np.array_equal(ref.view(np.uint32), got.view(np.uint32))
     assert np.all(np.isfinite(got32))
+
+
+@pytest.fixture
+def chain_mode(emu):
+    emu.lib.hostemu_set_chain(1)
+    yield emu
+    emu.lib.hostemu_set_chain(0)
+
+
+@pytest.mark.parametrize("W,TC,delta", [(70, 352, 5), (70, 512, 5), (20, 64, 2), (21, 96, 5), (150, 352, 10), (71, 256, 5)])
+def test_centre_line_chain_matches_direct_sums(emu, chain_mode, W, TC, delta):
+    """The chain formulation of the generic interior-loop sums (acc_tile.h, "Centre-line chain": H_{s+2} of the cell
+    grown by one base on both sides = H_s + two end elements) evaluates the same terms as the time-tiled direct sums
+    in another order: in double the float outputs agree to rounding; W = 21 / 71 exercise odd group starts."""
+    got, _, _ = _tiled(emu.lib, _MIX, W, delta, TC)
+    emu.lib.hostemu_set_chain(0)
+    ref, _, _ = _tiled(emu.lib, _MIX, W, delta, TC)
+    assert np.all(np.isfinite(got))
+    assert np.abs(ref - got).max() < 1e-6
+    ulp = np.abs(ref.view(np.int32).astype(np.int64) - got.view(np.int32).astype(np.int64))
+    assert ulp.max() <= 2 and (ulp > 0).mean() < 0.01, (ulp.max(), (ulp > 0).mean())
+
+
+def test_centre_line_chain_fp32_and_poison(emu, chain_mode):
+    """FP32 span-scaled arithmetic with the chain (the device's fast engine), on NaN-poisoned state."""
+    emu.lib.hostemu_set_chain(0)
+    ref, _, lens = _tiled(emu.lib, _MIX, 70, 5, None)
+    emu.lib.hostemu_set_chain(1)
+    emu.lib.hostemu_set_poison(1)
+    try:
+        got, flags, _ = _tiled(emu.lib, _MIX, 70, 5, 512, scale=(0.3, 4.0, 16.0), f32=True)
+    finally:
+        emu.lib.hostemu_set_poison(0)
+    off = 0
+    for k, L in enumerate(lens):
+        seg = slice(off, off + 2 * int(L))
+        off += 2 * int(L)
+        if not flags[k]:
+            assert np.abs(ref[seg] - got[seg]).max() < 6e-6, k
+    assert flags[len(_MIX) - 1] == 1 and flags[0] == 0 and flags[1] == 0
