@@ -553,7 +553,7 @@ struct prib_ctx {
   cudaStream_t own_stream = nullptr, stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk0 = nullptr, evk1 = nullptr;
   cudaEvent_t evp[PRIB_NUM_PHASES + 1] = {};
-  bool phases_pending = false, kernel_timed = true;
+  bool phases_pending = false, kernel_timed = true, stage_timed = true;
   Engine<float> e32;
   Engine<double> e64;
   ExactEngine *ex = nullptr;  // mode 2: the reference's own arithmetic (acc_exact.h)
@@ -566,15 +566,21 @@ struct prib_ctx {
   long long state_budget = 0;     // upper bound fixed at create time (batches are sized for it)
   // staged work
   std::vector<Batch> batches;
-  std::vector<std::string> seqs;  // host copies (needed to re-run flagged sequences in double)
+  std::vector<int32_t> seq_len;     // staged sequences, caller order
+  std::vector<long long> seq_pos;   // offset of each sequence's bytes in h_arena
+  // One page-locked arena holds the raw bytes of every staged sequence in BATCH order (longest first), so each batch
+  // goes to the device straight from it: one host copy per sequence, no per-batch staging buffer and hence no stream
+  // synchronisation between batches.  Copies for the FP64 re-run of flagged sequences are appended behind.
+  unsigned char *h_arena = nullptr;
+  size_t h_arena_cap = 0, h_arena_used = 0;
+  unsigned char *h_meta = nullptr;  // page-locked per-batch offset arrays (bump-allocated per stage)
+  size_t h_meta_cap = 0, h_meta_used = 0;
   size_t n_batches = 0;           // batches[0..n_batches) are live; the rest keep their buffers for reuse
   float *d_out = nullptr;
   long long out_floats = 0, out_cap = 0;
   bool staged = false, computed = false;
   float *h_stage = nullptr;
   long long h_stage_floats = 0;
-  unsigned char *h_in = nullptr;  // pinned staging of one batch's inputs
-  size_t h_in_cap = 0;
   int32_t *h_flags = nullptr;
   long long h_flags_cap = 0;
   int32_t *d_bad = nullptr;       // number of non-finite outputs of the current compute (finalize_position)
@@ -609,7 +615,8 @@ void free_batches(prib_ctx *c) {
   c->d_out = nullptr;
   c->out_cap = 0;
   c->out_floats = 0;
-  c->seqs.clear();
+  c->seq_len.clear();
+  c->seq_pos.clear();
   c->staged = c->computed = false;
 }
 
@@ -686,51 +693,54 @@ int ensure_state(prib_ctx *c, long long bytes) {
   return PRIB_OK;
 }
 
-// Builds the device-side layout of one batch.  ids: caller's indices; offsets absolute into d_out.
+// Grows a page-locked buffer, keeping the first `keep` bytes.  The stream is drained first: an asynchronous copy may
+// still read the old block.
+int grow_pinned(prib_ctx *c, unsigned char **buf, size_t *cap, size_t keep, size_t need) {
+  if (need <= *cap) return PRIB_OK;
+  CU(cudaStreamSynchronize(c->stream));
+  unsigned char *nb = nullptr;
+  const size_t want = need + need / 8 + 4096;
+  CU(cudaMallocHost(&nb, want));
+  if (*buf && keep) std::memcpy(nb, *buf, keep);
+  if (*buf) cudaFreeHost(*buf);
+  *buf = nb;
+  *cap = want;
+  return PRIB_OK;
+}
+
+// Builds the device-side layout of one batch.  ids: caller's indices (their bytes lie back to back in the arena,
+// starting at raw_begin); offsets absolute into d_out.  Everything is enqueued on the stream; nothing waits.
 int make_batch(prib_ctx *c, const std::vector<int> &ids, const std::vector<long long> &acc_off,
-               const std::vector<long long> &cond_off, Batch &b) {
+               const std::vector<long long> &cond_off, Batch &b, size_t raw_begin) {
   b.ids = ids;
   b.acc_off = acc_off;
   b.cond_off = cond_off;
   b.n = (int)ids.size();
-  // host side: offsets only; the raw bytes go up as they are (pinned staging), the device builds the layout
+  // host side: offsets only; the raw bytes go up as they are, the device builds the layout
   const size_t n1 = (size_t)std::max(b.n, 1);
-  std::vector<int32_t> sl(n1);
-  std::vector<long long> so(n1), ro(n1 + 1);
+  // page-locked block of this batch: [seq_off | raw_off (n + 1) | acc_off | cond_off | seq_len]
+  const size_t need = (n1 * 4 + 1) * 8 + n1 * 4 + 16;
+  if (c->h_meta_used + need > c->h_meta_cap)
+    return fail(PRIB_ECUDA, "internal: batch metadata arena too small");
+  long long *h_so = reinterpret_cast<long long *>(c->h_meta + c->h_meta_used);
+  c->h_meta_used += (need + 15) / 16 * 16;
+  long long *h_ro = h_so + n1, *h_ao = h_ro + n1 + 1, *h_co = h_ao + n1;
+  int32_t *h_sl = reinterpret_cast<int32_t *>(h_co + n1);
   b.nt = 0;
   long long g = kPad;
   for (int k = 0; k < b.n; k++) {
-    sl[k] = (int32_t)c->seqs[ids[k]].size();
-    so[k] = g;
-    ro[k] = b.nt;
-    g += layout_columns(sl[k]);
-    b.nt += sl[k];
-  }
-  ro[b.n] = b.nt;
-  b.NC = (g + kPad + 31) / 32 * 32;
-  const long long raw_bytes = std::max<long long>(b.nt, 1);
-  // one pinned staging block: [raw | seq_len | seq_off | raw_off | acc_off | cond_off]
-  const size_t need = (size_t)((raw_bytes + 15) / 16 * 16) + n1 * 4 + 16 + (n1 * 4 + 1) * 8;
-  if (c->h_in_cap < need) {
-    if (c->h_in) cudaFreeHost(c->h_in);
-    c->h_in = nullptr;
-    c->h_in_cap = 0;
-    CU(cudaMallocHost(&c->h_in, need));
-    c->h_in_cap = need;
-  }
-  unsigned char *h_raw = c->h_in;
-  long long *h_so = reinterpret_cast<long long *>(c->h_in + (raw_bytes + 15) / 16 * 16);
-  long long *h_ro = h_so + n1, *h_ao = h_ro + n1 + 1, *h_co = h_ao + n1;
-  int32_t *h_sl = reinterpret_cast<int32_t *>(h_co + n1);
-  for (int k = 0; k < b.n; k++) {
-    std::memcpy(h_raw + ro[k], c->seqs[ids[k]].data(), (size_t)sl[k]);
-    h_so[k] = so[k];
-    h_ro[k] = ro[k];
+    const int32_t L = c->seq_len[ids[k]];
+    h_sl[k] = L;
+    h_so[k] = g;
+    h_ro[k] = b.nt;
     h_ao[k] = acc_off[k];
     h_co[k] = cond_off[k];
-    h_sl[k] = sl[k];
+    g += layout_columns(L);
+    b.nt += L;
   }
   h_ro[b.n] = b.nt;
+  b.NC = (g + kPad + 31) / 32 * 32;
+  const long long raw_bytes = std::max<long long>(b.nt, 1);
   if (b.NC > b.cap_cols) {
     cudaFree(b.d_S);
     cudaFree(b.d_col_seq);
@@ -766,36 +776,39 @@ int make_batch(prib_ctx *c, const std::vector<int> &ids, const std::vector<long 
     CU(cudaMalloc(&b.d_raw_off, (n1 + 1) * sizeof(long long)));
     b.cap_seqs = (long long)n1;
   }
-  CU(cudaEventRecord(c->ev0, c->stream));
-  CU(cudaMemcpyAsync(b.d_raw, h_raw, (size_t)raw_bytes, cudaMemcpyHostToDevice, c->stream));
+  if (b.nt > 0)
+    CU(cudaMemcpyAsync(b.d_raw, c->h_arena + raw_begin, (size_t)b.nt, cudaMemcpyHostToDevice, c->stream));
   CU(cudaMemcpyAsync(b.d_seq_len, h_sl, (size_t)b.n * 4, cudaMemcpyHostToDevice, c->stream));
   CU(cudaMemcpyAsync(b.d_seq_off, h_so, (size_t)b.n * 8, cudaMemcpyHostToDevice, c->stream));
   CU(cudaMemcpyAsync(b.d_raw_off, h_ro, (size_t)(b.n + 1) * 8, cudaMemcpyHostToDevice, c->stream));
   CU(cudaMemcpyAsync(b.d_acc_off, h_ao, (size_t)b.n * 8, cudaMemcpyHostToDevice, c->stream));
   CU(cudaMemcpyAsync(b.d_cond_off, h_co, (size_t)b.n * 8, cudaMemcpyHostToDevice, c->stream));
-  CU(cudaEventRecord(c->ev1, c->stream));
   k_build_layout<<<(unsigned)((b.NC + 255) / 256), 256, 0, c->stream>>>(b.NC, b.n, b.d_seq_off, b.d_seq_len,
                                                                          b.d_raw_off, b.d_raw, b.d_S, b.d_col_seq);
   CU(cudaGetLastError());
-  CU(cudaStreamSynchronize(c->stream));  // the pinned staging block is reused by the next batch
-  float ms = 0;
-  CU(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
-  c->cnt.h2d_ms += ms;
-  c->cnt.h2d_bytes += raw_bytes + (long long)b.n * 36 + 8;
+  c->cnt.h2d_bytes += b.nt + (long long)b.n * 36 + 8;
   c->cnt.kernel_launches += 1;
   return PRIB_OK;
 }
 
-// Greedy partition of `order` (already longest-first) into batches that fit `max_cols` columns.
+// Greedy partition of `order` (already longest-first; the bytes of order[k] lie in the arena in this order, starting
+// at raw_begin) into batches that fit `max_cols` columns.
 int partition(prib_ctx *c, const std::vector<int> &order, long long max_cols, const std::vector<long long> &acc_abs,
-              const std::vector<long long> &cond_abs, std::vector<Batch> &out, size_t *n_live) {
+              const std::vector<long long> &cond_abs, std::vector<Batch> &out, size_t *n_live, size_t raw_begin) {
   size_t pos = 0, used = 0;
+  {  // metadata arena for all batches of this partition (a bound: every batch pads to 16 bytes and has n + 1 offsets)
+    const size_t need = c->h_meta_used + order.size() * 100 + 4096;
+    int rc = grow_pinned(c, &c->h_meta, &c->h_meta_cap, c->h_meta_used, need);
+    if (rc != PRIB_OK) return rc;
+  }
   while (pos < order.size()) {
     std::vector<int> ids;
     std::vector<long long> ao, co;
     long long cols = 2 * kPad;
-    while (pos < order.size() && cols + layout_columns((int)c->seqs[order[pos]].size()) <= max_cols) {
-      cols += layout_columns((int)c->seqs[order[pos]].size());
+    size_t bytes = 0;
+    while (pos < order.size() && cols + layout_columns(c->seq_len[order[pos]]) <= max_cols) {
+      cols += layout_columns(c->seq_len[order[pos]]);
+      bytes += (size_t)c->seq_len[order[pos]];
       ids.push_back(order[pos]);
       ao.push_back(acc_abs[order[pos]]);
       co.push_back(cond_abs[order[pos]]);
@@ -804,8 +817,9 @@ int partition(prib_ctx *c, const std::vector<int> &order, long long max_cols, co
     if (ids.empty())
       return fail(PRIB_ECUDA, "sequence " + std::to_string(order[pos]) + " does not fit the device DP budget");
     if (used == out.size()) out.emplace_back();
-    int rc = make_batch(c, ids, ao, co, out[used]);
+    int rc = make_batch(c, ids, ao, co, out[used], raw_begin);
     if (rc != PRIB_OK) return rc;
+    raw_begin += bytes;
     ++used;
   }
   *n_live = used;
@@ -955,6 +969,12 @@ int setup_engine(prib_ctx *c, const ScaleSpec &spec, size_t smem_max, std::strin
 
 int settle_kernel_time(prib_ctx *c) {
   if (settle_phases(c) != PRIB_OK) return PRIB_ECUDA;
+  if (!c->stage_timed) {  // host-to-device copies + layout kernels of the last stage (events on the stream)
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, c->ev0, c->ev1) == cudaSuccess) c->cnt.h2d_ms += ms;
+    else cudaGetLastError();
+    c->stage_timed = true;
+  }
   if (!c->kernel_timed) {
     float ms = 0;
     CU(cudaEventElapsedTime(&ms, c->evk0, c->evk1));
@@ -1066,7 +1086,8 @@ void prib_acc_destroy(prib_ctx *c) {
   exact_destroy(c->ex);
   cudaFree(c->d_log);
   if (c->h_stage) cudaFreeHost(c->h_stage);
-  if (c->h_in) cudaFreeHost(c->h_in);
+  if (c->h_arena) cudaFreeHost(c->h_arena);
+  if (c->h_meta) cudaFreeHost(c->h_meta);
   if (c->h_flags) cudaFreeHost(c->h_flags);
   if (c->h_bad) cudaFreeHost(c->h_bad);
   cudaFree(c->d_bad);
@@ -1097,15 +1118,15 @@ int prib_acc_stage(prib_ctx *c, int32_t n, const char *const *seq, const int32_t
     if (layout_columns(len[k]) + 2 * kPad > std::min(max_cols, c->e64.max_cols))
       return fail(PRIB_ECUDA, "sequence " + std::to_string(k) + " does not fit the device DP budget");
   }
-  c->seqs.resize(n);
-  for (int k = 0; k < n; k++) c->seqs[k].assign(seq[k], (size_t)len[k]);
   // packed device output image: [acc L | cond L] per sequence in caller order
   std::vector<long long> acc_abs(n), cond_abs(n);
-  long long o = 0;
+  long long o = 0, total = 0;
+  c->seq_len.assign(len, len + n);
   for (int k = 0; k < n; k++) {
     acc_abs[k] = o;
     cond_abs[k] = o + len[k];
     o += 2LL * len[k];
+    total += len[k];
   }
   c->out_floats = o;
   // longest first (the order of SortSequences, utils.cpp:53-60), then greedy fill of column budgets:
@@ -1113,8 +1134,29 @@ int prib_acc_stage(prib_ctx *c, int32_t n, const char *const *seq, const int32_t
   std::vector<int> order(n);
   std::iota(order.begin(), order.end(), 0);
   std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return len[a] > len[b]; });
-  int rc = partition(c, order, max_cols, acc_abs, cond_abs, c->batches, &c->n_batches);
+  // the one host copy of the input: into the page-locked arena, in batch order
+  c->h_arena_used = c->h_meta_used = 0;
+  {
+    int rc = grow_pinned(c, &c->h_arena, &c->h_arena_cap, 0, (size_t)total + 64);
+    if (rc != PRIB_OK) return rc;
+    CU(cudaStreamSynchronize(c->stream));  // a previous stage's copies out of the arena / metadata must be done
+  }
+  c->seq_pos.resize(n);
+  {
+    size_t p = 0;
+    for (int k = 0; k < n; k++) {
+      const int q = order[k];
+      c->seq_pos[q] = (long long)p;
+      std::memcpy(c->h_arena + p, seq[q], (size_t)len[q]);
+      p += (size_t)len[q];
+    }
+    c->h_arena_used = p;
+  }
+  CU(cudaEventRecord(c->ev0, c->stream));
+  int rc = partition(c, order, max_cols, acc_abs, cond_abs, c->batches, &c->n_batches, 0);
   if (rc != PRIB_OK) return rc;
+  CU(cudaEventRecord(c->ev1, c->stream));
+  c->stage_timed = false;
   if (o > c->out_cap || !c->d_out) {
     if (c->d_out) cudaFree(c->d_out);
     c->d_out = nullptr;
@@ -1135,7 +1177,18 @@ int prib_acc_compute(prib_ctx *c) {
   // entries the kernels never write (acc tail, cond head) must read 0: raccess.cpp:487-488
   CU(cudaMemsetAsync(c->d_out, 0, (size_t)std::max<long long>(c->out_floats, 1) * sizeof(float), c->stream));
   CU(cudaMemsetAsync(c->d_bad, 0, sizeof(int32_t), c->stream));
-  std::vector<int> flagged;
+  // range flags of all batches come back with ONE wait after the last batch (each batch has its own flag array)
+  long long nflags = 0;
+  for (size_t bi = 0; bi < c->n_batches; ++bi) nflags += c->batches[bi].n;
+  if (c->use_fp32 && c->h_flags_cap < nflags) {
+    CU(cudaStreamSynchronize(c->stream));
+    if (c->h_flags) cudaFreeHost(c->h_flags);
+    c->h_flags = nullptr;
+    c->h_flags_cap = 0;
+    CU(cudaMallocHost(&c->h_flags, sizeof(int32_t) * (size_t)std::max<long long>(nflags, 1)));
+    c->h_flags_cap = std::max<long long>(nflags, 1);
+  }
+  long long fpos = 0;
   for (size_t bi = 0; bi < c->n_batches; ++bi) {
     const Batch &b = c->batches[bi];
     if (b.n == 0) continue;
@@ -1144,38 +1197,55 @@ int prib_acc_compute(prib_ctx *c) {
     c->cnt.sequences += b.n;
     c->cnt.nucleotides += b.nt;
     if (c->use_fp32) {
-      // range flags of this batch (tiny D2H; the wait also keeps the next batch from overwriting state)
-      if (c->h_flags_cap < b.n) {
-        if (c->h_flags) cudaFreeHost(c->h_flags);
-        c->h_flags = nullptr;
-        CU(cudaMallocHost(&c->h_flags, sizeof(int32_t) * (size_t)b.n));
-        c->h_flags_cap = b.n;
-      }
-      CU(cudaMemcpyAsync(c->h_flags, b.d_flags, sizeof(int32_t) * (size_t)b.n, cudaMemcpyDeviceToHost, c->stream));
-      CU(cudaStreamSynchronize(c->stream));
+      CU(cudaMemcpyAsync(c->h_flags + fpos, b.d_flags, sizeof(int32_t) * (size_t)b.n, cudaMemcpyDeviceToHost, c->stream));
+      fpos += b.n;
+    }
+  }
+  std::vector<int> flagged;
+  if (c->use_fp32) {
+    CU(cudaStreamSynchronize(c->stream));
+    fpos = 0;
+    for (size_t bi = 0; bi < c->n_batches; ++bi) {
+      const Batch &b = c->batches[bi];
       for (int k = 0; k < b.n; k++)
-        if (c->h_flags[k]) flagged.push_back(b.ids[k]);
+        if (c->h_flags[fpos + k]) flagged.push_back(b.ids[k]);
+      fpos += b.n;
     }
   }
   if (!flagged.empty()) {
     // re-run in double, on the GPU, writing to the same places of the output image
-    std::vector<long long> acc_abs(c->seqs.size()), cond_abs(c->seqs.size());
+    const size_t nall = c->seq_len.size();
+    std::vector<long long> acc_abs(nall), cond_abs(nall);
     long long o = 0;
-    for (size_t k = 0; k < c->seqs.size(); k++) {
+    for (size_t k = 0; k < nall; k++) {
       acc_abs[k] = o;
-      cond_abs[k] = o + (long long)c->seqs[k].size();
-      o += 2LL * (long long)c->seqs[k].size();
+      cond_abs[k] = o + (long long)c->seq_len[k];
+      o += 2LL * (long long)c->seq_len[k];
     }
-    std::stable_sort(flagged.begin(), flagged.end(),
-                     [&](int a, int b) { return c->seqs[a].size() > c->seqs[b].size(); });
+    std::stable_sort(flagged.begin(), flagged.end(), [&](int a, int b) { return c->seq_len[a] > c->seq_len[b]; });
+    // their bytes, back to back behind the staged ones
+    size_t extra = 0;
+    for (int q : flagged) extra += (size_t)c->seq_len[q];
+    const size_t rerun_begin = c->h_arena_used;
+    int rc = grow_pinned(c, &c->h_arena, &c->h_arena_cap, c->h_arena_used, c->h_arena_used + extra + 64);
+    if (rc != PRIB_OK) return rc;
+    {
+      size_t p = rerun_begin;
+      for (int q : flagged) {
+        std::memcpy(c->h_arena + p, c->h_arena + c->seq_pos[q], (size_t)c->seq_len[q]);
+        p += (size_t)c->seq_len[q];
+      }
+    }
+    const size_t meta_keep = c->h_meta_used;
     std::vector<Batch> fb;
     size_t nfb = 0;
-    int rc = partition(c, flagged, c->e64.max_cols, acc_abs, cond_abs, fb, &nfb);
+    rc = partition(c, flagged, c->e64.max_cols, acc_abs, cond_abs, fb, &nfb, rerun_begin);
     for (Batch &b : fb) {
       if (rc == PRIB_OK) rc = run_batch<double>(c, b, false);
       if (rc == PRIB_OK && cudaStreamSynchronize(c->stream) != cudaSuccess) rc = fail(PRIB_ECUDA, "fp64 re-run failed");
       free_batch(b);
     }
+    c->h_meta_used = meta_keep;  // (compute may be called again on the same staged batches)
     if (rc != PRIB_OK) return rc;
     c->cnt.fp64_rerun_sequences += (long long)flagged.size();
   }
@@ -1201,8 +1271,8 @@ int prib_acc_fetch(prib_ctx *c, float *out, const int64_t *acc_off, const int64_
   bool direct = c->out_floats > 0;
   {
     long long o = 0;
-    for (size_t k = 0; k < c->seqs.size() && direct; k++) {
-      const long long L = (long long)c->seqs[k].size();
+    for (size_t k = 0; k < c->seq_len.size() && direct; k++) {
+      const long long L = (long long)c->seq_len[k];
       direct = acc_off[k] == o && cond_off[k] == o + L;
       o += 2 * L;
     }
@@ -1242,8 +1312,8 @@ int prib_acc_fetch(prib_ctx *c, float *out, const int64_t *acc_off, const int64_
   }
   if (!direct) {
     long long o = 0;
-    for (size_t k = 0; k < c->seqs.size(); k++) {
-      const size_t L = c->seqs[k].size();
+    for (size_t k = 0; k < c->seq_len.size(); k++) {
+      const size_t L = (size_t)c->seq_len[k];
       std::memcpy(out + acc_off[k], c->h_stage + o, sizeof(float) * L);
       std::memcpy(out + cond_off[k], c->h_stage + o + L, sizeof(float) * L);
       o += 2LL * (long long)L;

@@ -33,6 +33,9 @@ GOLDEN = load_golden()
 # math.  |fast - reference| is therefore bounded by the reference's own noise; 1e-4 + 1e-6*|x| covers it.
 ATOL_VS_REF = 1e-4
 RTOL_VS_REF = 1e-6
+# The mean is gated as well (SURVEY §7 asked for mean <= 2e-6 against exact math; against the REFERENCE the mean is
+# bounded by the reference's own float-log noise, ~2e-6): a systematic offset would pass a max-only gate.
+MEAN_VS_REF = 5e-6
 ATOL_VS_EXACT = 6e-6
 RTOL_VS_EXACT = 3e-7
 
@@ -63,3 +66,15 @@ def ref_lib():
     if not RefLib.available():
         pytest.skip("oracle/_ref not built (needs /root/reference at build time)")
     return RefLib()
+
+
+def parity_stats(got, want):
+    """max/mean absolute and max relative deviation (kcal/mol) of two lists of (acc, cond) results."""
+    g = np.concatenate([np.concatenate([np.asarray(a, np.float64), np.asarray(c, np.float64)]) for a, c in got])
+    w = np.concatenate([np.concatenate([np.asarray(a, np.float64), np.asarray(c, np.float64)]) for a, c in want])
+    assert g.shape == w.shape
+    assert np.all(np.isfinite(g)), "non-finite output"
+    err = np.abs(g - w)
+    nz = np.abs(w) > 1e-3
+    return {"n": int(g.size), "max_abs": float(err.max()), "mean_abs": float(err.mean()),
+            "max_rel": float((err[nz] / np.abs(w[nz])).max()) if nz.any() else 0.0}

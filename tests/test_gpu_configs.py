@@ -1,0 +1,89 @@
+"""Parity at the sizes of BASELINE.json's configs ("what's weak" #1): every config is checked at its own
+sequence length and span against the reference's arithmetic — the compiled reference (oracle/_ref) where the CPU can
+afford it, otherwise the GPU exact engine (mode 2), which tests/test_gpu_exact.py pins bit for bit to the reference.
+Max AND mean deviations are gated and printed (`pytest -s` shows them; bench.py reports the same in its JSON line)."""
+import numpy as np
+import pytest
+
+from conftest import ATOL_VS_REF, MEAN_VS_REF, parity_stats
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(seqs, W, delta, mode=0, budget=48 << 30):
+    from priblast_b200 import Raccess
+    with Raccess(W, delta, max_batch_bytes=budget, mode=mode) as r:
+        res = r.run_batch(seqs)
+        out = [(np.array(a), np.array(c)) for a, c in res]
+        cnt = r.counters()
+    return out, cnt
+
+
+def _gate(st, what):
+    print(f"{what}: n={st['n']} max|d|={st['max_abs']:.3e} mean|d|={st['mean_abs']:.3e} max rel={st['max_rel']:.3e} kcal/mol")
+    assert st["max_abs"] <= ATOL_VS_REF, (what, st)
+    assert st["mean_abs"] <= MEAN_VS_REF, (what, st)
+
+
+def test_cfg1_in_full_vs_compiled_reference(ref_lib):
+    """cfg1 = 1,000 x 500 nt, W=70, delta=5 (the Q1 float-overflow clamp regime): ALL sequences against the
+    unmodified reference compiled from /root/reference (oracle/_ref), not a slice."""
+    from priblast_b200 import workloads
+    seqs = workloads.cfg1()
+    got, _ = _run(seqs, 70, 5)
+    want, _ = ref_lib.run_batch(seqs, 70, 5)
+    _gate(parity_stats(got, want), "cfg1 1000x500 W=70 fast engine vs reference")
+
+
+def test_cfg3_100kb_fast_vs_exact_engine():
+    """cfg3 spans 10-100 kb: the LONGEST sequence of the config (and one of median length) through the fast engine
+    and through the exact engine (the reference's float-table log-sums, bit-pinned in test_gpu_exact.py).  The
+    reference's own noise grows with L; this shows where the fast engine sits against it at 100 kb."""
+    from priblast_b200 import workloads
+    lens = np.array([len(s) for s in workloads.cfg3(first=400)])
+    seqs_all = workloads.cfg3(first=400)
+    pick = [int(np.argmax(lens)), int(np.argsort(lens)[len(lens) // 2])]
+    seqs = [seqs_all[k] for k in pick]
+    assert max(len(s) for s in seqs) > 95_000
+    fast, _ = _run(seqs, 70, 5)
+    exact, _ = _run(seqs, 70, 5, mode=2)
+    _gate(parity_stats(fast, exact), f"cfg3 L={[len(s) for s in seqs]} W=70 fast vs exact engine")
+
+
+@pytest.mark.parametrize("W", [20, 70, 150])
+def test_cfg4_2kb_span_sweep_fast_vs_exact_engine(W):
+    """cfg4 = 2 kb sequences at W = 20 / 70 / 150: 200 of them at their own size; at W = 150 a good part of the batch
+    takes the FP32 -> FP64 re-run path, which is exactly what has to be checked."""
+    from priblast_b200 import workloads
+    seqs = workloads.cfg4(first=200)
+    fast, cnt = _run(seqs, W, 5)
+    exact, _ = _run(seqs, W, 5, mode=2)
+    print(f"W={W}: {cnt['fp64_rerun_sequences']} of {len(seqs)} sequences re-run in FP64")
+    _gate(parity_stats(fast, exact), f"cfg4 200x2000 W={W} fast vs exact engine")
+
+
+def test_cfg2_sample_fast_vs_exact_engine():
+    """cfg2 (the bench workload): 192 transcripts strided through the first 1,536 — all three finalisation regimes
+    (Z < 88.7, clamp, log path) occur."""
+    from priblast_b200 import workloads
+    seqs = workloads.cfg2(first=1536)[::8]
+    fast, _ = _run(seqs, 70, 5)
+    exact, _ = _run(seqs, 70, 5, mode=2)
+    _gate(parity_stats(fast, exact), "cfg2 192 transcripts W=70 fast vs exact engine")
+
+
+@pytest.mark.parametrize("W", [150, 200])
+def test_long_gc_helix_far_from_the_start_does_not_overflow_the_outer_scans(oracle_lib, W):
+    """the linear-domain outer-array scans rescale by powers of two; a perfect GC helix of ~W/2 pairs placed
+    behind > 2 kb of random sequence multiplies a ring value near the rescale threshold by an un-normalised weight of
+    up to e^405.  The result must stay finite and match the oracle (which works in the log domain)."""
+    rng = np.random.default_rng(77)
+    pairs = W // 2 - 4
+    head = "".join("ACGU"[k] for k in rng.integers(0, 4, 2100))
+    tail = "".join("ACGU"[k] for k in rng.integers(0, 4, 60))
+    seq = head + "G" * pairs + "AAAA" + "C" * pairs + tail
+    got, cnt = _run([seq], W, 5, budget=16 << 30)
+    want, _ = oracle_lib.run_batch([seq], W, 5)
+    st = parity_stats(got, want)
+    print(f"W={W} helix of {pairs} pairs at 2.1 kb: max|d|={st['max_abs']:.3e}, fp64 re-runs {cnt['fp64_rerun_sequences']}")
+    assert st["max_abs"] <= ATOL_VS_REF, st
