@@ -11,6 +11,7 @@
 // are flagged on the device and re-run by the double engine inside the same prib_acc_compute call, on
 // the GPU.  There is no CPU path.
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>  // header-only NVTX v3: ranges show up in Nsight Systems / ncu --nvtx, cost nothing otherwise
 
 #include <algorithm>
 #include <cstdio>
@@ -30,6 +31,12 @@
 using namespace prib;
 
 namespace {
+
+// NVTX range over a host-side scope (one per C-ABI call and per phase of a device batch)
+struct NvtxRange {
+  explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
 
 constexpr int kThreads = 128;
 constexpr int kScanWarps = 4;
@@ -841,6 +848,8 @@ int run_batch(prib_ctx *c, const Batch &b, bool timed) {
   CU(cudaMemsetAsync(b.d_flags, 0, sizeof(int32_t) * (size_t)std::max(b.n, 1), st));
   const unsigned grid = (unsigned)((b.NC + kThreads - 1) / kThreads);
   if (timed) CU(cudaEventRecord(c->evp[1], st));
+  NvtxRange nvtx_batch("prib:device_batch");
+  nvtxRangePushA("prib:inside");
   const int TX = e.TC - (c->W + 1);
   const long long ntiles = (b.NC + TX - 1) / TX;
   const int tgrid = (int)std::min<long long>(ntiles, c->grid_tiles);
@@ -848,19 +857,28 @@ int run_batch(prib_ctx *c, const Batch &b, bool timed) {
   if (Tile<real>::first_group(c->W) & 1) k_inside_tile<real, 1><<<tgrid, e.TC, e.tile_smem, st>>>(k, TX, ntiles, scratch);
   else k_inside_tile<real, 0><<<tgrid, e.TC, e.tile_smem, st>>>(k, TX, ntiles, scratch);
   if (timed) CU(cudaEventRecord(c->evp[2], st));
+  nvtxRangePop();
+  nvtxRangePushA("prib:outer_scans");
   k_outer_scans_warp<real><<<(2 * b.n + e.scan_warps - 1) / e.scan_warps, 32 * e.scan_warps,
                              (size_t)e.scan_warps * 2 * (c->W + 2) * 32 * sizeof(real), st>>>(k);
   if (timed) CU(cudaEventRecord(c->evp[3], st));
+  nvtxRangePop();
+  nvtxRangePushA("prib:outside");
   k_outside_tile<real><<<tgrid, e.TC, e.tile_smem, st>>>(k, TX, ntiles, scratch);
   if (timed) CU(cudaEventRecord(c->evp[4], st));
+  nvtxRangePop();
+  nvtxRangePushA("prib:strand_weights");
   const unsigned bgrid = (unsigned)((b.NC + e.TXb - 1) / e.TXb);
   launch_biloop<real, true>(k, bgrid, e.TXb, e.bi_smem, st);
   if (timed) CU(cudaEventRecord(c->evp[5], st));
   launch_biloop<real, false>(k, bgrid, e.TXb, e.bi_smem, st);
   if (timed) CU(cudaEventRecord(c->evp[6], st));
+  nvtxRangePop();
+  nvtxRangePushA("prib:hairpin_finalize");
   k_hairpin_suffix<real><<<grid, kThreads, 0, st>>>(k);
   k_finalize<real><<<grid, kThreads, 0, st>>>(k);
   if (timed) CU(cudaEventRecord(c->evp[7], st));
+  nvtxRangePop();
   CU(cudaGetLastError());
   if (timed) c->phases_pending = true;
   c->cnt.kernel_launches += 7;
@@ -1108,6 +1126,7 @@ int prib_acc_set_stream(prib_ctx *c, void *cuda_stream) {
 }
 
 int prib_acc_stage(prib_ctx *c, int32_t n, const char *const *seq, const int32_t *len) {
+  NvtxRange nvtx_call("prib_acc_stage");
   if (!c || n < 0 || (n > 0 && (!seq || !len))) return fail(PRIB_EINVAL, "bad argument");
   CU(cudaSetDevice(c->prm.device));
   c->staged = c->computed = false;
@@ -1169,6 +1188,7 @@ int prib_acc_stage(prib_ctx *c, int32_t n, const char *const *seq, const int32_t
 }
 
 int prib_acc_compute(prib_ctx *c) {
+  NvtxRange nvtx_call("prib_acc_compute");
   if (!c) return fail(PRIB_EINVAL, "null context");
   if (!c->staged) return fail(PRIB_ESTATE, "prib_acc_compute called before prib_acc_stage");
   CU(cudaSetDevice(c->prm.device));
@@ -1263,6 +1283,7 @@ int prib_acc_sync(prib_ctx *c) {
 }
 
 int prib_acc_fetch(prib_ctx *c, float *out, const int64_t *acc_off, const int64_t *cond_off) {
+  NvtxRange nvtx_call("prib_acc_fetch");
   if (!c || !out || !acc_off || !cond_off) return fail(PRIB_EINVAL, "null argument");
   if (!c->computed) return fail(PRIB_ESTATE, "prib_acc_fetch called before prib_acc_compute");
   CU(cudaSetDevice(c->prm.device));

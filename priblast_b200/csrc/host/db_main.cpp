@@ -4,7 +4,16 @@
 // becomes ONE prib_acc_run call per GPU; the block/heap/dynamic distributors (-a) all map to the
 // length-balanced partitioner over the GPUs of this box (db_format.h lpt_partition); output order is the
 // FASTA order, i.e. what the reference emits with -np 1 and -a heap|block.
+//
+// Process model: one WORKER PROCESS per GPU (the reference: one MPI rank per node), forked before the first CUDA
+// call and pinned to its device through CUDA_VISIBLE_DEVICES, so the CUDA start-up of eight B200s (0.55 s each,
+// 5.4 s when one process opens all of them: profiles/r1/cuda_init_8gpu.txt) runs in parallel.  Every worker writes
+// the records of its sequences straight into <db>.acc at their final offsets (pwrite; the record sizes are known
+// from the lengths), so there is no gather step at all.  The parent builds <db>.seq/.ind/.nam/.bas meanwhile (suffix
+// arrays on the last GPU).
+#include <fcntl.h>
 #include <getopt.h>
+#include <sys/wait.h>
 #include <unistd.h>
 
 #include <cstdio>
@@ -66,20 +75,6 @@ static int count_device_nodes() {
   return n;
 }
 
-// wall-time model: driver start-up 0.55 + 0.69 (n - 1) s, accessibility at 5.5e7 nt/s per GPU end to end
-static int pick_gpus(double total_nt, int avail) {
-  int best = 1;
-  double best_t = 1e300;
-  for (int n = 1; n <= avail; n++) {
-    const double t = 0.55 + 0.69 * (n - 1) + total_nt / 5.5e7 / n;
-    if (t < best_t) {
-      best_t = t;
-      best = n;
-    }
-  }
-  return best;
-}
-
 static void usage() {
   std::printf(
       "pRIblast-b200 db: database construction with GPU accessibility\n"
@@ -90,7 +85,7 @@ static void usage() {
       "-m (extension; also PRIB_ACC_MODE): auto = FP32 span-scaled engine with FP64 re-run (default; .acc within\n"
       "   1e-4 kcal/mol of the reference), fp64, exact = the reference's own arithmetic on the GPU (.acc, hence\n"
       "   the whole database and the ris output, byte-identical to the reference; ~50x slower than auto)\n"
-      "environment: PRIB_NUM_GPUS=n fixes the number of GPUs (default: as many as the job is worth, see pick_gpus)\n");
+      "environment: PRIB_NUM_GPUS=n limits the number of GPUs (default: every visible one, one worker process each)\n");
 }
 
 int main(int argc, char *argv[]) {
@@ -142,19 +137,14 @@ int main(int argc, char *argv[]) {
 
   // ---- accessibility on the GPUs ---------------------------------------------------------------
   const bool formats_only = std::getenv("PRIB_DB_FORMATS_ONLY") != nullptr;  // test switch: no .acc, no GPU
-  std::vector<int64_t> acc_off(seqs.size()), cond_off(seqs.size());
-  int64_t total = 0;
-  for (size_t k = 0; k < seqs.size(); k++) {
-    acc_off[k] = total;
-    cond_off[k] = total + (int64_t)seqs[k].size();
-    total += 2 * (int64_t)seqs[k].size();
-  }
-  int want = 0;
+  // record k of <db>.acc starts at rec_off[k] (raccess.cpp:447-481: 8 + 4 (2L - delta + 1) bytes per sequence)
+  std::vector<int64_t> rec_off(seqs.size() + 1, 0);
+  for (size_t k = 0; k < seqs.size(); k++) rec_off[k + 1] = rec_off[k] + prib_acc_record_bytes((int32_t)seqs[k].size(), delta);
+  std::vector<pid_t> workers;
+  std::vector<std::string> devs;
   if (!formats_only) {
-    // how many GPUs is this job worth?  Decided before the first CUDA call (see count_device_nodes)
-    if (const char *e = std::getenv("PRIB_NUM_GPUS")) want = std::max(1, std::atoi(e));
     // the devices we may use: the caller's CUDA_VISIBLE_DEVICES list if there is one, else the /dev/nvidiaN nodes
-    std::vector<std::string> devs;
+    // (counted without touching CUDA: nothing in this process may initialise it before the fork)
     if (const char *cv = std::getenv("CUDA_VISIBLE_DEVICES")) {
       std::string item;
       for (const char *q = cv;; ++q) {
@@ -170,16 +160,78 @@ int main(int argc, char *argv[]) {
       const int nodes = count_device_nodes();
       for (int k = 0; k < nodes; k++) devs.push_back(std::to_string(k));
     }
-    if (devs.size() > 1) {
-      const int n = std::min((int)devs.size(), want > 0 ? want : pick_gpus((double)total / 2, (int)devs.size()));
-      if (n < (int)devs.size()) {
-        std::string vis;
-        for (int k = 0; k < n; k++) vis += (k ? "," : "") + devs[k];
-        setenv("CUDA_VISIBLE_DEVICES", vis.c_str(), 1);
-      }
+    if (const char *e = std::getenv("PRIB_NUM_GPUS"))
+      if (std::atoi(e) >= 1 && (size_t)std::atoi(e) < devs.size()) devs.resize((size_t)std::atoi(e));
+    if (devs.empty()) return die("Error: no CUDA device available (there is no CPU path)");
+    const int ngpu = (int)std::min(devs.size(), std::max<size_t>(seqs.size(), 1));
+    devs.resize((size_t)ngpu);
+    if (timer.on) std::fprintf(stderr, "[db] using %d GPU(s), one worker process each\n", ngpu);
+    {  // <db>.acc at its final size; the workers fill it in place
+      const int fd = open((db + ".acc").c_str(), O_CREAT | O_TRUNC | O_WRONLY, 0644);
+      if (fd < 0 || ftruncate(fd, (off_t)rec_off[seqs.size()]) != 0) return die("Error: can't open " + db + ".acc");
+      close(fd);
     }
+    std::vector<std::vector<int>> part;
+    lpt_partition(seqs, ngpu, part);
+    std::fflush(nullptr);
+    for (int d = 0; d < ngpu; d++) {
+      const pid_t pid = fork();
+      if (pid < 0) return die("Error: fork failed");
+      if (pid == 0) {  // ---- worker d: its own CUDA context on its own device
+        setenv("CUDA_VISIBLE_DEVICES", devs[(size_t)d].c_str(), 1);
+        const std::vector<int> &ids = part[(size_t)d];
+        if (ids.empty()) _exit(0);
+        auto fail_w = [&](const std::string &msg) {
+          std::fprintf(stderr, "Error: GPU %s: %s\n", devs[(size_t)d].c_str(), msg.c_str());
+          _exit(1);
+        };
+        StageTimer wt;
+        prib_acc_params ap;
+        std::memset(&ap, 0, sizeof(ap));
+        ap.maximal_span = prm.maximal_span;
+        ap.min_accessible_length = delta;
+        ap.device = 0;
+        ap.mode = acc_mode;
+        prib_ctx *ctx = nullptr;
+        if (prib_acc_create(&ctx, &ap) != PRIB_OK) fail_w(prib_last_error());
+        wt.lap("  worker: context (CUDA init, tables)");
+        std::vector<const char *> sp(ids.size());
+        std::vector<int32_t> sl(ids.size());
+        std::vector<int64_t> ao(ids.size()), co(ids.size());
+        int64_t total = 0;
+        for (size_t k = 0; k < ids.size(); k++) {
+          sp[k] = seqs[(size_t)ids[k]].data();
+          sl[k] = (int32_t)seqs[(size_t)ids[k]].size();
+          ao[k] = total;
+          co[k] = total + sl[k];
+          total += 2 * (int64_t)sl[k];
+        }
+        float *image = (float *)prib_host_alloc(sizeof(float) * (size_t)std::max<int64_t>(total, 1));
+        if (!image) fail_w(prib_last_error());
+        if (prib_acc_run(ctx, (int32_t)ids.size(), sp.data(), sl.data(), image, ao.data(), co.data()) != PRIB_OK)
+          fail_w(prib_last_error());
+        wt.lap("  worker: prib_acc_run");
+        const int fd = open((db + ".acc").c_str(), O_WRONLY);
+        if (fd < 0) fail_w("can't open " + db + ".acc");
+        std::vector<char> rec;
+        for (size_t k = 0; k < ids.size(); k++) {
+          const int64_t bytes = rec_off[(size_t)ids[k] + 1] - rec_off[(size_t)ids[k]];
+          rec.resize((size_t)bytes);
+          prib_acc_write_record(image + ao[k], image + co[k], sl[k], delta, rec.data());
+          if (pwrite(fd, rec.data(), (size_t)bytes, (off_t)rec_off[(size_t)ids[k]]) != (ssize_t)bytes)
+            fail_w("short write on " + db + ".acc");
+        }
+        close(fd);
+        wt.lap("  worker: records -> .acc");
+        _exit(0);  // no teardown: the process exit frees the device state faster than cudaFree would
+      }
+      workers.push_back(pid);
+    }
+    // the parent's own CUDA use (suffix arrays) sees one device only: the last one, whose worker has the lightest
+    // share under LPT ties
+    setenv("CUDA_VISIBLE_DEVICES", devs.back().c_str(), 1);
   }
-  // <db>.seq / <db>.ind need only the sequences: they are built (suffix arrays on GPU 0) while the GPUs work on
+  // <db>.seq / <db>.ind need only the sequences: they are built (suffix arrays on the GPU) while the workers compute
   // the accessibility
   std::string err_si;
   StageTimer t_si;
@@ -188,89 +240,22 @@ int main(int argc, char *argv[]) {
     t_si.lap(".seq/.ind (SA on GPU, hash) [overlapped]");
     return ok;
   });
-  float *image = nullptr;
-  std::vector<std::thread> workers;
-  if (!formats_only) {
-    int ngpu = prib_device_count();
-    if (want > 0) ngpu = std::min(ngpu, want);
-    if (timer.on) std::fprintf(stderr, "[db] using %d GPU(s)\n", ngpu);
-    if (ngpu <= 0) {
-      seq_ind.wait();
-      return die("Error: no CUDA device available (there is no CPU path)");
-    }
-    image = (float *)prib_host_alloc(sizeof(float) * (size_t)std::max<int64_t>(total, 1));
-    if (!image) {
-      seq_ind.wait();
-      return die(std::string("Error: ") + prib_last_error());
-    }
-    timer.lap("pinned output image");
-    std::vector<std::vector<int>> part;
-    lpt_partition(seqs, ngpu, part);
-    std::vector<std::string> errors(ngpu);
-    std::vector<std::promise<void>> done(ngpu);  // results of GPU d are in the image (its context may still be tearing down)
-    for (int d = 0; d < ngpu; d++) {
-      workers.emplace_back([&, d]() {
-        const std::vector<int> &ids = part[d];
-        if (ids.empty()) {
-          done[d].set_value();
-          return;
-        }
-        prib_acc_params ap;
-        std::memset(&ap, 0, sizeof(ap));
-        ap.maximal_span = prm.maximal_span;
-        ap.min_accessible_length = delta;
-        ap.device = d;
-        ap.mode = acc_mode;
-        prib_ctx *ctx = nullptr;
-        StageTimer wt;
-        if (prib_acc_create(&ctx, &ap) != PRIB_OK) {
-          errors[d] = prib_last_error();
-          done[d].set_value();
-          return;
-        }
-        wt.lap("  context (CUDA init, tables)");
-        std::vector<const char *> sp(ids.size());
-        std::vector<int32_t> sl(ids.size());
-        std::vector<int64_t> ao(ids.size()), co(ids.size());
-        for (size_t k = 0; k < ids.size(); k++) {
-          sp[k] = seqs[ids[k]].data();
-          sl[k] = (int32_t)seqs[ids[k]].size();
-          ao[k] = acc_off[ids[k]];
-          co[k] = cond_off[ids[k]];
-        }
-        if (prib_acc_run(ctx, (int32_t)ids.size(), sp.data(), sl.data(), image, ao.data(), co.data()) != PRIB_OK)
-          errors[d] = prib_last_error();
-        wt.lap("  prib_acc_run");
-        done[d].set_value();
-        prib_acc_destroy(ctx);  // freeing the DP state overlaps the file writing below
-        wt.lap("  context teardown [overlapped]");
-      });
-    }
-    for (int d = 0; d < ngpu; d++) done[d].get_future().wait();
-    for (int d = 0; d < ngpu; d++)
-      if (!errors[d].empty()) {
-        for (auto &w : workers) w.join();
-        seq_ind.wait();
-        return die("Error: GPU " + std::to_string(d) + ": " + errors[d]);
-      }
-  }
-
-  timer.lap("accessibility (GPU)");
-  // ---- database files --------------------------------------------------------------------------
   bool ok = true;
-  if (!formats_only && !write_acc(db, seqs, image, acc_off, cond_off, delta, err)) ok = false;
-  timer.lap(".acc");
-  if (ok && !write_nam(db, names, err)) ok = false;
+  if (!write_nam(db, names, err)) ok = false;
   if (ok && !write_bas(db, prm, err)) ok = false;
   timer.lap(".nam/.bas");
+  bool workers_ok = true;
+  for (pid_t pid : workers) {
+    int st = 0;
+    if (waitpid(pid, &st, 0) < 0 || !WIFEXITED(st) || WEXITSTATUS(st) != 0) workers_ok = false;
+  }
+  timer.lap("accessibility (GPU workers) + .acc");
   if (!seq_ind.get()) {
     ok = false;
     err = err_si;
   }
   timer.lap("wait for .seq/.ind");
-  for (auto &w : workers) w.join();
-  timer.lap("wait for context teardown");
+  if (!workers_ok) return die("Error: an accessibility worker failed (see above); the database is incomplete");
   if (!ok) return die(err);
-  if (image) prib_host_free(image);
   return 0;
 }

@@ -81,3 +81,23 @@ def test_large_page_is_sorted():
     for j in rng.integers(0, len(sa) - 1, 4000):
         a, b = int(sa[j]), int(sa[j + 1])
         assert raw[a:a + 64] <= raw[b:b + 64] and (raw[a:a + 64] != raw[b:b + 64] or raw[a:] < raw[b:])
+
+
+def test_matches_the_references_own_sais():
+    """The reference's builder itself (sais.cpp:656 compiled into oracle/_ref/libsais_ref.so, the call of
+    db_construction.cpp:334): same text in, same `int` array out."""
+    from priblast_b200 import suffix_array
+    path = os.path.join(ROOT, "oracle", "_ref", "libsais_ref.so")
+    if not os.path.exists(path):
+        pytest.skip("oracle/_ref/libsais_ref.so not built (make -C oracle refsais)")
+    lib = ctypes.CDLL(path)
+    lib.ref_sais.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
+    rng = np.random.default_rng(5)
+    texts = [_page(rng, rng.integers(20, 4000, 300)), _page(rng, [700] * 3, alphabet=(2,)),
+             _page(rng, rng.integers(50, 500, 40), alphabet=(2, 3, 4, 5, 6, 7, 8, 9)),
+             np.tile(_page(rng, [333]), 7)]
+    for text in texts:
+        text = np.ascontiguousarray(text, np.uint8)
+        want = np.zeros(len(text), np.int32)
+        assert lib.ref_sais(text.ctypes.data_as(ctypes.c_void_p), want.ctypes.data_as(ctypes.c_void_p), len(text)) == 0
+        assert np.array_equal(suffix_array(text), want)
