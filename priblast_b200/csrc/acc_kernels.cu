@@ -1081,7 +1081,12 @@ int prib_acc_create(prib_ctx **out, const prib_acc_params *params) {
 
   size_t free_b = 0, total_b = 0;
   CUB(cudaMemGetInfo(&free_b, &total_b));
-  long long budget = params->max_batch_bytes > 0 ? params->max_batch_bytes : (long long)(free_b * 0.6);
+  // Default DP budget: 32 GiB per device batch (~6 M nt at W = 70: thousands of tiles per launch, so nothing is lost
+  // against one huge batch) instead of most of the HBM — allocating and tearing down a 100 GB block costs ~0.5 s per
+  // process, more than the whole accessibility step of a 25 M nt shard.  Long sequences need more: a caller (or the
+  // stage call, below) raises it up to 90 % of the free memory.
+  long long budget = params->max_batch_bytes > 0 ? params->max_batch_bytes
+                                                 : std::min<long long>((long long)(free_b * 0.6), 32LL << 30);
   if (budget > (long long)(free_b * 0.9)) budget = (long long)(free_b * 0.9);
   c->e64.max_cols = budget / state_bytes_per_column(c->W, 8) / 32 * 32;
   c->e32.max_cols = budget / state_bytes_per_column(c->W, 4) / 32 * 32;

@@ -141,6 +141,7 @@ int main(int argc, char *argv[]) {
   std::vector<int64_t> rec_off(seqs.size() + 1, 0);
   for (size_t k = 0; k < seqs.size(); k++) rec_off[k + 1] = rec_off[k] + prib_acc_record_bytes((int32_t)seqs[k].size(), delta);
   std::vector<pid_t> workers;
+  std::vector<int> status_fd;
   std::vector<std::string> devs;
   if (!formats_only) {
     // the devices we may use: the caller's CUDA_VISIBLE_DEVICES list if there is one, else the /dev/nvidiaN nodes
@@ -175,16 +176,43 @@ int main(int argc, char *argv[]) {
     lpt_partition(seqs, ngpu, part);
     std::fflush(nullptr);
     for (int d = 0; d < ngpu; d++) {
+      int fds[2];
+      if (pipe(fds) != 0) return die("Error: pipe failed");
       const pid_t pid = fork();
       if (pid < 0) return die("Error: fork failed");
       if (pid == 0) {  // ---- worker d: its own CUDA context on its own device
+        close(fds[0]);
         setenv("CUDA_VISIBLE_DEVICES", devs[(size_t)d].c_str(), 1);
         const std::vector<int> &ids = part[(size_t)d];
-        if (ids.empty()) _exit(0);
+        // the worker reports through the pipe as soon as its files are complete and exits afterwards: tearing down a
+        // CUDA context with ~100 GB of DP state takes about a second that nobody has to wait for
+        auto finish = [&](char status) {
+          if (write(fds[1], &status, 1) != 1) _exit(2);
+          close(fds[1]);
+          _exit(status == 'k' ? 0 : 1);
+        };
         auto fail_w = [&](const std::string &msg) {
           std::fprintf(stderr, "Error: GPU %s: %s\n", devs[(size_t)d].c_str(), msg.c_str());
-          _exit(1);
+          finish('e');
         };
+        // <db>.seq / <db>.ind need only the sequences: the LAST worker (the lightest share under LPT ties) builds them
+        // in a second thread of its process, suffix arrays on its GPU (one CUDA start-up per device)
+        std::string err_si;
+        std::future<bool> seq_ind;
+        if (d == ngpu - 1)
+          seq_ind = std::async(std::launch::async, [&]() {
+            StageTimer t_si;
+            const bool ok_si = write_seq_ind(db, seqs, prm, err_si, gpu_suffix_array);
+            t_si.lap("  worker: .seq/.ind (SA on GPU, hash) [thread]");
+            return ok_si;
+          });
+        auto join_si = [&]() {
+          if (seq_ind.valid() && !seq_ind.get()) fail_w(err_si);
+        };
+        if (ids.empty()) {
+          join_si();
+          finish('k');
+        }
         StageTimer wt;
         prib_acc_params ap;
         std::memset(&ap, 0, sizeof(ap));
@@ -223,38 +251,31 @@ int main(int argc, char *argv[]) {
         }
         close(fd);
         wt.lap("  worker: records -> .acc");
-        _exit(0);  // no teardown: the process exit frees the device state faster than cudaFree would
+        join_si();
+        finish('k');
       }
+      close(fds[1]);
       workers.push_back(pid);
+      status_fd.push_back(fds[0]);
     }
-    // the parent's own CUDA use (suffix arrays) sees one device only: the last one, whose worker has the lightest
-    // share under LPT ties
-    setenv("CUDA_VISIBLE_DEVICES", devs.back().c_str(), 1);
   }
-  // <db>.seq / <db>.ind need only the sequences: they are built (suffix arrays on the GPU) while the workers compute
-  // the accessibility
-  std::string err_si;
-  StageTimer t_si;
-  std::future<bool> seq_ind = std::async(std::launch::async, [&]() {
-    const bool ok = write_seq_ind(db, seqs, prm, err_si, formats_only ? nullptr : gpu_suffix_array);
-    t_si.lap(".seq/.ind (SA on GPU, hash) [overlapped]");
-    return ok;
-  });
   bool ok = true;
-  if (!write_nam(db, names, err)) ok = false;
-  if (ok && !write_bas(db, prm, err)) ok = false;
-  timer.lap(".nam/.bas");
-  bool workers_ok = true;
-  for (pid_t pid : workers) {
-    int st = 0;
-    if (waitpid(pid, &st, 0) < 0 || !WIFEXITED(st) || WEXITSTATUS(st) != 0) workers_ok = false;
-  }
-  timer.lap("accessibility (GPU workers) + .acc");
-  if (!seq_ind.get()) {
+  std::string err_si;
+  if (formats_only && !write_seq_ind(db, seqs, prm, err_si, nullptr)) {  // test switch: host suffix arrays, no GPU
     ok = false;
     err = err_si;
   }
-  timer.lap("wait for .seq/.ind");
+  if (ok && !write_nam(db, names, err)) ok = false;
+  if (ok && !write_bas(db, prm, err)) ok = false;
+  timer.lap(".nam/.bas");
+  bool workers_ok = true;
+  for (int fd : status_fd) {  // one status byte per worker; its process may still be tearing down afterwards
+    char st = 0;
+    if (read(fd, &st, 1) != 1 || st != 'k') workers_ok = false;
+    close(fd);
+  }
+  for (pid_t pid : workers) waitpid(pid, nullptr, WNOHANG);
+  timer.lap("accessibility (GPU workers) + .acc/.seq/.ind");
   if (!workers_ok) return die("Error: an accessibility worker failed (see above); the database is incomplete");
   if (!ok) return die(err);
   return 0;
