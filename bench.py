@@ -185,10 +185,16 @@ def ours(args, rank: int, local_rank: int, world: int) -> None:
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    result_fd = 1
     if world > 1:
-        # stdout must carry exactly one JSON line: NCCL's own log (communicator, nranks, transport) goes to stderr
+        # NCCL's own log (communicator, nranks, transport) is NOT muted; it prints to stdout, which must carry exactly
+        # one JSON line, so everything written to fd 1 from here on is sent to stderr and the JSON line goes out
+        # through a duplicate of the real stdout.
         os.environ.setdefault("NCCL_DEBUG", "INFO")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
+        sys.stdout.flush()
+        result_fd = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
         print(f"[bench] NCCL communicator up: rank {rank} of nranks {dist.get_world_size()} on cuda:{local_rank} "
               f"(timing all-reduce only; the data path has no collective)", file=sys.stderr, flush=True)
@@ -381,7 +387,8 @@ def ours(args, rank: int, local_rank: int, world: int) -> None:
             "parity": parity,
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
         }
-        print(json.dumps(line), flush=True)
+        sys.stdout.flush()
+        os.write(result_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 

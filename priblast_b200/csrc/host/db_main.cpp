@@ -13,6 +13,8 @@
 // arrays on the last GPU).
 #include <fcntl.h>
 #include <getopt.h>
+#include <signal.h>
+#include <sys/mman.h>
 #include <sys/wait.h>
 #include <unistd.h>
 
@@ -140,12 +142,12 @@ int main(int argc, char *argv[]) {
   // record k of <db>.acc starts at rec_off[k] (raccess.cpp:447-481: 8 + 4 (2L - delta + 1) bytes per sequence)
   std::vector<int64_t> rec_off(seqs.size() + 1, 0);
   for (size_t k = 0; k < seqs.size(); k++) rec_off[k + 1] = rec_off[k] + prib_acc_record_bytes((int32_t)seqs[k].size(), delta);
-  std::vector<pid_t> workers;
-  std::vector<int> status_fd;
-  std::vector<std::string> devs;
+  bool ok = true;
+  bool workers_ok = true;
   if (!formats_only) {
     // the devices we may use: the caller's CUDA_VISIBLE_DEVICES list if there is one, else the /dev/nvidiaN nodes
     // (counted without touching CUDA: nothing in this process may initialise it before the fork)
+    std::vector<std::string> devs;
     if (const char *cv = std::getenv("CUDA_VISIBLE_DEVICES")) {
       std::string item;
       for (const char *q = cv;; ++q) {
@@ -161,120 +163,221 @@ int main(int argc, char *argv[]) {
       const int nodes = count_device_nodes();
       for (int k = 0; k < nodes; k++) devs.push_back(std::to_string(k));
     }
-    if (const char *e = std::getenv("PRIB_NUM_GPUS"))
-      if (std::atoi(e) >= 1 && (size_t)std::atoi(e) < devs.size()) devs.resize((size_t)std::atoi(e));
+    int fixed_gpus = 0;  // PRIB_NUM_GPUS=n: exactly n workers, all started at once (scaling measurements)
+    if (const char *e = std::getenv("PRIB_NUM_GPUS")) fixed_gpus = std::max(1, std::atoi(e));
+    if (fixed_gpus > 0 && (size_t)fixed_gpus < devs.size()) devs.resize((size_t)fixed_gpus);
     if (devs.empty()) return die("Error: no CUDA device available (there is no CPU path)");
-    const int ngpu = (int)std::min(devs.size(), std::max<size_t>(seqs.size(), 1));
-    devs.resize((size_t)ngpu);
-    if (timer.on) std::fprintf(stderr, "[db] using %d GPU(s), one worker process each\n", ngpu);
     {  // <db>.acc at its final size; the workers fill it in place
       const int fd = open((db + ".acc").c_str(), O_CREAT | O_TRUNC | O_WRONLY, 0644);
       if (fd < 0 || ftruncate(fd, (off_t)rec_off[seqs.size()]) != 0) return die("Error: can't open " + db + ".acc");
       close(fd);
     }
-    std::vector<std::vector<int>> part;
-    lpt_partition(seqs, ngpu, part);
-    std::fflush(nullptr);
-    for (int d = 0; d < ngpu; d++) {
-      int fds[2];
-      if (pipe(fds) != 0) return die("Error: pipe failed");
-      const pid_t pid = fork();
-      if (pid < 0) return die("Error: fork failed");
-      if (pid == 0) {  // ---- worker d: its own CUDA context on its own device
-        close(fds[0]);
-        setenv("CUDA_VISIBLE_DEVICES", devs[(size_t)d].c_str(), 1);
-        const std::vector<int> &ids = part[(size_t)d];
-        // the worker reports through the pipe as soon as its files are complete and exits afterwards: tearing down a
-        // CUDA context with ~100 GB of DP state takes about a second that nobody has to wait for
-        auto finish = [&](char status) {
-          if (write(fds[1], &status, 1) != 1) _exit(2);
-          close(fds[1]);
-          _exit(status == 'k' ? 0 : 1);
-        };
-        auto fail_w = [&](const std::string &msg) {
-          std::fprintf(stderr, "Error: GPU %s: %s\n", devs[(size_t)d].c_str(), msg.c_str());
-          finish('e');
-        };
-        // <db>.seq / <db>.ind need only the sequences: the LAST worker (the lightest share under LPT ties) builds them
-        // in a second thread of its process, suffix arrays on its GPU (one CUDA start-up per device)
-        std::string err_si;
-        std::future<bool> seq_ind;
-        if (d == ngpu - 1)
-          seq_ind = std::async(std::launch::async, [&]() {
-            StageTimer t_si;
-            const bool ok_si = write_seq_ind(db, seqs, prm, err_si, gpu_suffix_array);
-            t_si.lap("  worker: .seq/.ind (SA on GPU, hash) [thread]");
-            return ok_si;
-          });
-        auto join_si = [&]() {
-          if (seq_ind.valid() && !seq_ind.get()) fail_w(err_si);
-        };
-        if (ids.empty()) {
-          join_si();
-          finish('k');
+    // Work units: the sequences longest first (the order of SortSequences, utils.cpp:53-60: neighbours in a device
+    // batch have similar lengths), cut into chunks of ~4 M nt.  The workers claim chunks from a shared counter — the
+    // reference's `-a dynamic` distributor (the MPI RMA counter of db_construction.cpp:85-95, 191-197) in shared memory.
+    std::vector<int> order(seqs.size());
+    for (size_t k = 0; k < order.size(); k++) order[k] = (int)k;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b2) { return seqs[(size_t)a].size() > seqs[(size_t)b2].size(); });
+    std::vector<size_t> chunk_begin(1, 0);
+    {
+      const int64_t target = 4 << 20;
+      int64_t acc_nt = 0;
+      for (size_t k = 0; k < order.size(); k++) {
+        acc_nt += (int64_t)seqs[(size_t)order[k]].size();
+        if (acc_nt >= target && k + 1 < order.size()) {
+          chunk_begin.push_back(k + 1);
+          acc_nt = 0;
         }
-        StageTimer wt;
-        prib_acc_params ap;
-        std::memset(&ap, 0, sizeof(ap));
-        ap.maximal_span = prm.maximal_span;
-        ap.min_accessible_length = delta;
-        ap.device = 0;
-        ap.mode = acc_mode;
-        prib_ctx *ctx = nullptr;
-        if (prib_acc_create(&ctx, &ap) != PRIB_OK) fail_w(prib_last_error());
-        wt.lap("  worker: context (CUDA init, tables)");
-        std::vector<const char *> sp(ids.size());
-        std::vector<int32_t> sl(ids.size());
-        std::vector<int64_t> ao(ids.size()), co(ids.size());
-        int64_t total = 0;
-        for (size_t k = 0; k < ids.size(); k++) {
-          sp[k] = seqs[(size_t)ids[k]].data();
-          sl[k] = (int32_t)seqs[(size_t)ids[k]].size();
-          ao[k] = total;
-          co[k] = total + sl[k];
-          total += 2 * (int64_t)sl[k];
-        }
-        float *image = (float *)prib_host_alloc(sizeof(float) * (size_t)std::max<int64_t>(total, 1));
-        if (!image) fail_w(prib_last_error());
-        if (prib_acc_run(ctx, (int32_t)ids.size(), sp.data(), sl.data(), image, ao.data(), co.data()) != PRIB_OK)
-          fail_w(prib_last_error());
-        wt.lap("  worker: prib_acc_run");
-        const int fd = open((db + ".acc").c_str(), O_WRONLY);
-        if (fd < 0) fail_w("can't open " + db + ".acc");
-        std::vector<char> rec;
-        for (size_t k = 0; k < ids.size(); k++) {
-          const int64_t bytes = rec_off[(size_t)ids[k] + 1] - rec_off[(size_t)ids[k]];
-          rec.resize((size_t)bytes);
-          prib_acc_write_record(image + ao[k], image + co[k], sl[k], delta, rec.data());
-          if (pwrite(fd, rec.data(), (size_t)bytes, (off_t)rec_off[(size_t)ids[k]]) != (ssize_t)bytes)
-            fail_w("short write on " + db + ".acc");
-        }
-        close(fd);
-        wt.lap("  worker: records -> .acc");
-        join_si();
-        finish('k');
       }
-      close(fds[1]);
-      workers.push_back(pid);
-      status_fd.push_back(fds[0]);
+      chunk_begin.push_back(order.size());
     }
+    const int nchunks = (int)chunk_begin.size() - 1;
+    struct Shared {  // one page of MAP_SHARED memory
+      int next_chunk, done_chunks, ready, failed, sa_claimed, sa_done;
+      long long nt_done;
+      double t_first_ready, t_last_ready;
+    };
+    Shared *sh = (Shared *)mmap(nullptr, 4096, PROT_READ | PROT_WRITE, MAP_SHARED | MAP_ANONYMOUS, -1, 0);
+    if (sh == MAP_FAILED) return die("Error: mmap failed");
+    std::memset(sh, 0, sizeof(*sh));
+    const auto t_start = std::chrono::steady_clock::now();
+    auto since_start = [&]() { return std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count(); };
+    std::fflush(nullptr);
+
+    auto worker_main = [&](int d) {  // ---- worker d: its own process, its own CUDA context on its own device
+      setenv("CUDA_VISIBLE_DEVICES", devs[(size_t)d].c_str(), 1);
+      auto fail_w = [&](const std::string &msg) {
+        std::fprintf(stderr, "Error: GPU %s: %s\n", devs[(size_t)d].c_str(), msg.c_str());
+        __atomic_store_n(&sh->failed, 1, __ATOMIC_SEQ_CST);
+        _exit(1);
+      };
+      // <db>.seq / <db>.ind need only the sequences: the first worker that gets here builds them in a second thread
+      // of its process, suffix arrays on its GPU (one CUDA start-up per device)
+      std::string err_si;
+      std::future<bool> seq_ind;
+      if (__atomic_exchange_n(&sh->sa_claimed, 1, __ATOMIC_SEQ_CST) == 0)
+        seq_ind = std::async(std::launch::async, [&]() {
+          StageTimer t_si;
+          const bool ok_si = write_seq_ind(db, seqs, prm, err_si, gpu_suffix_array);
+          t_si.lap("  worker: .seq/.ind (SA on GPU, hash) [thread]");
+          return ok_si;
+        });
+      StageTimer wt;
+      prib_acc_params ap;
+      std::memset(&ap, 0, sizeof(ap));
+      ap.maximal_span = prm.maximal_span;
+      ap.min_accessible_length = delta;
+      ap.device = 0;
+      ap.mode = acc_mode;
+      prib_ctx *ctx = nullptr;
+      if (prib_acc_create(&ctx, &ap) != PRIB_OK) fail_w(prib_last_error());
+      wt.lap("  worker: context (CUDA init, tables)");
+      {
+        const double tr = since_start();
+        if (__atomic_fetch_add(&sh->ready, 1, __ATOMIC_SEQ_CST) == 0) sh->t_first_ready = tr;
+        sh->t_last_ready = tr;
+      }
+      const int fd = open((db + ".acc").c_str(), O_WRONLY);
+      if (fd < 0) fail_w("can't open " + db + ".acc");
+      // two page-locked result images: while the records of chunk c go to the file (a second thread: memcpy + pwrite),
+      // the GPU already works on chunk c + 1
+      struct Slot {
+        float *image = nullptr;
+        int64_t floats = 0;
+        std::vector<int32_t> sl;
+        std::vector<int64_t> ao, co;
+        std::future<bool> writing;
+      } slot[2];
+      std::vector<const char *> sp;
+      int mine = 0;
+      for (int cur = 0;; cur ^= 1) {
+        const int ch = __atomic_fetch_add(&sh->next_chunk, 1, __ATOMIC_SEQ_CST);
+        if (ch >= nchunks) break;
+        Slot &S = slot[cur];
+        if (S.writing.valid() && !S.writing.get()) fail_w("short write on " + db + ".acc");
+        const size_t k0 = chunk_begin[(size_t)ch], k1 = chunk_begin[(size_t)ch + 1], n = k1 - k0;
+        sp.resize(n);
+        S.sl.resize(n);
+        S.ao.resize(n);
+        S.co.resize(n);
+        int64_t total = 0;
+        for (size_t k = 0; k < n; k++) {
+          const std::string &sq = seqs[(size_t)order[k0 + k]];
+          sp[k] = sq.data();
+          S.sl[k] = (int32_t)sq.size();
+          S.ao[k] = total;
+          S.co[k] = total + S.sl[k];
+          total += 2 * (int64_t)S.sl[k];
+        }
+        if (total > S.floats) {
+          if (S.image) prib_host_free(S.image);
+          S.floats = total + total / 8;
+          S.image = (float *)prib_host_alloc(sizeof(float) * (size_t)std::max<int64_t>(S.floats, 1));
+          if (!S.image) fail_w(prib_last_error());
+        }
+        if (prib_acc_run(ctx, (int32_t)n, sp.data(), S.sl.data(), S.image, S.ao.data(), S.co.data()) != PRIB_OK)
+          fail_w(prib_last_error());
+        S.writing = std::async(std::launch::async, [&, k0, n, total, cur]() {
+          Slot &W = slot[cur];
+          std::vector<char> rec;
+          for (size_t k = 0; k < n; k++) {
+            const size_t q = (size_t)order[k0 + k];
+            const int64_t bytes = rec_off[q + 1] - rec_off[q];
+            rec.resize((size_t)bytes);
+            prib_acc_write_record(W.image + W.ao[k], W.image + W.co[k], W.sl[k], delta, rec.data());
+            if (pwrite(fd, rec.data(), (size_t)bytes, (off_t)rec_off[q]) != (ssize_t)bytes) return false;
+          }
+          __atomic_fetch_add(&sh->nt_done, total / 2, __ATOMIC_SEQ_CST);
+          __atomic_fetch_add(&sh->done_chunks, 1, __ATOMIC_SEQ_CST);
+          return true;
+        });
+        ++mine;
+      }
+      for (Slot &S : slot)
+        if (S.writing.valid() && !S.writing.get()) fail_w("short write on " + db + ".acc");
+      close(fd);
+      if (wt.on) std::fprintf(stderr, "[db]   worker on GPU %s: %d of %d chunks\n", devs[(size_t)d].c_str(), mine, nchunks);
+      wt.lap("  worker: prib_acc_run + records -> .acc");
+      if (seq_ind.valid()) {
+        if (!seq_ind.get()) fail_w(err_si);
+        __atomic_store_n(&sh->sa_done, 1, __ATOMIC_SEQ_CST);
+      }
+      // no teardown: the parent stops waiting as soon as the counters say everything is on disk; freeing the DP state
+      // of a CUDA context takes longer than the process exit that frees it anyway
+      _exit(0);
+    };
+
+    // Demand-driven recruitment of GPUs.  Bringing up a CUDA context costs about a second per process on an NVSwitch
+    // box, and start-ups of different processes do not overlap (measured: profiles/r2/db_scaling.txt), so a second
+    // GPU only pays if the work still unclaimed outlasts one more start-up.  Worker 0 starts at once; worker k + 1 is
+    // forked when all k + 1 running workers are up and, at the rate MEASURED so far, the unclaimed chunks would keep
+    // them busy longer than the MEASURED start-up of the last context.  No model constants.
+    std::vector<pid_t> workers;
+    auto spawn = [&](int d) {
+      const pid_t pid = fork();
+      if (pid < 0) return false;
+      if (pid == 0) worker_main(d);
+      workers.push_back(pid);
+      return true;
+    };
+    double t_spawn_last = since_start();
+    if (!spawn(0)) return die("Error: fork failed");
+    if (fixed_gpus > 0)
+      for (int d = 1; d < (int)devs.size(); d++) spawn(d);
+    // .nam / .bas meanwhile
+    if (!write_nam(db, names, err)) ok = false;
+    if (ok && !write_bas(db, prm, err)) ok = false;
+    int64_t total_nt = 0;
+    for (auto &sq : seqs) total_nt += (int64_t)sq.size();
+    for (;;) {
+      if (__atomic_load_n(&sh->failed, __ATOMIC_SEQ_CST)) {
+        workers_ok = false;
+        break;
+      }
+      const int done = __atomic_load_n(&sh->done_chunks, __ATOMIC_SEQ_CST);
+      if (done >= nchunks && __atomic_load_n(&sh->sa_done, __ATOMIC_SEQ_CST)) break;
+      // a worker that died without setting the flag (killed, out of memory)
+      for (pid_t pid : workers) {
+        int st = 0;
+        if (waitpid(pid, &st, WNOHANG) == pid && !(WIFEXITED(st) && WEXITSTATUS(st) == 0)) workers_ok = false;
+      }
+      if (!workers_ok) break;
+      const int ready = __atomic_load_n(&sh->ready, __ATOMIC_SEQ_CST);
+      if (fixed_gpus == 0 && ready == (int)workers.size() && workers.size() < devs.size()) {
+        const double t_init = sh->t_last_ready - t_spawn_last;  // measured start-up of the newest worker
+        const int claimed = std::min(__atomic_load_n(&sh->next_chunk, __ATOMIC_SEQ_CST), nchunks);
+        const long long nt_done = __atomic_load_n(&sh->nt_done, __ATOMIC_SEQ_CST);
+        const double busy = since_start() - sh->t_first_ready;
+        // rate of the running workers together; before the first chunk is back, assume the rest takes forever
+        const double rate = (nt_done > 0 && busy > 0) ? (double)nt_done / busy : 0.0;
+        const double unclaimed_nt = (double)total_nt * (double)(nchunks - claimed) / (double)std::max(nchunks, 1);
+        const double remaining = rate > 0 ? unclaimed_nt / rate : 1e30;
+        if (nchunks - claimed > (int)workers.size() && remaining > t_init) {
+          t_spawn_last = since_start();
+          if (timer.on)
+            std::fprintf(stderr, "[db] t=%.2f s: recruiting GPU %s (start-up %.2f s measured, %.2f s of work unclaimed)\n",
+                         t_spawn_last, devs[workers.size()].c_str(), t_init, remaining > 1e29 ? -1.0 : remaining);
+          spawn((int)workers.size());
+        }
+      }
+      usleep(2000);
+    }
+    if (timer.on) std::fprintf(stderr, "[db] used %d GPU(s), one worker process each\n", (int)workers.size());
+    // whoever still runs is starting up or tearing down and has nothing left to do
+    for (pid_t pid : workers) {
+      int st = 0;
+      if (waitpid(pid, &st, WNOHANG) == 0) kill(pid, SIGKILL);
+    }
+    munmap(sh, 4096);
+  } else {
+    std::string err_si;
+    if (!write_seq_ind(db, seqs, prm, err_si, nullptr)) {  // test switch: host suffix arrays, no GPU
+      ok = false;
+      err = err_si;
+    }
+    if (ok && !write_nam(db, names, err)) ok = false;
+    if (ok && !write_bas(db, prm, err)) ok = false;
   }
-  bool ok = true;
-  std::string err_si;
-  if (formats_only && !write_seq_ind(db, seqs, prm, err_si, nullptr)) {  // test switch: host suffix arrays, no GPU
-    ok = false;
-    err = err_si;
-  }
-  if (ok && !write_nam(db, names, err)) ok = false;
-  if (ok && !write_bas(db, prm, err)) ok = false;
-  timer.lap(".nam/.bas");
-  bool workers_ok = true;
-  for (int fd : status_fd) {  // one status byte per worker; its process may still be tearing down afterwards
-    char st = 0;
-    if (read(fd, &st, 1) != 1 || st != 'k') workers_ok = false;
-    close(fd);
-  }
-  for (pid_t pid : workers) waitpid(pid, nullptr, WNOHANG);
   timer.lap("accessibility (GPU workers) + .acc/.seq/.ind");
   if (!workers_ok) return die("Error: an accessibility worker failed (see above); the database is incomplete");
   if (!ok) return die(err);
