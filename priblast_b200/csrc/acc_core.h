@@ -157,6 +157,8 @@ struct Ctx {
   int32_t *bad;            // one counter per batch: outputs that are not finite (0 = all good); may be null
 
   PRIB_HD real &at(int a, int d, long long g) const { return arr[a][(long long)d * NC + g]; }
+  // persistent result of a tile kernel (streaming stores, st.global.cs, were measured here: no difference)
+  PRIB_HD void put(int a, int d, long long g, real v) const { arr[a][(long long)d * NC + g] = v; }
   PRIB_HD real ld(int a, int d, long long g) const { return arr[a][(long long)d * NC + g]; }
 };
 

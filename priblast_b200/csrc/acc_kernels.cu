@@ -84,10 +84,36 @@ __device__ __forceinline__ void prog_wait(const int *prog, int warp, int need) {
     asm volatile("ld.acquire.cta.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
   } while (v < need);
 }
+#if defined(PRIB_RELAXED_SYNC)
+// Shared-memory-only hand-over: the ring rows and the counter live in the same shared memory, whose accesses are
+// performed in the order the SM issues them (STS of the data, then — after __syncwarp — the STS of the counter; the
+// reader's LDS of the data are issued after its LDS of the counter returned).  No fence, hence no wait for the global
+// stores in flight.  The scratch rows in GLOBAL memory are covered by the release/acquire pair of the last step of
+// each group (prog_signal / prog_wait), which is the event the deep steps wait for.
+__device__ __forceinline__ void prog_signal_smem(int *prog, int warp, int lane, int value) {
+  __syncwarp();
+  if (lane == 0)
+    asm volatile("st.volatile.shared.b32 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(prog + warp)), "r"(value) : "memory");
+}
+__device__ __forceinline__ void prog_wait_smem(const int *prog, int warp, int need) {
+  const unsigned addr = (unsigned)__cvta_generic_to_shared(prog + warp);
+  int v;
+  do {
+    asm volatile("ld.volatile.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  } while (v < need);
+}
+#else
+__device__ __forceinline__ void prog_signal_smem(int *prog, int warp, int lane, int value) { prog_signal(prog, warp, lane, value); }
+__device__ __forceinline__ void prog_wait_smem(const int *prog, int warp, int need) { prog_wait(prog, warp, need); }
+#endif
 struct StepSignal {  // the hook of Tile::inside_shallow / outside_shallow: runs right after the ring / scratch stores
   int *prog;
   int warp, lane, value;
-  __device__ __forceinline__ void operator()() const { prog_signal(prog, warp, lane, value); }
+  bool release;  // last step of a group: release semantics (covers the scratch rows in global memory)
+  __device__ __forceinline__ void operator()() const {
+    if (release) prog_signal(prog, warp, lane, value);
+    else prog_signal_smem(prog, warp, lane, value);
+  }
 };
 
 template <typename real, int PAR /* parity of the first span of every group (chain formulation) */>
@@ -141,16 +167,16 @@ k_inside_tile(typename Core<real>::Ctx c, int TX, long long ntiles, real *scratc
       } else {
         TL::template inside_deep<TC>(T, ge, sm, scrM1, scrM2, t, d0, gs, mb, bs);
       }
-      prog_signal(prog, warp, lane, ++ev);
+      prog_signal_smem(prog, warp, lane, ++ev);
 #pragma unroll
       for (int k = 0; k < kTT; ++k) {
         ++ev;  // this step's event
         if (d0 + k >= kTurn) {  // uniform
-          if ((k > 0 || CH) && warp + 1 < NW) prog_wait(prog, warp + 1, ev - 1);
-          if (CH && warp + 2 < NW) prog_wait(prog, warp + 2, ev - 1 - k);  // its deep step of this group wrote my columns
-          if (warp > 0) prog_wait(prog, warp - 1, ev - kEvSlackIn);
+          if ((k > 0 || CH) && warp + 1 < NW) prog_wait_smem(prog, warp + 1, ev - 1);
+          if (CH && warp + 2 < NW) prog_wait_smem(prog, warp + 2, ev - 1 - k);  // its deep step of this group wrote my columns
+          if (warp > 0) prog_wait_smem(prog, warp - 1, ev - kEvSlackIn);
           TL::template inside_shallow<TC>(c, T, ge, sm, scrM1, scrM2, t, cs, d0 + k, CH ? xch[k * TC + t] : gs[k], mb[k],
-                                          bs[k], StepSignal{prog, warp, lane, ev});
+                                          bs[k], StepSignal{prog, warp, lane, ev, k == kTT - 1});
         } else {
           prog_signal(prog, warp, lane, ev);
         }
@@ -215,16 +241,16 @@ k_outside_tile(typename Core<real>::Ctx c, int TX, long long ntiles, real *scrat
       } else {
         TL::template outside_deep<TC>(c, T, ge, sm, scrBif, t, cs, d0, slot, o);
       }
-      prog_signal(prog, warp, lane, ++ev);
+      prog_signal_smem(prog, warp, lane, ++ev);
 #pragma unroll
       for (int k = 0; k < kTT; ++k) {
         ++ev;
         if (d0 - k >= kTurn) {  // uniform
-          if ((k > 0 || CH) && warp > 0) prog_wait(prog, warp - 1, ev - 1);
-          if (CH && warp >= 2) prog_wait(prog, warp - 2, ev - 1 - k);
-          if (warp + 1 < NW) prog_wait(prog, warp + 1, ev - kEvSlackOut);
+          if ((k > 0 || CH) && warp > 0) prog_wait_smem(prog, warp - 1, ev - 1);
+          if (CH && warp >= 2) prog_wait_smem(prog, warp - 2, ev - 1 - k);
+          if (warp + 1 < NW) prog_wait_smem(prog, warp + 1, ev - kEvSlackOut);
           TL::template outside_shallow<TC>(c, T, ge, sm, scrBif, t, cs, d0 - k, slot, CH ? xch[k * TC + t] : o.gs[k],
-                                           o.bs[k], o.bm1[k], o.ks[k], StepSignal{prog, warp, lane, ev});
+                                           o.bs[k], o.bm1[k], o.ks[k], StepSignal{prog, warp, lane, ev, k == kTT - 1});
         } else {
           prog_signal(prog, warp, lane, ev);
         }
@@ -293,11 +319,24 @@ __device__ void warp_scan(const typename Core<real>::Ctx &c, int sq, double *rin
     }
     const real *wb = wbuf + cur * half;
     double ext = 0;
-    for (int d = imax(5, lane + 1); d <= dhi; ++d)  // partners before the block
-      ext += (double)wb[(d - 5) * 32 + lane] * usm[d] * ring[(st - d) & 255];
+    {  // partners before the block: four independent partial sums (the DFMA chain is the latency here)
+      double e0 = 0, e1 = 0, e2s = 0, e3 = 0;
+      int d = imax(5, lane + 1);
+      for (; d + 3 <= dhi; d += 4) {
+        const double w0 = (double)wb[(d - 5) * 32 + lane] * usm[d], w1 = (double)wb[(d - 4) * 32 + lane] * usm[d + 1];
+        const double w2 = (double)wb[(d - 3) * 32 + lane] * usm[d + 2], w3 = (double)wb[(d - 2) * 32 + lane] * usm[d + 3];
+        e0 += w0 * ring[(st - d) & 255];
+        e1 += w1 * ring[(st - d - 1) & 255];
+        e2s += w2 * ring[(st - d - 2) & 255];
+        e3 += w3 * ring[(st - d - 3) & 255];
+      }
+      for (; d <= dhi; ++d) e0 += (double)wb[(d - 5) * 32 + lane] * usm[d] * ring[(st - d) & 255];
+      ext = (e0 + e1) + (e2s + e3);
+    }
     double vprev = ring[(st0 - 1) & 255];
     double myv = 0;
     const int nsub = imin(32, L - st0 + 1);
+#pragma unroll 4
     for (int s = 0; s < nsub; ++s) {
       const double vs = __shfl_sync(0xffffffffu, vprev + ext, s);  // lane s holds v[s-1] + ext[s]
       if (lane == s) myv = vs;

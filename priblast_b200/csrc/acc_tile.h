@@ -524,13 +524,13 @@ struct Tile {
     if (t < ge.TX && i >= 0 && j <= L) {
 #endif
       const long long g = ge.g0 + t;
-      if (c.delta == 2) c.at(A_STEM, d, g) = stem;  // only the 2x1 / 2x2 loops of delta == 2 read it (BiTile)
-      c.at(A_STEMI, d, g) = stemI;
-      c.at(A_STEMB, d, g) = stemB;
-      c.at(A_STEMD, d, g) = stemD;
-      c.at(A_MULTI, d, g) = mu;
-      c.at(A_MULTI1, d, g) = m1;
-      c.at(A_MULTI2, d, g) = m2;
+      if (c.delta == 2) c.put(A_STEM, d, g, stem);  // only the 2x1 / 2x2 loops of delta == 2 read it (BiTile)
+      c.put(A_STEMI, d, g, stemI);
+      c.put(A_STEMB, d, g, stemB);
+      c.put(A_STEMD, d, g, stemD);
+      c.put(A_MULTI, d, g, mu);
+      c.put(A_MULTI1, d, g, m1);
+      c.put(A_MULTI2, d, g, m2);
       if (!(K::in_safe_range(stem) && K::in_safe_range(se) && K::in_safe_range(mu) && K::in_safe_range(m1) &&
             K::in_safe_range(m2)))
         c.flags[cs.sq] = 1;
@@ -927,11 +927,11 @@ struct Tile {
 #else
     if (t >= ge.H && p >= 0 && q <= L) {
 #endif
-      c.at(B_STEM, d, g) = bstem;
-      c.at(B_STEMO, d, g) = bstemO;
-      c.at(B_STEMB, d, g) = bstemB;
-      c.at(B_MULTI, d, g) = bmulti;
-      c.at(B_MULTI2, d, g) = bmulti2;
+      c.put(B_STEM, d, g, bstem);
+      c.put(B_STEMO, d, g, bstemO);
+      c.put(B_STEMB, d, g, bstemB);
+      c.put(B_MULTI, d, g, bmulti);
+      c.put(B_MULTI2, d, g, bmulti2);
       if (!(K::in_safe_range(bstem) && K::in_safe_range(bmulti) && K::in_safe_range(bmulti2) &&
             K::in_safe_range(bmbif)))
         c.flags[cs.sq] = 1;
