@@ -62,6 +62,8 @@ typedef struct prib_acc_counters {
   int64_t dp_state_bytes_used; /* part of it the largest batch so far used */
   double phase_ms[PRIB_NUM_PHASES]; /* device time per phase, summed over batches */
   int64_t fp64_rerun_sequences;  /* sequences the FP32 engine flagged and the FP64 engine recomputed */
+  int64_t fp32_flagged[4];       /* sequences whose FIRST FP32 pass left the safe range: [0] inside values too
+                                    large, [1] inside too small, [2] outside too large, [3] outside too small */
 } prib_acc_counters;
 
 /* Replaces the `Raccess` constructor.  One context per GPU; not re-entrant per context. */

@@ -41,6 +41,7 @@ class AccCounters(ctypes.Structure):
         ("dp_state_bytes_used", ctypes.c_int64),
         ("phase_ms", ctypes.c_double * 7),
         ("fp64_rerun_sequences", ctypes.c_int64),
+        ("fp32_flagged", ctypes.c_int64 * 4),
     ]
 
 

@@ -208,6 +208,20 @@ static PRIB_HD bool in_safe_range(real v) {
   const real hi = (real)3.6028797018963968e16, lo = (real)2.7755575615628914e-17;
   return (v <= hi) && (v == 0 || v >= lo);
 }
+// which side a value left the safe range on: 1 = too large (or NaN), 2 = too small; the host uses it to pick the scale
+// of the second FP32 attempt (prib_acc_compute)
+static PRIB_HD int range_bits(real v) {
+  if (sizeof(real) == 8) return 0;
+  const real hi = (real)3.6028797018963968e16, lo = (real)2.7755575615628914e-17;
+  return !(v <= hi) ? 1 : (v != 0 && v < lo) ? 2 : 0;
+}
+static PRIB_HD void raise_flag(int32_t *flag, int bits) {
+#if defined(__CUDA_ARCH__)
+  atomicOr(flag, bits);
+#else
+  *flag |= bits;
+#endif
+}
 
 static PRIB_HD real e_dangle(const SmallTables &T, int t, bool a_gt0, int sa, bool b_lt_L, int sb1) {
   real x = 1;

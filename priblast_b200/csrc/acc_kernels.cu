@@ -1107,7 +1107,11 @@ int prib_acc_create(prib_ctx **out, const prib_acc_params *params) {
   int rc = setup_engine<double>(c, ScaleSpec(), prop.sharedMemPerBlockOptin, err);
   if (rc != PRIB_OK) return bail(rc == PRIB_EINVAL ? fail(rc, err) : rc);
   if (c->use_fp32) {
-    rc = setup_engine<float>(c, default_scale_fp32(), prop.sharedMemPerBlockOptin, err);
+    ScaleSpec sp32 = default_scale_fp32();
+    if (const char *e = getenv("PRIB_KLOG2")) sp32.klog2 = atof(e);  // tuning knobs (profiles/scale_scan.py)
+    if (const char *e = getenv("PRIB_ALOG2")) sp32.alog2 = atof(e);
+    if (const char *e = getenv("PRIB_BLOG2")) sp32.blog2 = atof(e);
+    rc = setup_engine<float>(c, sp32, prop.sharedMemPerBlockOptin, err);
     if (rc != PRIB_OK) return bail(rc == PRIB_EINVAL ? fail(rc, err) : rc);
   }
   if (params->mode == 2) {
@@ -1272,7 +1276,11 @@ int prib_acc_compute(prib_ctx *c) {
     for (size_t bi = 0; bi < c->n_batches; ++bi) {
       const Batch &b = c->batches[bi];
       for (int k = 0; k < b.n; k++)
-        if (c->h_flags[fpos + k]) flagged.push_back(b.ids[k]);
+        if (const int bits = c->h_flags[fpos + k]) {
+          flagged.push_back(b.ids[k]);
+          for (int q = 0; q < 4; q++)
+            if (bits & (1 << q)) c->cnt.fp32_flagged[q] += 1;
+        }
       fpos += b.n;
     }
   }

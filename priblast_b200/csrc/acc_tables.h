@@ -26,7 +26,12 @@ struct ScaleSpec {
 };
 inline ScaleSpec default_scale_fp32() {
   ScaleSpec s;
-  s.klog2 = 0.3;   // random-sequence inside weights grow ~2^0.6 per nt at the top, ~2^0 at the bottom
+  // kappa = 2^-0.45 per unit of span: measured on B200 over 1,000 uniform 2 kb sequences per span (profiles/r2/
+  // scale_scan.txt): sequences that leave the FP32 safe range and are re-run in FP64 with klog2 = 0.30 / 0.45:
+  // W = 70: 1 / 0, W = 100: 12 / 0, W = 150: 227 / 3, W = 200: 802 / 22.  What binds is the OUTSIDE side: Beta / Z of a
+  // wide cell is ~1 / Alpha of that cell, i.e. 2^-0.6..-0.7 per nt for well-structured windows, and the stored value
+  // cB kappa^-d (Beta / Z) fell under 2^-55 with the round-1 choice of 0.30.
+  s.klog2 = 0.45;
   s.alog2 = 4.0;
   s.blog2 = 16.0;
   return s;

@@ -533,7 +533,8 @@ struct Tile {
       c.put(A_MULTI2, d, g, m2);
       if (!(K::in_safe_range(stem) && K::in_safe_range(se) && K::in_safe_range(mu) && K::in_safe_range(m1) &&
             K::in_safe_range(m2)))
-        c.flags[cs.sq] = 1;
+        K::raise_flag(&c.flags[cs.sq], K::range_bits(stem) | K::range_bits(se) | K::range_bits(mu) | K::range_bits(m1) |
+                                           K::range_bits(m2));
     }
   }
 
@@ -934,7 +935,8 @@ struct Tile {
       c.put(B_MULTI2, d, g, bmulti2);
       if (!(K::in_safe_range(bstem) && K::in_safe_range(bmulti) && K::in_safe_range(bmulti2) &&
             K::in_safe_range(bmbif)))
-        c.flags[cs.sq] = 1;
+        K::raise_flag(&c.flags[cs.sq], 4 * (K::range_bits(bstem) | K::range_bits(bmulti) | K::range_bits(bmulti2) |
+                                                K::range_bits(bmbif)));
     }
   }
 };

@@ -189,6 +189,7 @@ class Raccess:
         _capi.check(self._lib.prib_acc_get_counters(self._ctx, ctypes.byref(c)))
         d = {k: getattr(c, k) for k, _ in c._fields_}
         d["phase_ms"] = dict(zip(_capi.PHASE_NAMES, list(c.phase_ms)))
+        d["fp32_flagged"] = list(c.fp32_flagged)
         return d
 
 

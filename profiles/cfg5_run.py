@@ -87,16 +87,27 @@ def main():
             out[name] = hits(os.path.join(d, f"hits_{name}.txt"))
         rr, rt = out["ref"]
         res["hits_reference"] = len(rr)
+        ref_by_key = {a[:3]: a for a in rr}
         for name in ("fast", "exact"):
             gr, gt = out[name]
-            same_struct = [a[:3] for a in rr] == [b[:3] for b in gr]
+            got_by_key = {b[:3]: b for b in gr}
+            common = [k for k in ref_by_key if k in got_by_key]
+            only_ref = [ref_by_key[k] for k in ref_by_key if k not in got_by_key]
+            only_got = [got_by_key[k] for k in got_by_key if k not in ref_by_key]
             res[f"hits_{name}"] = len(gr)
-            res[f"structural_hit_list_identical_{name}"] = same_struct
+            res[f"structural_hit_list_identical_{name}"] = not only_ref and not only_got
+            res[f"hits_common_{name}"] = len(common)
+            res[f"hits_only_in_reference_{name}"] = len(only_ref)
+            res[f"hits_only_in_gpu_db_{name}"] = len(only_got)
+            # the hits that exist on one side only: their interaction energy against the `-e` cut-off of ris (-6 by
+            # default, main.cpp): a hit whose energy sits within the .acc tolerance of the cut-off can fall either way
+            res[f"one_sided_hits_interaction_energy_{name}"] = sorted(round(h[5], 4) for h in only_ref + only_got)[:20]
+            if common:
+                res[f"max_energy_difference_common_hits_{name}"] = max(
+                    max(abs(ref_by_key[k][3] - got_by_key[k][3]), abs(ref_by_key[k][4] - got_by_key[k][4]),
+                        abs(ref_by_key[k][5] - got_by_key[k][5])) for k in common)
             res[f"text_identical_{name}"] = rt == gt
-            if same_struct and rr:
-                res[f"max_energy_difference_{name}"] = max(max(abs(a[3] - b[3]), abs(a[4] - b[4]), abs(a[5] - b[5]))
-                                                           for a, b in zip(rr, gr))
-            res[f"printed_lines_differing_{name}"] = sum(1 for a, b in zip(rt, gt) if a != b) + abs(len(rt) - len(gt))
+            res[f"printed_lines_differing_{name}"] = len(set(rt) ^ set(gt)) // 2
     s = json.dumps(res, indent=1)
     print(s)
     if len(sys.argv) > 3:

@@ -4,5 +4,8 @@
 cd "$(dirname "$0")/.."
 for tool in memcheck racecheck initcheck synccheck; do
   echo "=== compute-sanitizer --tool $tool python -c '__graft_entry__.smoke()'"
-  timeout 900 compute-sanitizer --tool $tool --print-limit 5 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | grep -E "ERROR SUMMARY|smoke ok|Error|error|RACECHECK SUMMARY|hazard" | head -12
+  timeout 900 compute-sanitizer --tool $tool --print-limit 5 python -c "import __graft_entry__ as g; g.smoke()" > /tmp/san_$tool.log 2>&1
+  echo "exit code $?"
+  grep -E "ERROR SUMMARY|smoke ok|RACECHECK SUMMARY|hazard|Invalid|Uninitialized|Barrier error" /tmp/san_$tool.log | head -12
+  tail -3 /tmp/san_$tool.log
 done
