@@ -410,7 +410,7 @@ __device__ __forceinline__ void load_band_tile(const typename Core<real>::Ctx &c
 }
 
 template <typename real, bool LEFT, int ULO, int TXB>
-__global__ void __launch_bounds__(512) k_biloop_tile(typename Core<real>::Ctx c) {
+__global__ void __launch_bounds__(TXB > 0 ? TXB : 512, TXB == 256 ? 2 : TXB == 192 ? 3 : TXB == 128 ? 4 : 1) k_biloop_tile(typename Core<real>::Ctx c) {
   typedef BiTile<real> BT;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   typename BT::Geo ge;
@@ -442,13 +442,17 @@ __global__ void __launch_bounds__(512) k_biloop_tile(typename Core<real>::Ctx c)
 template <typename real, bool LEFT>
 void launch_biloop(const typename Core<real>::Ctx &k, unsigned grid, int TXb, size_t smem, cudaStream_t st) {
   const bool d5 = k.delta >= 5;
-  if (TXb == 256) {  // the default width: row stride known at compile time
-    if (d5) k_biloop_tile<real, LEFT, 5, 256><<<grid, TXb, smem, st>>>(k);
-    else k_biloop_tile<real, LEFT, 2, 256><<<grid, TXb, smem, st>>>(k);
-  } else {
-    if (d5) k_biloop_tile<real, LEFT, 5, 0><<<grid, TXb, smem, st>>>(k);
-    else k_biloop_tile<real, LEFT, 2, 0><<<grid, TXb, smem, st>>>(k);
-  }
+#define PRIB_BI_LAUNCH(X)                                                         \
+  do {                                                                            \
+    if (d5) k_biloop_tile<real, LEFT, 5, X><<<grid, TXb, smem, st>>>(k);          \
+    else k_biloop_tile<real, LEFT, 2, X><<<grid, TXb, smem, st>>>(k);             \
+  } while (0)
+  // the tuned widths have the tile row stride (and the CTAs per SM) fixed at compile time
+  if (TXb == 256) PRIB_BI_LAUNCH(256);
+  else if (TXb == 192) PRIB_BI_LAUNCH(192);
+  else if (TXb == 128) PRIB_BI_LAUNCH(128);
+  else PRIB_BI_LAUNCH(0);
+#undef PRIB_BI_LAUNCH
 }
 
 template <typename real>
@@ -1019,6 +1023,8 @@ int setup_engine(prib_ctx *c, const ScaleSpec &spec, size_t smem_max, std::strin
 #define PRIB_BI_ATTR(L, U, X) \
   CU(cudaFuncSetAttribute((k_biloop_tile<real, L, U, X>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max))
   PRIB_BI_ATTR(true, 5, 256); PRIB_BI_ATTR(true, 2, 256); PRIB_BI_ATTR(false, 5, 256); PRIB_BI_ATTR(false, 2, 256);
+  PRIB_BI_ATTR(true, 5, 192); PRIB_BI_ATTR(true, 2, 192); PRIB_BI_ATTR(false, 5, 192); PRIB_BI_ATTR(false, 2, 192);
+  PRIB_BI_ATTR(true, 5, 128); PRIB_BI_ATTR(true, 2, 128); PRIB_BI_ATTR(false, 5, 128); PRIB_BI_ATTR(false, 2, 128);
   PRIB_BI_ATTR(true, 5, 0); PRIB_BI_ATTR(true, 2, 0); PRIB_BI_ATTR(false, 5, 0); PRIB_BI_ATTR(false, 2, 0);
 #undef PRIB_BI_ATTR
   return PRIB_OK;

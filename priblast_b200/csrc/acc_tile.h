@@ -52,6 +52,18 @@ enum {
   kOutBaseTail = 8,  // ... and reach W + 4 columns past its right edge (s[d + 3] of the last column)
 };
 
+// L1 prefetch of a global line a few loop rounds ahead (multibranch sums: every round touches one new line per array).
+// Measured on B200 (profiles/r2/experiments.md): slightly SLOWER than without (the extra issue slots cost more than the
+// L2 latency they hide), so it stays an opt-in experiment switch.
+PRIB_HD void prefetch_l1(const void *p) {
+#if defined(__CUDA_ARCH__) && defined(PRIB_PREFETCH)
+  asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+#else
+  (void)p;
+#endif
+}
+enum { kPfDist = 6 };  // rows ahead
+
 #if defined(__CUDA_ARCH__)
 // Blackwell packed FP32: one FFMA2 = two FMAs with the same multiplicand v (scalar operand, broadcast to both
 // halves) and a coefficient PAIR from the constant bank (uniform-register operand): acc.lo += v * g.x, acc.hi += v * g.y.
@@ -299,6 +311,10 @@ struct Tile {
       if (d0 == 1000)
 #endif
       for (; m + 1 <= d0 - 5; m += 2) {  // two m per round, 10 independent loads in flight
+        if (m + kPfDist + 1 <= d0 - 5) {
+          prefetch_l1(pa + (kPfDist + 1) * TC);
+          prefetch_l1(pb - (kPfDist + 1) * (TC - 1));
+        }
         const real a0 = pa[0], a1 = pa[TC];
         real b0[kTT], b1[kTT];
 #pragma unroll
@@ -685,6 +701,10 @@ struct Tile {
       if (d0 == 1000)
 #endif
       for (; s + 1 <= shi; s += 2) {  // two rows per round, 10 independent loads in flight
+        if (s + kPfDist + 1 <= shi) {
+          prefetch_l1(pa + (kPfDist + 1) * TC);
+          prefetch_l1(pb + (long long)(kPfDist + 1) * nc + (long long)(kTT - 1) * (nc - 1));
+        }
         const real a0 = pa[0], a1 = pa[TC];
         real b0[kTT], b1[kTT];
 #pragma unroll
@@ -715,6 +735,10 @@ struct Tile {
       if (d0 == 1000)
 #endif
       for (; m + 1 <= mhi; m += 2) {
+        if (m + kPfDist + 1 <= mhi) {
+          prefetch_l1(pb + (long long)(kPfDist + 1) * (nc - 1));
+          prefetch_l1(pa + (kPfDist + 1) * (TC - 1));
+        }
         const real b0 = pb[0], b1 = pb[nc - 1];
         real a0[kTT], a1[kTT];
 #pragma unroll
