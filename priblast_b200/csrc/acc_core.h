@@ -78,6 +78,9 @@ static __constant__ float g_cf_f[32];
 // (cg[a], cg[b]) for a, b = 0..7 (index 7 = 0): coefficient pairs of the packed FP32 stencils (FFMA2 takes the pair
 // as a 64-bit uniform-register operand, so the coefficients cost no vector registers)
 static __constant__ float2 g_cgpair_f[64];
+// (conv[u][sum - u], conv[u + 1][sum - u - 1]) at [u * 32 + sum]: the coefficient pairs of the packed strand-weight
+// pass (two strand lengths per FFMA2; a 64-bit constant operand instead of two LDC + a MOV per pair)
+static __constant__ float2 g_convpair_f[32 * 32];
 // cg[0..6] for the centre-line chain of the tile kernels (acc_tile.h)
 static __constant__ double g_cg_d[8];
 static __constant__ float g_cg_f[8];
@@ -570,6 +573,7 @@ static PRIB_HD void hairpin_suffix(const Ctx &c, long long g) {
   const SmallTables &T = *c.T;
   const uint8_t *s = c.S + g;
   real suf = 0;
+#pragma unroll 4
   for (int dd = W; dd >= 4; --dd) {
     if (i >= 1 && i + dd <= L) {
       const real bse = c.ld(B_STEM, dd + 1, g - 1);
@@ -631,6 +635,7 @@ static PRIB_HD void multi_prob_pair(const Ctx &c, long long off, int L, int x, i
     const int e0 = x + w - 1 + 5;  // first term of the w sum; the w + 1 sum starts one later
     if (e0 <= hi)
       v0 += (double)c.ld(B_MULTI, e0 - x + 1, off + x - 1) * (double)c.ld(A_MULTI, e0 - x - w + 1, off + x + w - 1);
+#pragma unroll 4
     for (int e = e0 + 1; e <= hi; ++e) {
       const double b = (double)c.ld(B_MULTI, e - x + 1, off + x - 1);
       v0 += b * (double)c.ld(A_MULTI, e - x - w + 1, off + x + w - 1);
@@ -641,6 +646,7 @@ static PRIB_HD void multi_prob_pair(const Ctx &c, long long off, int L, int x, i
     const int lo0 = imax(0, x + w - 1 - W), lo1 = imax(0, x + w - W);
     if (lo1 > lo0 && lo0 <= x - 1 - 5)  // the w sum reaches one column further to the left
       v0 += (double)c.ld(B_MULTI2, x + w - 1 - lo0, off + lo0) * (double)c.ld(A_MULTI2, x - lo0 - 1, off + lo0);
+#pragma unroll 4
     for (int b = lo1; b <= x - 1 - 5; ++b) {
       const double a = (double)c.ld(A_MULTI2, x - b - 1, off + b);
       v0 += (double)c.ld(B_MULTI2, x + w - 1 - b, off + b) * a;
@@ -653,6 +659,7 @@ static PRIB_HD void multi_prob_pair(const Ctx &c, long long off, int L, int x, i
 
 static PRIB_HD double hairpin_prob(const Ctx &c, long long off, int x, int w) {  // :536-579
   double v = 0;
+#pragma unroll 4
   for (int i = imax(1, x - c.W); i < x; ++i) {
     const int dd = x + w - i;
     if (dd <= c.W) v += c.ld(X_SUFH, dd < 4 ? 4 : dd, off + i);
@@ -665,11 +672,13 @@ static PRIB_HD void biloop_gather(const Ctx &c, long long off, int L, int k, dou
   const int w = c.delta;
   b = 0;
   cc = 0;
+#pragma unroll 4
   for (int i = imax(1, k + w - 1 - kMaxLoop); i <= k - 1; ++i) {
     const int ub = k + w - 1 - i;  // strand length whose last base is the window end
     b += c.ld(X_ML, ub, off + i);
     if (ub + 1 <= kMaxLoop) cc += c.ld(X_MLS, ub + 1, off + i);
   }
+#pragma unroll 4
   for (int jp = k + w - 1; jp <= imin(L - 1, k + kMaxLoop - 1); ++jp) {
     const int umin = jp - k + 1;  // strand must start before k
     if (jp == k + w - 1) b += c.ld(X_MRS, umin, off + jp);

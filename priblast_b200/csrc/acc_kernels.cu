@@ -297,10 +297,10 @@ __device__ void warp_scan(const typename Core<real>::Ctx &c, int sq, double *rin
   auto stage = [&](int st0, real *buf) {  // this lane's weights of block st0: w(st, d), d = 5 .. W + 1
     const int st = st0 + lane;
     const int dhi = st <= L ? imin(W + 1, st) : 0;
-    const real *col = src + off + (ALPHA ? st : L - st);
-    for (int d = 5; d <= W + 1; ++d)
-      cp_async_or_zero<(int)sizeof(real)>(buf + (d - 5) * 32 + lane, d <= dhi ? col + (long long)d * (c.NC - (ALPHA ? 1 : 0)) : src,
-                                           d <= dhi);
+    const long long stride = c.NC - (ALPHA ? 1 : 0);
+    const real *p = src + off + (ALPHA ? st : L - st) + 5 * stride;  // running pointers: the address arithmetic of this
+    real *q = buf + lane;                                             // loop was 27 % of the kernel's instructions
+    for (int d = 5; d <= W + 1; ++d, p += stride, q += 32) cp_async_or_zero<(int)sizeof(real)>(q, d <= dhi ? p : src, d <= dhi);
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
   int cur = 0;
@@ -322,9 +322,10 @@ __device__ void warp_scan(const typename Core<real>::Ctx &c, int sq, double *rin
     {  // partners before the block: four independent partial sums (the DFMA chain is the latency here)
       double e0 = 0, e1 = 0, e2s = 0, e3 = 0;
       int d = imax(5, lane + 1);
-      for (; d + 3 <= dhi; d += 4) {
-        const double w0 = (double)wb[(d - 5) * 32 + lane] * usm[d], w1 = (double)wb[(d - 4) * 32 + lane] * usm[d + 1];
-        const double w2 = (double)wb[(d - 3) * 32 + lane] * usm[d + 2], w3 = (double)wb[(d - 2) * 32 + lane] * usm[d + 3];
+      const real *wp = wb + (d - 5) * 32 + lane;
+      for (; d + 3 <= dhi; d += 4, wp += 128) {
+        const double w0 = (double)wp[0] * usm[d], w1 = (double)wp[32] * usm[d + 1];
+        const double w2 = (double)wp[64] * usm[d + 2], w3 = (double)wp[96] * usm[d + 3];
         e0 += w0 * ring[(st - d) & 255];
         e1 += w1 * ring[(st - d - 1) & 255];
         e2s += w2 * ring[(st - d - 2) & 255];
@@ -983,6 +984,15 @@ int setup_engine(prib_ctx *c, const ScaleSpec &spec, size_t smem_max, std::strin
       for (int b = 0; b < 8; b++)
         pairs[a * 8 + b] = make_float2(a < 7 ? (float)tab.small.cg[a] : 0.f, b < 7 ? (float)tab.small.cg[b] : 0.f);
     CU(cudaMemcpyToSymbol(g_cgpair_f, pairs, sizeof(pairs)));
+    std::vector<float2> cp(32 * 32, make_float2(0.f, 0.f));
+    for (int u = 0; u < 32; u++)
+      for (int sum = 0; sum < 32; sum++) {
+        const int u2a = sum - u, u2b = sum - u - 1;
+        const float a = (u2a >= 0 && u2a < 32) ? (float)tab.small.conv[u][u2a] : 0.f;
+        const float b = (u + 1 < 32 && u2b >= 0 && u2b < 32) ? (float)tab.small.conv[u + 1][u2b] : 0.f;
+        cp[u * 32 + sum] = make_float2(a, b);
+      }
+    CU(cudaMemcpyToSymbol(g_convpair_f, cp.data(), sizeof(float2) * cp.size()));
   }
   if (c->d_log == nullptr) {
     CU(cudaMalloc(&c->d_log, tab.log_tbl.size() * sizeof(float)));

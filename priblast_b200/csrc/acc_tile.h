@@ -240,6 +240,9 @@ struct Tile {
         // FP32 engine: targets (0, 1) and (2, 3) share one FFMA2 each per source element; a target that does not
         // take the element gets the coefficient 0 (index 7 of the pair table) — the same sums, two FMAs per issue slot
         unsigned long long r01 = 0, r23 = 0;
+#if defined(PRIB_SPLIT_ACC)
+        unsigned long long r01b = 0, r23b = 0;  // even / odd elements in separate chains: half the dependent-FFMA2 depth
+#endif
 #pragma unroll
         for (int x = 1; x <= S + kTT - 2; ++x) {
 #if defined(PRIB_EXP_HALFLDS)
@@ -248,6 +251,13 @@ struct Tile {
           const float v = row[x];
 #endif
           const int a0 = in_cidx(x, S), a1 = in_cidx(x, S + 1), a2 = in_cidx(x, S + 2), a3 = in_cidx(x, S + 3);
+#if defined(PRIB_SPLIT_ACC)
+          if (x & 1) {
+            if (a0 != 7 || a1 != 7) ffma2_bcast(r01b, v, g_cgpair_f[a0 * 8 + a1]);
+            if (a2 != 7 || a3 != 7) ffma2_bcast(r23b, v, g_cgpair_f[a2 * 8 + a3]);
+            continue;
+          }
+#endif
           if (a0 != 7 || a1 != 7) ffma2_bcast(r01, v, g_cgpair_f[a0 * 8 + a1]);
 #if !defined(PRIB_EXP_HALFFMA)
           if (a2 != 7 || a3 != 7) ffma2_bcast(r23, v, g_cgpair_f[a2 * 8 + a3]);
@@ -256,6 +266,14 @@ struct Tile {
         float q0, q1, q2, q3;
         unpack2(r01, q0, q1);
         unpack2(r23, q2, q3);
+#if defined(PRIB_SPLIT_ACC)
+        {
+          float p0, p1, p2, p3;
+          unpack2(r01b, p0, p1);
+          unpack2(r23b, p2, p3);
+          q0 += p0, q1 += p1, q2 += p2, q3 += p3;
+        }
+#endif
         rs[0] = q0, rs[1] = q1, rs[2] = q2, rs[3] = q3;
       } else
 #endif
@@ -1110,9 +1128,7 @@ struct BiTile {
 #pragma unroll
         for (int k = 0; k < kTT; ++k) {
           const bool a = dn_valid(U, S + k), b = dn_valid(U + 1, S + k);
-          if (a || b)
-            ffma2(qq, pack2(w[k], w[k]),
-                  pack2(a ? cv[U * 32 + (S + k - U)] : 0.f, b ? cv[(U + 1) * 32 + (S + k - U - 1)] : 0.f));
+          if (a || b) ffma2_bcast(qq, w[k], g_convpair_f[U * 32 + S + k]);  // the table holds 0 where a loop does not exist
         }
       } else {
         float q0 = 0, q1 = 0;
@@ -1237,6 +1253,10 @@ struct BiTile {
     const int delta = c.delta, TXb = ge.TXb, cols = COLS > 0 ? COLS : ge.cols;
     real (&ml)[kMaxLoop + 1] = st.w;
     real bseB_next = st.cnt > 0 ? c.ld(B_STEMB, list[t] + 2, g - 1) : (real)0;
+    // sum over the closing spans first, the bulge factor bu[u1] once at the end (it does not depend on the span)
+    real bsum[kMaxLoop + 1];
+#pragma unroll
+    for (int u1 = 0; u1 <= kMaxLoop; ++u1) bsum[u1] = 0;
     for (int k = 0; k < st.cnt; ++k) {
       const int dp = list[k * TXb + t];
       const real bseB = bseB_next;
@@ -1245,8 +1265,11 @@ struct BiTile {
       const real *base = tile + (dp - 5) * cols + t;
 #pragma unroll
       for (int u1 = ULO; u1 <= kMaxLoop; ++u1)
-        if (u1 >= delta && u1 <= umax) ml[u1] += bseB * bu[u1] * base[u1 - u1 * cols];  // cell (i+u1, j'), span dp-u1
+        if (u1 <= umax) bsum[u1] += bseB * base[u1 - u1 * cols];  // cell (i+u1, j'), span dp-u1
     }
+#pragma unroll
+    for (int u1 = ULO; u1 <= kMaxLoop; ++u1)
+      if (u1 >= delta) ml[u1] += bu[u1] * bsum[u1];
     real suf = 0;
 #pragma unroll
     for (int u1 = kMaxLoop; u1 >= 2; --u1) {
@@ -1345,6 +1368,9 @@ struct BiTile {
     const int delta = c.delta, TXb = ge.TXb, cols = COLS > 0 ? COLS : ge.cols;
     real (&mr)[kMaxLoop + 1] = st.w;
     real bseB_next = st.cnt > 0 ? c.ld(B_STEMB, list[t] + 2, g2 - list[t] - 1) : (real)0;
+    real bsum[kMaxLoop + 1];
+#pragma unroll
+    for (int u2 = 0; u2 <= kMaxLoop; ++u2) bsum[u2] = 0;
     for (int k = 0; k < st.cnt; ++k) {
       const int dp = list[k * TXb + t];
       const real bseB = bseB_next;
@@ -1356,8 +1382,11 @@ struct BiTile {
       const real *base = tile + (dp - 5) * cols + t + 31;
 #pragma unroll
       for (int u2 = ULO; u2 <= kMaxLoop; ++u2)
-        if (u2 >= delta && u2 <= umax) mr[u2] += bseB * bu[u2] * base[-u2 - u2 * cols];  // cell (i, j'-u2), span dp-u2
+        if (u2 <= umax) bsum[u2] += bseB * base[-u2 - u2 * cols];  // cell (i, j'-u2), span dp-u2
     }
+#pragma unroll
+    for (int u2 = ULO; u2 <= kMaxLoop; ++u2)
+      if (u2 >= delta) mr[u2] += bu[u2] * bsum[u2];
     real suf = 0;
 #pragma unroll
     for (int u2 = kMaxLoop; u2 >= 2; --u2) {
