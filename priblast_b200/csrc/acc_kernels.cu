@@ -57,12 +57,45 @@ template <typename real> struct TileMaxThreads { static constexpr int value = si
 // ---------------------------------------------------------------------------------------------
 // grid = resident CTAs (one per SM: the rings take ~all shared memory), blockDim = TC, tiles round-robin.
 // dynamic smem: (kTilePad + kTileRows * TC) reals + hot tables + (TC + 16) base codes.
-constexpr int kProgBytes = 128;  // 32 per-warp progress counters (warp-to-warp synchronisation of the tile kernels)
+constexpr int kProgBytes = 128 + 16;  // 32 per-warp progress counters (warp-to-warp synchronisation of the tile kernels) + the
+                                      // transaction barrier of the table copy
 template <typename real>
 __host__ __device__ constexpr size_t tile_smem_bytes() {
   return ((size_t)kTilePad + (size_t)kTileRows * TileMaxThreads<real>::value) * sizeof(real) +
          (Core<real>::kHotBytes + TileMaxThreads<real>::value + kMaxSpan + 16 + 15) / 16 * 16  // + base codes (outside: TC + W + 8)
          + kProgBytes;                                                                           // + the per-warp progress counters
+}
+
+// ---- TMA (bulk asynchronous copy) staging of a band tile -------------------------------------------------
+// The start-indexed tile of the left-strand kernel is `rows` contiguous, 16-byte aligned segments of a span-major
+// array (row r = columns g0 .. g0 + cols - 1 of span r + 5), so ONE thread hands the whole tile to the copy engine
+// (cp.async.bulk.shared.global, SASS UBLKCP) and every thread waits on the transaction barrier; no registers and no
+// LSU instructions carry the data.  Cells that do not exist (the DP state is not cleared between batches) are masked
+// in shared memory afterwards, each thread its own column.  The end-indexed tile of the right-strand kernel is skewed
+// (row r starts at column g0 - 31 - r: not 16-byte aligned) and keeps the LDG -> STS path.
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void tma_bar_init(unsigned long long *bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void tma_bar_expect(unsigned long long *bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_bar_wait(unsigned long long *bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "TMA_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra TMA_DONE;\n"
+      "bra TMA_WAIT;\n"
+      "TMA_DONE:\n"
+      "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_copy_g2s(void *smem_dst, const void *gsrc, unsigned bytes, unsigned long long *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
 }
 
 // Warp-to-warp synchronisation of the tile kernels (acc_tile.h, "Synchronisation"): one progress counter per warp in
@@ -128,8 +161,6 @@ k_inside_tile(typename Core<real>::Ctx c, int TX, long long ntiles, real *scratc
   real *base = reinterpret_cast<real *>(smem_raw) + kTilePad;
   unsigned char *stab = smem_raw + ((size_t)kTilePad + (size_t)kTileRows * TC) * sizeof(real);  // 16-byte aligned
   uint8_t *sS = stab + Core<real>::kHotBytes;
-  for (int k = t; k < Core<real>::kHotBytes / 4; k += TC)
-    reinterpret_cast<uint32_t *>(stab)[k] = reinterpret_cast<const uint32_t *>(c.T)[k];
   const typename Core<real>::SmallTables &T = *reinterpret_cast<const typename Core<real>::SmallTables *>(stab);
   real *scrM1 = scratch + (size_t)blockIdx.x * 2 * (W + 4) * TC;
   real *scrM2 = scrM1 + (size_t)(W + 4) * TC;
@@ -137,6 +168,16 @@ k_inside_tile(typename Core<real>::Ctx c, int TX, long long ntiles, real *scratc
   const int dfirst = TL::first_group(W);
   int *prog = reinterpret_cast<int *>(smem_raw + tile_smem_bytes<real>() - kProgBytes);
   if (t < 32) prog[t] = 0;
+  {  // the hot Boltzmann tables (SmallTables up to hot_end) come in as ONE bulk asynchronous copy (TMA engine)
+    unsigned long long *tbar = reinterpret_cast<unsigned long long *>(prog + 32);
+    if (t == 0) {
+      tma_bar_init(tbar, 1);
+      tma_bar_expect(tbar, (unsigned)Core<real>::kHotBytes);
+      tma_copy_g2s(stab, c.T, (unsigned)Core<real>::kHotBytes, tbar);
+    }
+    __syncthreads();  // the barrier is initialised before anybody polls it
+    tma_bar_wait(tbar, 0);
+  }
   int ebase = 0;  // events completed by every warp before this tile
   __syncthreads();
   for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -198,8 +239,6 @@ k_outside_tile(typename Core<real>::Ctx c, int TX, long long ntiles, real *scrat
   real *pad = reinterpret_cast<real *>(smem_raw);
   real *base = pad + kTilePad;
   unsigned char *stab = smem_raw + ((size_t)kTilePad + (size_t)kTileRows * TC) * sizeof(real);
-  for (int k = t; k < Core<real>::kHotBytes / 4; k += TC)
-    reinterpret_cast<uint32_t *>(stab)[k] = reinterpret_cast<const uint32_t *>(c.T)[k];
   const typename Core<real>::SmallTables &T = *reinterpret_cast<const typename Core<real>::SmallTables *>(stab);
   uint8_t *sS = stab + Core<real>::kHotBytes;
   real *scrBif = scratch + (size_t)blockIdx.x * 2 * (W + 4) * TC;
@@ -207,6 +246,16 @@ k_outside_tile(typename Core<real>::Ctx c, int TX, long long ntiles, real *scrat
   const int dlast = TL::first_group(W);  // the groups of the inside pass, walked downwards
   int *prog = reinterpret_cast<int *>(smem_raw + tile_smem_bytes<real>() - kProgBytes);
   if (t < 32) prog[t] = 0;
+  {  // the hot Boltzmann tables (SmallTables up to hot_end) come in as ONE bulk asynchronous copy (TMA engine)
+    unsigned long long *tbar = reinterpret_cast<unsigned long long *>(prog + 32);
+    if (t == 0) {
+      tma_bar_init(tbar, 1);
+      tma_bar_expect(tbar, (unsigned)Core<real>::kHotBytes);
+      tma_copy_g2s(stab, c.T, (unsigned)Core<real>::kHotBytes, tbar);
+    }
+    __syncthreads();  // the barrier is initialised before anybody polls it
+    tma_bar_wait(tbar, 0);
+  }
   int ebase = 0;
   __syncthreads();
   for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -410,6 +459,29 @@ __device__ __forceinline__ void load_band_tile(const typename Core<real>::Ctx &c
   }
 }
 
+template <typename real>
+__device__ __forceinline__ void load_band_tile_tma(const typename Core<real>::Ctx &c, const typename BiTile<real>::Geo &ge,
+                                                   int arr, real *tile, int lim, const int *lim_halo,
+                                                   unsigned long long *bar, unsigned parity) {
+  const int tid = threadIdx.x, rows = ge.rows, cols = ge.cols;
+  if (rows <= 0) return;
+  if (tid == 0) {
+    // generic-proxy accesses of the tile (the previous pass) are ordered before the copy engine's writes
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    const unsigned row_bytes = (unsigned)(cols * sizeof(real));
+    tma_bar_expect(bar, (unsigned)rows * row_bytes);
+    const real *src = c.arr[arr] + 5 * c.NC + ge.g0;
+    for (int r = 0; r < rows; ++r) tma_copy_g2s(tile + (size_t)r * cols, src + (long long)r * c.NC, row_bytes, bar);
+  }
+  tma_bar_wait(bar, parity);
+  // mask: a cell of span r exists iff r <= limit of its column (own column, then the 32 halo columns)
+  for (int r = lim + 1 > 5 ? lim + 1 : 5; r < rows + 5; ++r) tile[(size_t)(r - 5) * cols + tid] = 0;
+  if (tid < 32) {
+    const int lh = lim_halo[tid];
+    for (int r = lh + 1 > 5 ? lh + 1 : 5; r < rows + 5; ++r) tile[(size_t)(r - 5) * cols + ge.TXb + tid] = 0;
+  }
+}
+
 template <typename real, bool LEFT, int ULO, int TXB>
 __global__ void __launch_bounds__(TXB > 0 ? TXB : 512, TXB == 256 ? 2 : TXB == 192 ? 3 : TXB == 128 ? 4 : 1) k_biloop_tile(typename Core<real>::Ctx c) {
   typedef BiTile<real> BT;
@@ -422,19 +494,24 @@ __global__ void __launch_bounds__(TXB > 0 ? TXB : 512, TXB == 256 ? 2 : TXB == 1
   real *tile = reinterpret_cast<real *>(smem_raw);
   uint8_t *list = reinterpret_cast<uint8_t *>(tile + (size_t)ge.rows * ge.cols);
   int *lim_halo = reinterpret_cast<int *>(list + (size_t)(c.W + 1) * ge.TXb);  // (W + 1) * TXb is a multiple of 4
+  unsigned long long *bar = reinterpret_cast<unsigned long long *>(
+      (reinterpret_cast<uintptr_t>(lim_halo + 32) + 7) & ~(uintptr_t)7);  // inside the 64 spare bytes of bi_bytes()
   constexpr int COLS = TXB > 0 ? TXB + 32 : 0;  // TXB > 0: block width (hence the tile row stride) known at compile time
   typename BT::Strand st;
   const int lim = BT::tile_col_limit(c, ge, LEFT, threadIdx.x);
   if (threadIdx.x < 32) lim_halo[threadIdx.x] = BT::tile_col_limit(c, ge, LEFT, ge.TXb + threadIdx.x);
+  if (LEFT && threadIdx.x == 0) tma_bar_init(bar, 1);
   __syncthreads();
   // generic loops out of the Alpha_stemI tile
-  load_band_tile<real, LEFT>(c, ge, A_STEMI, tile, lim, lim_halo);
+  if (LEFT) load_band_tile_tma<real>(c, ge, A_STEMI, tile, lim, lim_halo, bar, 0);
+  else load_band_tile<real, LEFT>(c, ge, A_STEMI, tile, lim, lim_halo);
   __syncthreads();
   if (LEFT) BT::template left<COLS, ULO>(c, ge, tile, list, threadIdx.x, st);
   else BT::template right<COLS, ULO>(c, ge, tile, list, threadIdx.x, st);
   __syncthreads();
   // bulges out of the Alpha_stemB tile (same buffer)
-  load_band_tile<real, LEFT>(c, ge, A_STEMB, tile, lim, lim_halo);
+  if (LEFT) load_band_tile_tma<real>(c, ge, A_STEMB, tile, lim, lim_halo, bar, 1);
+  else load_band_tile<real, LEFT>(c, ge, A_STEMB, tile, lim, lim_halo);
   __syncthreads();
   if (LEFT) BT::template left_bulge<COLS, ULO>(c, ge, tile, list, threadIdx.x, st);
   else BT::template right_bulge<COLS, ULO>(c, ge, tile, list, threadIdx.x, st);
