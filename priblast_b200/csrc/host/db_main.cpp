@@ -86,7 +86,9 @@ static void usage() {
       "defaults: -r 0 -s 8 -w 70 -d 5 -a heap -c INT_MAX   (reference: main.cpp:43-73)\n"
       "-m (extension; also PRIB_ACC_MODE): auto = FP32 span-scaled engine with FP64 re-run (default; .acc within\n"
       "   1e-4 kcal/mol of the reference), fp64, exact = the reference's own arithmetic on the GPU (.acc, hence\n"
-      "   the whole database and the ris output, byte-identical to the reference; ~50x slower than auto)\n"
+      "   the whole database and the ris output, byte-identical to a reference built WITHOUT FMA contraction,\n"
+      "   i.e. -ffp-contract=off or no -march; the upstream Makefile's -march=native build differs from that in\n"
+      "   the last bit of 65 %% of the values, max 4.8e-7 kcal/mol; ~50x slower than auto)\n"
       "environment: PRIB_NUM_GPUS=n limits the number of GPUs (default: every visible one, one worker process each)\n");
 }
 
