@@ -691,7 +691,14 @@ struct prib_ctx {
   char *d_tile_scratch = nullptr;
   char *d_state = nullptr;
   long long state_cap_bytes = 0;  // current size of d_state (grow-only)
-  long long state_budget = 0;     // upper bound fixed at create time (batches are sized for it)
+  long long state_budget = 0;     // upper bound of the current stage (batches are sized for it)
+  long long budget_default = 0, budget_long = 0;
+  void set_budget(long long budget) {
+    e64.max_cols = budget / state_bytes_per_column(W, 8) / 32 * 32;
+    e32.max_cols = budget / state_bytes_per_column(W, 4) / 32 * 32;
+    ex_max_cols = budget / exact_state_bytes_per_column(W) / 32 * 32;
+    state_budget = budget;  // the block itself is allocated by the first batch (ensure_state)
+  }
   // staged work
   std::vector<Batch> batches;
   std::vector<int32_t> seq_len;     // staged sequences, caller order
@@ -1224,11 +1231,14 @@ int prib_acc_create(prib_ctx **out, const prib_acc_params *params) {
   long long budget = params->max_batch_bytes > 0 ? params->max_batch_bytes
                                                  : std::min<long long>((long long)(free_b * 0.6), 32LL << 30);
   if (budget > (long long)(free_b * 0.9)) budget = (long long)(free_b * 0.9);
+  // Long sequences (mean > 8 kb, e.g. lncRNA sets) get the large budget when no explicit one was given: the two
+  // outer-array chains of a 100 kb sequence are a fixed ~16 ms per BATCH, so fewer, larger batches keep the scans
+  // below a tenth of the step (prib_acc_stage decides per call).
+  c->budget_long = params->max_batch_bytes > 0 ? budget : std::max<long long>(budget, (long long)(free_b * 0.6));
+  c->budget_default = budget;
   c->e64.max_cols = budget / state_bytes_per_column(c->W, 8) / 32 * 32;
-  c->e32.max_cols = budget / state_bytes_per_column(c->W, 4) / 32 * 32;
-  c->ex_max_cols = budget / exact_state_bytes_per_column(c->W) / 32 * 32;
   if (c->e64.max_cols < 4096) return bail(fail(PRIB_ECUDA, "device memory budget too small for the DP state"));
-  c->state_budget = budget;  // the block itself is allocated by the first batch (ensure_state)
+  c->set_budget(budget);
 #undef CUB
   *out = c;
   return PRIB_OK;
@@ -1272,6 +1282,11 @@ int prib_acc_stage(prib_ctx *c, int32_t n, const char *const *seq, const int32_t
   CU(cudaSetDevice(c->prm.device));
   c->staged = c->computed = false;
   c->n_batches = 0;
+  {
+    long long total_len = 0;
+    for (int k = 0; k < n; k++) total_len += len[k] > 0 ? len[k] : 0;
+    c->set_budget(n > 0 && total_len / n > 8192 ? c->budget_long : c->budget_default);
+  }
   const long long max_cols = c->ex ? c->ex_max_cols : c->use_fp32 ? c->e32.max_cols : c->e64.max_cols;
   for (int k = 0; k < n; k++) {
     if (len[k] < 0) return fail(PRIB_EINVAL, "negative sequence length");
