@@ -1,7 +1,8 @@
-"""TEST INFRASTRUCTURE.  Writes a patched copy of the reference's db_construction.cpp into the (git-ignored) build
-directory: the two functions INTEGRATION.md replaces are swapped for oracle/integration/*.inc, nothing else changes.
+"""TEST INFRASTRUCTURE.  Writes patched copies of the reference's db_construction.cpp and rna_interaction_search.cpp
+into the (git-ignored) build directory: the three functions INTEGRATION.md replaces are swapped for
+oracle/integration/*.inc, nothing else changes.
 
-  python apply_patch.py /root/reference/src/db_construction.cpp oracle/_ref/patched/db_construction.cpp
+  python apply_patch.py /root/reference/src oracle/_ref/patched
 """
 import os
 import sys
@@ -25,14 +26,17 @@ def replace_function(src: str, head: str, body: str) -> str:
 
 
 def main():
-    src = open(sys.argv[1]).read()
-    src = replace_function(src, "void DbConstruction::CalculateAccessibility(",
-                           open(os.path.join(HERE, "CalculateAccessibility.inc")).read())
-    src = replace_function(src, "void DbConstruction::ConstructSuffixArray(",
-                           open(os.path.join(HERE, "ConstructSuffixArray.inc")).read())
-    src = '#include "priblast_acc.h"\n#include <cstdlib>\n#include <fstream>\n' + src
-    os.makedirs(os.path.dirname(os.path.abspath(sys.argv[2])), exist_ok=True)
-    open(sys.argv[2], "w").write(src)
+    ref, out = sys.argv[1], sys.argv[2]
+    os.makedirs(out, exist_ok=True)
+    inc = lambda name: open(os.path.join(HERE, name)).read()
+    head = '#include "priblast_acc.h"\n#include <cstdlib>\n#include <fstream>\n#include <mutex>\n'
+    src = open(os.path.join(ref, "db_construction.cpp")).read()
+    src = replace_function(src, "void DbConstruction::CalculateAccessibility(", inc("CalculateAccessibility.inc"))
+    src = replace_function(src, "void DbConstruction::ConstructSuffixArray(", inc("ConstructSuffixArray.inc"))
+    open(os.path.join(out, "db_construction.cpp"), "w").write(head + src)
+    src = open(os.path.join(ref, "rna_interaction_search.cpp")).read()
+    src = replace_function(src, "void RnaInteractionSearch::CalculateAccessibility(", inc("RisCalculateAccessibility.inc"))
+    open(os.path.join(out, "rna_interaction_search.cpp"), "w").write(head + src)
 
 
 if __name__ == "__main__":

@@ -39,11 +39,11 @@ def built(tmp_path_factory):
                        stdout=subprocess.DEVNULL)
         return {x: open(str(d / f"{name}.{x}"), "rb").read() for x in EXTS}
 
-    return seqs, run
+    return seqs, run, str(d)
 
 
 def test_patched_reference_exact_mode_is_byte_identical(built):
-    seqs, run = built
+    seqs, run, dbdir = built
     ref = run(REFBIN, "ref")
     got = run(PATCHED, "pat_exact", mode="exact")
     for x in EXTS:
@@ -51,7 +51,7 @@ def test_patched_reference_exact_mode_is_byte_identical(built):
 
 
 def test_patched_reference_fast_mode_and_paging(built, tmp_path):
-    seqs, run = built
+    seqs, run, dbdir = built
     ref = run(REFBIN, "ref_c", extra=("-c", "16", "-w", "40", "-d", "6"))
     got = run(PATCHED, "pat_fast", extra=("-c", "16", "-w", "40", "-d", "6"))
     for x in ("bas", "nam", "seq", "ind"):  # the suffix arrays come from prib_suffix_array here
@@ -62,3 +62,42 @@ def test_patched_reference_fast_mode_and_paging(built, tmp_path):
     for (ra, rc), (ga, gc) in zip(_read_acc(pr, len(seqs)), _read_acc(pg, len(seqs))):
         assert_close_kcal(ga, ra, ATOL_VS_REF, RTOL_VS_REF, "acc")
         assert_close_kcal(gc, rc, ATOL_VS_REF, RTOL_VS_REF, "cond")
+
+
+def test_patched_ris_query_accessibility_on_the_gpu(built, tmp_path):
+    """`ris` of the patched binary computes the QUERY accessibility through prib_acc_run (n = 1,
+    oracle/integration/RisCalculateAccessibility.inc).  In exact mode its hit list equals the reference's in every
+    printed digit; in fast mode the structural hit list is the same and the energies agree within 2e-4."""
+    from test_gpu_db import _hits
+    seqs, run, dbdir = built
+    run(REFBIN, "refdb")
+    d = tmp_path
+    rng = np.random.default_rng(9)
+    comp = {"A": "U", "C": "G", "G": "C", "U": "A", "a": "u", "c": "g", "g": "c", "u": "a", "N": "A"}
+    queries = []
+    for k in range(6):
+        src = seqs[5 * k + 1].upper()
+        st = int(rng.integers(5, len(src) - 40))
+        site = "".join(comp.get(b, "A") for b in reversed(src[st:st + 28]))
+        pad = "".join("ACGU"[i] for i in rng.integers(0, 4, 150))
+        queries.append(pad[:75] + site + pad[75:])
+    qa = str(d / "q.fa")
+    _write(qa, queries, "q")
+    db = os.path.join(dbdir, "refdb")
+    env = dict(os.environ, OMP_NUM_THREADS="4")
+
+    def ris(binary, out, mode=None):
+        e = dict(env)
+        if mode:
+            e["PRIB_ACC_MODE"] = mode
+        subprocess.run([binary, "ris", "-i", qa, "-o", str(d / out), "-d", db], check=True, env=e, cwd=str(d),
+                       stdout=subprocess.DEVNULL)
+        text = sorted(ln.split(",", 1)[1] if ln[:1].isdigit() else ln for ln in open(str(d / out)).read().splitlines()
+                      if not ln.startswith("input:"))
+        return _hits(str(d / out)), text
+
+    (hr, tr), (he, te), (hf, tf) = ris(REFBIN, "ref.txt"), ris(PATCHED, "exact.txt", "exact"), ris(PATCHED, "fast.txt")
+    assert len(hr) > 0, "test set produced no hits"
+    assert tr == te, "exact mode: ris output differs from the reference's"
+    assert [h[:3] for h in hr] == [h[:3] for h in hf], "fast mode: structural hit list differs"
+    assert max(max(abs(a[3] - b[3]), abs(a[4] - b[4]), abs(a[5] - b[5])) for a, b in zip(hr, hf)) <= 2e-4
