@@ -81,6 +81,10 @@ static __constant__ float2 g_cgpair_f[64];
 // (conv[u][sum - u], conv[u + 1][sum - u - 1]) at [u * 32 + sum]: the coefficient pairs of the packed strand-weight
 // pass (two strand lengths per FFMA2; a 64-bit constant operand instead of two LDC + a MOV per pair)
 static __constant__ float2 g_convpair_f[32 * 32];
+// scalar factors of the shallow steps (k2, inv_cA, e_mlbase, e_mlintern, e_mlclose): constant-bank operands of the
+// FMAs instead of shared-memory loads
+static __constant__ double g_scal_d[8];
+static __constant__ float g_scal_f[8];
 // cg[0..6] for the centre-line chain of the tile kernels (acc_tile.h)
 static __constant__ double g_cg_d[8];
 static __constant__ float g_cg_f[8];
@@ -90,12 +94,14 @@ template <> struct ConstTab<double> {
   static __device__ __forceinline__ const double *bulge() { return g_bulge_d; }
   static __device__ __forceinline__ const double *cf() { return g_cf_d; }
   static __device__ __forceinline__ const double *cg() { return g_cg_d; }
+  static __device__ __forceinline__ const double *scal() { return g_scal_d; }
 };
 template <> struct ConstTab<float> {
   static __device__ __forceinline__ const float *conv() { return g_conv_f; }
   static __device__ __forceinline__ const float *bulge() { return g_bulge_f; }
   static __device__ __forceinline__ const float *cf() { return g_cf_f; }
   static __device__ __forceinline__ const float *cg() { return g_cg_f; }
+  static __device__ __forceinline__ const float *scal() { return g_scal_f; }
 };
 #endif
 
@@ -125,7 +131,8 @@ struct SmallTables {
   real inv_cA;                   // 1 / cA
   int8_t bp[5][5];
   int8_t rt[8];
-  int8_t hot_end[7];             // marks the end of the hot prefix
+  int8_t bpr[5][5];              // rt[bp[a][b]]: the reversed pair type in ONE look-up (the shallow steps chain bp -> rt -> table)
+  int8_t hot_end[6];             // marks the end of the hot prefix
   // ---- cold part ----
   real e_bulge[32];              // [u] (device copy in __constant__)
   real conv[32][32];             // generic interior loop: cf[u1+u2] * cg[min(|u1-u2|, 6)], else 0
@@ -180,6 +187,16 @@ static PRIB_HD const real *cf_tab(const SmallTables &T) {
   return ConstTab<real>::cf();
 #else
   return T.cf;
+#endif
+}
+// scalar factors: I = 0 k2, 1 inv_cA, 2 e_mlbase, 3 e_mlintern, 4 e_mlclose
+enum { kScK2 = 0, kScInvCA, kScMlBase, kScMlIntern, kScMlClose };
+template <int I>
+static PRIB_HD real scal(const SmallTables &T) {
+#if defined(__CUDA_ARCH__)
+  return ConstTab<real>::scal()[I];
+#else
+  return I == kScK2 ? T.k2 : I == kScInvCA ? T.inv_cA : I == kScMlBase ? T.e_mlbase : I == kScMlIntern ? T.e_mlintern : T.e_mlclose;
 #endif
 }
 static PRIB_HD const real *cg_tab(const SmallTables &T) {

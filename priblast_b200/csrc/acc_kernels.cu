@@ -1058,11 +1058,19 @@ int setup_engine(prib_ctx *c, const ScaleSpec &spec, size_t smem_max, std::strin
     CU(cudaMemcpyToSymbol(g_bulge_d, tab.small.e_bulge, sizeof(real) * 32));
     CU(cudaMemcpyToSymbol(g_cf_d, tab.small.cf, sizeof(real) * 32));
     CU(cudaMemcpyToSymbol(g_cg_d, tab.small.cg, sizeof(real) * 8));
+    {
+      const real sc[8] = {tab.small.k2, tab.small.inv_cA, tab.small.e_mlbase, tab.small.e_mlintern, tab.small.e_mlclose, 0, 0, 0};
+      CU(cudaMemcpyToSymbol(g_scal_d, sc, sizeof(sc)));
+    }
   } else {
     CU(cudaMemcpyToSymbol(g_conv_f, &tab.small.conv[0][0], sizeof(real) * 32 * 32));
     CU(cudaMemcpyToSymbol(g_bulge_f, tab.small.e_bulge, sizeof(real) * 32));
     CU(cudaMemcpyToSymbol(g_cf_f, tab.small.cf, sizeof(real) * 32));
     CU(cudaMemcpyToSymbol(g_cg_f, tab.small.cg, sizeof(real) * 8));
+    {
+      const real sc[8] = {tab.small.k2, tab.small.inv_cA, tab.small.e_mlbase, tab.small.e_mlintern, tab.small.e_mlclose, 0, 0, 0};
+      CU(cudaMemcpyToSymbol(g_scal_f, sc, sizeof(sc)));
+    }
     float2 pairs[64];
     for (int a = 0; a < 8; a++)
       for (int b = 0; b < 8; b++)

@@ -84,6 +84,8 @@ bool build_tables(int W, int delta, const ScaleSpec &spec, HostTablesT<real> &ou
     for (int b = 0; b < 5; b++) T.bp[a][b] = (int8_t)p->bp_pair[a][b];
   for (int t = 0; t < 7; t++) T.rt[t] = (int8_t)p->rtype[t];
   T.rt[7] = 0;
+  for (int a = 0; a < 5; a++)
+    for (int b = 0; b < 5; b++) T.bpr[a][b] = T.rt[T.bp[a][b]];
 
   out.e_int11.resize(8 * 8 * 5 * 5);
   out.e_int21.resize(8 * 8 * 5 * 5 * 5);

@@ -475,24 +475,24 @@ struct Tile {
       if (te) {
 #endif
         const int sd1 = s[d - 1], sd2 = s[d - 2], s2 = s[2], s3 = s[3];
-        if (smax >= 2) p11 = c.e_int11[idx11(te, T.rt[T.bp[s2][sd1]], si1, sj)];
+        if (smax >= 2) p11 = c.e_int11[idx11(te, T.bpr[s2][sd1], si1, sj)];
         if (smax >= 3) {
-          p21a = c.e_int21[idx21(te, T.rt[T.bp[s2][sd2]], si1, sd1, sj)];
-          p21b = c.e_int21[idx21(T.rt[T.bp[s3][sd1]], te, sj, si1, s2)];
+          p21a = c.e_int21[idx21(te, T.bpr[s2][sd2], si1, sd1, sj)];
+          p21b = c.e_int21[idx21(T.bpr[s3][sd1], te, sj, si1, s2)];
         }
-        if (smax >= 4) p22 = c.e_int22[idx22(te, T.rt[T.bp[s3][sd2]], si1, s2, sd1, sj)];
+        if (smax >= 4) p22 = c.e_int22[idx22(te, T.bpr[s3][sd2], si1, s2, sd1, sj)];
       }
       const int tp = T.bp[si1][sj];
       if (tp) {
-        const int t2 = T.bp[s[2]][s[d - 1]];
-        stem = T.k2 * (sm.se[((d - 2) & (kRingSE - 1)) * TC + t + 1] +
-                       sm.stem[((d - 2) & (kRingStem - 1)) * TC + t + 1] * T.e_stack[tp][T.rt[t2]]);
+        const int t2r = T.bpr[s[2]][s[d - 1]];
+        stem = K::template scal<K::kScK2>(T) * (sm.se[((d - 2) & (kRingSE - 1)) * TC + t + 1] +
+                       sm.stem[((d - 2) & (kRingStem - 1)) * TC + t + 1] * T.e_stack[tp][t2r]);
       }
-      mb *= T.inv_cA;
+      mb *= K::template scal<K::kScInvCA>(T);
       stemD = tp ? stem * K::e_dangle(T, tp, i > 0, si, j < L, sj1) : 0;
-      m2 = stemD * T.e_mlintern + sm.m2[((d - 1) & (kRingMu - 1)) * TC + t] * T.e_mlbase;
+      m2 = stemD * K::template scal<K::kScMlIntern>(T) + sm.m2[((d - 1) & (kRingMu - 1)) * TC + t] * K::template scal<K::kScMlBase>(T);
       m1 = m2 + mb;
-      mu = sm.mu[((d - 1) & (kRingMu - 1)) * TC + t + 1] * T.e_mlbase + mb;
+      mu = sm.mu[((d - 1) & (kRingMu - 1)) * TC + t + 1] * K::template scal<K::kScMlBase>(T) + mb;
       if (tp) {
         stemI = stem * T.e_mmI[T.rt[tp]][sj1][si];
         stemB = stem * T.tau[tp];
@@ -504,8 +504,8 @@ struct Tile {
         const real *st3 = sm.stem + ((d - 3) & (kRingStem - 1)) * TC + t;
         const real *st4 = sm.stem + ((d - 4) & (kRingStem - 1)) * TC + t;
         if (smax >= 1) {
-          a += bu[1] * (st1[1] * T.e_stack[te][T.rt[T.bp[s[2]][sj]]] +
-                        st1[0] * T.e_stack[te][T.rt[T.bp[si1][s[d - 1]]]]);
+          a += bu[1] * (st1[1] * T.e_stack[te][T.bpr[s[2]][sj]] +
+                        st1[0] * T.e_stack[te][T.bpr[si1][s[d - 1]]]);
         }
         if (smax >= 2) {
           a += st2[1] * p11;
@@ -528,7 +528,7 @@ struct Tile {
           a += T.e_mmI[te][si1][sj] * gs;
         }
         const int tt = T.rt[te];
-        a += mu * T.e_mlclose * T.e_d3[tt][si1] * T.e_d5[tt][sj];
+        a += mu * K::template scal<K::kScMlClose>(T) * T.e_d3[tt][si1] * T.e_d5[tt][sj];
         se = a;
       }
     }
@@ -901,7 +901,7 @@ struct Tile {
         la = c.lao[g];
         lb = c.lbo[g + d];
         lz = c.lao[cs.zcol];
-        const int t2r_ = T.rt[t2_];
+        const int t2r_ = T.bpr[sp1][sq_];
         const int sm1 = s[-1], sm2 = s[-2], sd2 = s[d + 2], sd3 = s[d + 3];
         if (smax >= 2) p11 = c.e_int11[idx11(T.bp[sm1][sd2], t2r_, sp, sq1)];
         if (smax >= 3) {
@@ -914,15 +914,15 @@ struct Tile {
       const real bse = (inner && d + 2 <= W + 1) ? b2[-1] : 0;  // Beta_stemend(p,q), :277-279
       if (inner) {
         const int tt = T.rt[te];
-        bmulti = (d + 1 <= W + 1 ? sm.mu[((d + 1) & (kRingMu - 1)) * TC + t - 1] * T.e_mlbase : (real)0) +
-                 T.k2 * bse * T.e_mlclose * T.e_d3[tt][sp1] * T.e_d5[tt][sq_];
-        bm1 *= T.inv_cA;
-        bmulti2 = bm1 + sm.m2[((d + 1) & (kRingMu - 1)) * TC + t] * T.e_mlbase + ks * T.inv_cA;
+        bmulti = (d + 1 <= W + 1 ? sm.mu[((d + 1) & (kRingMu - 1)) * TC + t - 1] * K::template scal<K::kScMlBase>(T) : (real)0) +
+                 K::template scal<K::kScK2>(T) * bse * K::template scal<K::kScMlClose>(T) * T.e_d3[tt][sp1] * T.e_d5[tt][sq_];
+        bm1 *= K::template scal<K::kScInvCA>(T);
+        bmulti2 = bm1 + sm.m2[((d + 1) & (kRingMu - 1)) * TC + t] * K::template scal<K::kScMlBase>(T) + ks * K::template scal<K::kScInvCA>(T);
         bmbif = bm1 + bmulti;
       }
       const int t2 = T.bp[sp1][sq_];
       if (t2) {
-        const int t2r = T.rt[t2];
+        const int t2r = T.bpr[sp1][sq_];
         const real dang = K::e_dangle(T, t2, p > 0, sp, q < L, sq1);
         real l = 0;
         if (smax >= 0) l += bse * T.e_stack[te][t2r];
@@ -948,7 +948,7 @@ struct Tile {
           l += T.e_mmI[t2r][sq1][sp] * gs;
         }
         const real base = (real)exp(la + lb - lz) * dang * T.sB[d];  // raccess.cpp:370, divided by Z
-        bstem = base + T.k2 * l + bmulti2 * T.e_mlintern * dang;
+        bstem = base + K::template scal<K::kScK2>(T) * l + bmulti2 * K::template scal<K::kScMlIntern>(T) * dang;
         bstemO = bstem * T.e_mmI[t2][s[2]][s[d - 1]];
         bstemB = bstem * T.tau[t2];
       }
