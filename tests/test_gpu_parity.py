@@ -201,3 +201,23 @@ def test_span_and_window_sweep_vs_oracle(oracle_lib, W, delta):
     for s, (a, c), (oa, oc) in zip(seqs, got, want):
         assert_close_kcal(a, oa, ATOL_VS_REF, RTOL_VS_REF, f"W={W} d={delta} L={len(s)} acc")
         assert_close_kcal(c, oc, ATOL_VS_REF, RTOL_VS_REF, f"W={W} d={delta} L={len(s)} cond")
+
+
+def test_repeated_runs_are_bit_identical():
+    """The tile kernels synchronise warp to warp through progress counters (acc_tile.h, "Synchronisation"): a missed
+    dependency would show up as run-to-run differences.  Twelve passes over the same 768 transcripts, two tile-kernel
+    engines (FP32 and FP64), every output bit compared."""
+    from priblast_b200 import Raccess
+    seqs = _cfg2_sample(768)
+    for mode in (0, 1):
+        with Raccess(70, 5, mode=mode, max_batch_bytes=(24 if mode == 0 else 40) << 30) as r:
+            r.stage(seqs if mode == 0 else seqs[:256])
+            ref = None
+            for it in range(12 if mode == 0 else 4):
+                r.compute()
+                out = r.fetch()
+                flat = np.concatenate([np.concatenate([a, c]) for a, c in out]).view(np.uint32).copy()
+                if ref is None:
+                    ref = flat
+                else:
+                    assert np.array_equal(ref, flat), f"mode {mode}: pass {it} differs from pass 0 in {(ref != flat).sum()} values"
