@@ -26,6 +26,7 @@
 // identical to acc_core.h's one-cell-at-a-time functions, so both give the same bits in the same
 // precision (checked by tests/test_hostemu.py).
 #pragma once
+#include <string.h>
 #include "acc_core.h"
 
 // 1 = the FP32 tile kernels evaluate the generic interior-loop sums by the centre-line chain (below); needs 8 more
@@ -137,6 +138,32 @@ struct Tile {
     if (!(sum >= 4 && sum <= kMaxLoop && u1 <= sum - 1 && !(sum == 4 && u1 == 2))) return 7;
     const int k = 2 * u1 - sum, a = k < 0 ? -k : k;
     return a > 6 ? 6 : a;
+  }
+  // One product of the generic-loop stencils.  The host emulation (tests/hostemu) can switch it to the arithmetic of a
+  // tensor-core formulation -- both operands split into TF32 halves, x_hi w_hi + x_lo w_hi + x_hi w_lo, FP32 sums
+  // (profiles/tc_probe.cu measures that formulation's rate) -- to see what it would do to the parity statement.
+#if !defined(__CUDA_ARCH__)
+  static int &emu_tf32() {
+    static int on = 0;
+    return on;
+  }
+  static float tf32_trunc(float v) {
+    uint32_t b;
+    memcpy(&b, &v, 4);
+    b &= 0xFFFFE000u;
+    memcpy(&v, &b, 4);
+    return v;
+  }
+#endif
+  static PRIB_HD real stencil_mul(real w, real v) {
+#if !defined(__CUDA_ARCH__)
+    if (sizeof(real) == 4 && emu_tf32()) {
+      const float wh = tf32_trunc((float)w), wl = tf32_trunc((float)w - wh);
+      const float vh = tf32_trunc((float)v), vl = tf32_trunc((float)v - vh);
+      return (real)((wh * vh + wl * vh) + wh * vl);
+    }
+#endif
+    return w * v;
   }
   static PRIB_HD real gsel(int k, real g0, real g1, real g2, real g3, real g4, real g5, real g6) {
     return k == 0 ? g0 : k == 1 ? g1 : k == 2 ? g2 : k == 3 ? g3 : k == 4 ? g4 : k == 5 ? g5 : g6;
@@ -285,7 +312,7 @@ struct Tile {
           for (int k = 0; k < kTT; ++k) {
             const int sum = S + k;
             if (sum >= 4 && sum <= kMaxLoop && x <= sum - 1 && !(sum == 4 && x == 2))
-              rs[k] += gsel(K::gidx(x, sum), g0, g1, g2, g3, g4, g5, g6) * v;
+              rs[k] += stencil_mul(gsel(K::gidx(x, sum), g0, g1, g2, g3, g4, g5, g6), v);
           }
         }
       }
@@ -651,7 +678,7 @@ struct Tile {
           for (int k = 0; k < kTT; ++k) {
             const int sum = S + k - 2;
             if (sum >= 4 && sum <= kMaxLoop && y <= sum - 1 && !(sum == 4 && y == 2))
-              rs[k] += gsel(K::gidx(y, sum), g0, g1, g2, g3, g4, g5, g6) * v;
+              rs[k] += stencil_mul(gsel(K::gidx(y, sum), g0, g1, g2, g3, g4, g5, g6), v);
           }
         }
       }
@@ -1184,29 +1211,37 @@ struct BiTile {
 #pragma unroll
     for (int u = 0; u <= kMaxLoop; ++u) ml[u] = 0;
     int cnt = 0;
-    if (i >= 1) {
-      const int dpmax = imin(W - 1, L - 1 - i);
-      // pass A (all lanes at the same span): list the closing spans, add bulges (u2 = 0) and, for
-      // delta == 2, the 2x1 / 2x2 special loops
-      for (int dp0 = delta + 5; dp0 <= dpmax; dp0 += 8) {
-        real bv[8];  // 8 independent loads in flight (the list update is a serial chain on the loaded values)
+    // pass A (all lanes at the same span, widest first): the suffix sums over span of the hairpin-loop weights
+    // (X_SUFH, restructured raccess.cpp:546-561 -- same Beta_stem loads as the list), the list of the closing spans
+    // and, for delta == 2, the 2x1 / 2x2 special loops
+    const int dpmax = i >= 1 ? imin(W - 1, L - 1 - i) : -1;
+    real suf = 0;
+    for (int dd0 = W; dd0 >= 4; dd0 -= 8) {
+      real bv[8];  // 8 independent loads in flight (the list update is a serial chain on the loaded values)
 #pragma unroll
-        for (int k = 0; k < 8; ++k) bv[k] = (dp0 + k <= dpmax) ? c.ld(B_STEM, dp0 + k + 2, g - 1) : (real)0;
+      for (int k = 0; k < 8; ++k) bv[k] = (dd0 - k >= 4 && dd0 - k - 1 <= dpmax) ? c.ld(B_STEM, dd0 - k + 1, g - 1) : (real)0;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const int dp = dp0 + k;
-          const real bse = bv[k];
-          if (bse == 0) continue;
-          list[cnt * TXb + t] = (uint8_t)dp;
-          ++cnt;
-          if (delta == 2) {
-            const int te = T.bp[s[0]][s[dp + 1]];
-            const real bseO = c.ld(B_STEMO, dp + 2, g - 1), bseB = c.ld(B_STEMB, dp + 2, g - 1);
-            if (dp - 5 >= 3) ml[2] += K::loop_weight(c, T, s, g, dp, te, bse, bseO, bseB, 2, 1);
-            if (dp - 5 >= 4) ml[2] += K::loop_weight(c, T, s, g, dp, te, bse, bseO, bseB, 2, 2);
+      for (int k = 0; k < 8; ++k) {
+        const int dd = dd0 - k, dp = dd - 1;
+        if (dd < 4) break;
+        const real bse = bv[k];
+        if (bse != 0) {
+          const int te = T.bp[s[0]][s[dd]];
+          suf += bse * T.hpB[dd] * (dd - 1 != 3 ? T.e_mmH[te][s[1]][s[dd - 1]] : T.tau[te]);
+          if (dp >= delta + 5) {
+            list[cnt * TXb + t] = (uint8_t)dp;
+            ++cnt;
+            if (delta == 2) {
+              const real bseO = c.ld(B_STEMO, dp + 2, g - 1), bseB = c.ld(B_STEMB, dp + 2, g - 1);
+              if (dp - 5 >= 3) ml[2] += K::loop_weight(c, T, s, g, dp, te, bse, bseO, bseB, 2, 1);
+              if (dp - 5 >= 4) ml[2] += K::loop_weight(c, T, s, g, dp, te, bse, bseO, bseB, 2, 2);
+            }
           }
         }
+        c.at(X_SUFH, dd, g) = suf;
       }
+    }
+    if (i >= 1) {
       // pass B: generic interior loops out of the shared-memory tile, dense over groups of kTT outer spans
       // (the outer-pair weights of the next group are loaded while this group is being evaluated)
       real wn[kTT];

@@ -220,8 +220,8 @@ void run_acc(EmuT<real> &e, int TXb = 0) {
     if (TXb == 0) {
       K::biloop_left(c, g);
       K::biloop_right(c, g);
+      K::hairpin_suffix(c, g);  // the tiled left strand-weight body produces X_SUFH itself
     }
-    K::hairpin_suffix(c, g);
   }
   for (long long g = 0; g < c.NC; g++) K::finalize_position(c, g);
 }
@@ -276,6 +276,8 @@ extern "C" {
 void hostemu_set_poison(int on) { g_poison = on; }
 // chain = 1: deep steps in the centre-line chain formulation (what the FP32 device engine runs)
 void hostemu_set_chain(int on) { g_chain = on; }
+// tf32 = 1: the FP32 engine's generic-loop stencil products in the 3-product TF32 split of a tensor-core formulation
+void hostemu_set_tf32_split(int on) { Tile<float>::emu_tf32() = on; }
 
 // FP32 band arithmetic with span scaling; flags_out[k] != 0 marks sequences whose stored values left
 // the safe range (the product re-runs those in FP64).

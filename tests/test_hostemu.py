@@ -170,3 +170,19 @@ def test_centre_line_chain_fp32_and_poison(emu, chain_mode):
         if not flags[k]:
             assert np.abs(ref[seg] - got[seg]).max() < 6e-6, k
     assert flags[len(_MIX) - 1] == 1 and flags[0] == 0 and flags[1] == 0
+
+
+def test_tf32_split_stencil_keeps_parity(emu):
+    """The generic-loop stencil products in the 3-product TF32 split of a tensor-core formulation
+    (profiles/tc_probe.cu, profiles/tc_parity.py): the FP32 engine stays inside the reference gate."""
+    emu.lib.hostemu_set_tf32_split(1)
+    try:
+        for name in ("rand_L500_W70_d5", "rand_L300_W70_d2"):
+            case = next(c for c in GOLDEN if c["name"] == name)
+            out, flags, lens = _tiled(emu.lib, [case["seq"]], case["W"], case["delta"], 256, (0.45, 4.0, 16.0), f32=True)
+            L = int(lens[0])
+            assert flags[0] == 0
+            assert_close_kcal(out[:L], case["acc"], ATOL_VS_REF, RTOL_VS_REF, "acc")
+            assert_close_kcal(out[L:2 * L], case["cond"], ATOL_VS_REF, RTOL_VS_REF, "cond")
+    finally:
+        emu.lib.hostemu_set_tf32_split(0)
