@@ -5,7 +5,7 @@
 //                                    tile, stencil source rows in shared-memory rings, halo recomputed,
 //                                    one deep step (kTT spans' long-range sums) per kTT shallow steps
 //   k_outer_scans_warp               the two outer arrays, one warp per sequence
-//   k_biloop_left/right, k_hairpin_suffix, k_finalize   accessibility, one thread per column
+//   k_biloop_tile<LEFT/RIGHT> (the left one also forms the hairpin suffix sums), k_finalize   accessibility
 // Every kernel exists for float and double band arithmetic.  The float engine (span-scaled, range
 // guarded) is the fast path (spans up to kFp32MaxSpan); sequences whose stored values leave the safe range
 // are flagged on the device and re-run by the double engine inside the same prib_acc_compute call, on
@@ -427,42 +427,14 @@ __global__ void __launch_bounds__(32 * kScanWarps) k_outer_scans_warp(typename C
   else warp_scan<real, false>(c, sq, rings[warp], wbuf, usm, lane);
 }
 
-// Cooperative load of one band-array tile (rows = spans 5..W-1) into shared memory: thread = tile column,
-// rows in batches of 8 so that 8 independent loads are in flight per thread; the 32 halo columns are
-// spread over all threads.  lim: this thread's column limit, lim_halo[32]: limits of the halo columns.
+// One band-array tile (rows = spans 5..W-1) into shared memory through the bulk-copy engine: one row = one copy,
+// issued by one thread, completion on a transaction barrier; cells that do not exist are zeroed afterwards.
+// lim: this thread's column limit, lim_halo[32]: limits of the halo columns.
 template <typename real, bool LEFT>
-__device__ __forceinline__ void load_band_tile(const typename Core<real>::Ctx &c, const typename BiTile<real>::Geo &ge,
-                                               int arr, real *tile, int lim, const int *lim_halo) {
-  typedef BiTile<real> BT;
-  const int tid = threadIdx.x, rows = ge.rows, cols = ge.cols;
-  for (int r0 = 0; r0 < rows; r0 += 8) {
-    real v[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) v[k] = (r0 + k < rows) ? BT::tile_elem(c, ge, LEFT, arr, r0 + k + 5, tid, lim) : (real)0;
-#pragma unroll
-    for (int k = 0; k < 8; ++k)
-      if (r0 + k < rows) tile[(r0 + k) * cols + tid] = v[k];
-  }
-  const int nh = rows * 32;
-  for (int e0 = tid; e0 < nh; e0 += 4 * ge.TXb) {
-    real v[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int e = e0 + k * ge.TXb;
-      v[k] = e < nh ? BT::tile_elem(c, ge, LEFT, arr, (e >> 5) + 5, ge.TXb + (e & 31), lim_halo[e & 31]) : (real)0;
-    }
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int e = e0 + k * ge.TXb;
-      if (e < nh) tile[(e >> 5) * cols + ge.TXb + (e & 31)] = v[k];
-    }
-  }
-}
-
-template <typename real>
 __device__ __forceinline__ void load_band_tile_tma(const typename Core<real>::Ctx &c, const typename BiTile<real>::Geo &ge,
                                                    int arr, real *tile, int lim, const int *lim_halo,
                                                    unsigned long long *bar, unsigned parity) {
+  typedef BiTile<real> BT;
   const int tid = threadIdx.x, rows = ge.rows, cols = ge.cols;
   if (rows <= 0) return;
   if (tid == 0) {
@@ -470,15 +442,20 @@ __device__ __forceinline__ void load_band_tile_tma(const typename Core<real>::Ct
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     const unsigned row_bytes = (unsigned)(cols * sizeof(real));
     tma_bar_expect(bar, (unsigned)rows * row_bytes);
+    // left: row r starts at column g0.  right (end-indexed): at column g0 - 31 - r, fetched from the aligned address
+    // below it (BiTile::row_off); for the first CTAs that is a few elements before the row, inside the array (r >= 5)
     const real *src = c.arr[arr] + 5 * c.NC + ge.g0;
-    for (int r = 0; r < rows; ++r) tma_copy_g2s(tile + (size_t)r * cols, src + (long long)r * c.NC, row_bytes, bar);
+    for (int r = 0; r < rows; ++r)
+      tma_copy_g2s(tile + (size_t)r * cols, src + (long long)r * c.NC - (LEFT ? 0 : 31 + r + 5 + BT::row_off(ge, false, r + 5)),
+                   row_bytes, bar);
   }
   tma_bar_wait(bar, parity);
   // mask: a cell of span r exists iff r <= limit of its column (own column, then the 32 halo columns)
-  for (int r = lim + 1 > 5 ? lim + 1 : 5; r < rows + 5; ++r) tile[(size_t)(r - 5) * cols + tid] = 0;
+  for (int r = lim + 1 > 5 ? lim + 1 : 5; r < rows + 5; ++r) tile[(size_t)(r - 5) * cols + tid + BT::row_off(ge, LEFT, r)] = 0;
   if (tid < 32) {
     const int lh = lim_halo[tid];
-    for (int r = lh + 1 > 5 ? lh + 1 : 5; r < rows + 5; ++r) tile[(size_t)(r - 5) * cols + ge.TXb + tid] = 0;
+    for (int r = lh + 1 > 5 ? lh + 1 : 5; r < rows + 5; ++r)
+      tile[(size_t)(r - 5) * cols + ge.TXb + tid + BT::row_off(ge, LEFT, r)] = 0;
   }
 }
 
@@ -489,29 +466,27 @@ __global__ void __launch_bounds__(TXB > 0 ? TXB : 512, TXB == 256 ? 2 : TXB == 1
   typename BT::Geo ge;
   ge.TXb = blockDim.x;
   ge.g0 = (long long)blockIdx.x * ge.TXb;
-  ge.cols = ge.TXb + 32;
+  ge.cols = BT::tile_cols(LEFT, ge.TXb);
   ge.rows = c.W - 5 > 0 ? c.W - 5 : 0;
   real *tile = reinterpret_cast<real *>(smem_raw);
   uint8_t *list = reinterpret_cast<uint8_t *>(tile + (size_t)ge.rows * ge.cols);
   int *lim_halo = reinterpret_cast<int *>(list + (size_t)(c.W + 1) * ge.TXb);  // (W + 1) * TXb is a multiple of 4
   unsigned long long *bar = reinterpret_cast<unsigned long long *>(
       (reinterpret_cast<uintptr_t>(lim_halo + 32) + 7) & ~(uintptr_t)7);  // inside the 64 spare bytes of bi_bytes()
-  constexpr int COLS = TXB > 0 ? TXB + 32 : 0;  // TXB > 0: block width (hence the tile row stride) known at compile time
+  constexpr int COLS = TXB > 0 ? TXB + 32 + (LEFT ? 0 : BT::kAl) : 0;  // TXB > 0: the tile row stride is known at compile time
   typename BT::Strand st;
   const int lim = BT::tile_col_limit(c, ge, LEFT, threadIdx.x);
   if (threadIdx.x < 32) lim_halo[threadIdx.x] = BT::tile_col_limit(c, ge, LEFT, ge.TXb + threadIdx.x);
-  if (LEFT && threadIdx.x == 0) tma_bar_init(bar, 1);
+  if (threadIdx.x == 0) tma_bar_init(bar, 1);
   __syncthreads();
   // generic loops out of the Alpha_stemI tile
-  if (LEFT) load_band_tile_tma<real>(c, ge, A_STEMI, tile, lim, lim_halo, bar, 0);
-  else load_band_tile<real, LEFT>(c, ge, A_STEMI, tile, lim, lim_halo);
+  load_band_tile_tma<real, LEFT>(c, ge, A_STEMI, tile, lim, lim_halo, bar, 0);
   __syncthreads();
   if (LEFT) BT::template left<COLS, ULO>(c, ge, tile, list, threadIdx.x, st);
   else BT::template right<COLS, ULO>(c, ge, tile, list, threadIdx.x, st);
   __syncthreads();
   // bulges out of the Alpha_stemB tile (same buffer)
-  if (LEFT) load_band_tile_tma<real>(c, ge, A_STEMB, tile, lim, lim_halo, bar, 1);
-  else load_band_tile<real, LEFT>(c, ge, A_STEMB, tile, lim, lim_halo);
+  load_band_tile_tma<real, LEFT>(c, ge, A_STEMB, tile, lim, lim_halo, bar, 1);
   __syncthreads();
   if (LEFT) BT::template left_bulge<COLS, ULO>(c, ge, tile, list, threadIdx.x, st);
   else BT::template right_bulge<COLS, ULO>(c, ge, tile, list, threadIdx.x, st);
@@ -533,11 +508,6 @@ void launch_biloop(const typename Core<real>::Ctx &k, unsigned grid, int TXb, si
 #undef PRIB_BI_LAUNCH
 }
 
-template <typename real>
-__global__ void __launch_bounds__(kThreads) k_hairpin_suffix(typename Core<real>::Ctx c) {
-  const long long g = (long long)blockIdx.x * kThreads + threadIdx.x;
-  if (g < c.NC) Core<real>::hairpin_suffix(c, g);
-}
 template <typename real>
 __global__ void __launch_bounds__(kThreads, 8) k_finalize(typename Core<real>::Ctx c) {
   const long long g = (long long)blockIdx.x * kThreads + threadIdx.x;
@@ -1108,7 +1078,7 @@ int setup_engine(prib_ctx *c, const ScaleSpec &spec, size_t smem_max, std::strin
   int TXb = 256;  // two CTAs per SM: one loads its tile while the other computes (measured: 256 beats 512)
   if (const char *te = getenv("PRIB_TXB")) TXb = std::max(32, std::min(512, atoi(te) / 32 * 32));  // tuning knob
   auto bi_bytes = [&](int txb) {
-    return (size_t)rows * (txb + 32) * sizeof(real) + (size_t)(c->W + 1) * txb + 32 * sizeof(int) + 64;
+    return (size_t)rows * (txb + 32 + 4) * sizeof(real) + (size_t)(c->W + 1) * txb + 32 * sizeof(int) + 64;  // + 4: right tile's alignment slack
   };
   while (TXb > 32 && bi_bytes(TXb) > smem_max) TXb -= 32;
   e.TXb = TXb;

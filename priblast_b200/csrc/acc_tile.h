@@ -1033,7 +1033,7 @@ struct BiTile {
   struct Geo {
     long long g0;  // first owned column
     int TXb;       // owned columns = threads
-    int cols;      // TXb + 32 (row stride of the tile; multiple of 32)
+    int cols;      // tile_cols(): row stride of the tile
     int rows;      // W - 5: spans 5 .. W-1
   };
 
@@ -1043,6 +1043,17 @@ struct BiTile {
   // exist must read as 0 rather than as whatever an earlier batch left in the DP state.  A cell exists iff
   // its span is <= the limit of its tile column: L - i of the start column (left), left index of the end
   // column (right); -1 for padding columns and columns outside the batch.
+  //
+  // Row r of the right kernel's tile is the contiguous run of start columns g0 - 31 - r .. of the band array, i.e. it
+  // begins one element further left per span.  So that the bulk-copy engine can fetch it (16-byte aligned source,
+  // destination and size) the row is copied from the aligned address below its first element: its element x then
+  // sits row_off(r) = (g0 - 31 - r) mod kAl elements into the shared-memory row, and the row stride has kAl spare
+  // elements.  The offset repeats every 4 spans, which is the step of the dense pass.
+  static constexpr int kAl = 16 / (int)sizeof(real);
+  static PRIB_HD int tile_cols(bool left_side, int TXb) { return TXb + 32 + (left_side ? 0 : kAl); }
+  static PRIB_HD int row_off(const Geo &ge, bool left_side, int r) {
+    return left_side ? 0 : (int)((ge.g0 - 31 - r) & (long long)(kAl - 1));
+  }
   static PRIB_HD int tile_col_limit(const Ctx &c, const Geo &ge, bool left_side, int x) {
     const long long col = left_side ? ge.g0 + x : ge.g0 - 31 + x;
     if (col < 0 || col >= c.NC) return -1;
@@ -1103,9 +1114,10 @@ struct BiTile {
 
   template <int S, int COLS, int ULO, int DIR>
   static PRIB_HD void dense_rows(const real *base, int cols, int dp0, const real *cv, const real (&w)[kTT],
-                                 real (&m)[kMaxLoop + 1]) {
+                                 real (&m)[kMaxLoop + 1], const int (&o)[4]) {
     if (dp0 - S >= 5) {  // uniform: inner spans below 5 hold no stems
       const real *row = base - S * (COLS > 0 ? COLS : cols);
+      if constexpr (DIR < 0) row += o[S & 3];  // right tile: row_off() of span dp0 - S
       real qsat = 0;
       if constexpr (dn_row_has_sat(S, ULO)) {
 #pragma unroll
@@ -1113,7 +1125,7 @@ struct BiTile {
       }
       dense_cols<S, ULO, ULO, DIR>(row, cv, w, qsat, m);
     }
-    if constexpr (S < kMaxLoop) dense_rows<S + 1, COLS, ULO, DIR>(base, cols, dp0, cv, w, m);
+    if constexpr (S < kMaxLoop) dense_rows<S + 1, COLS, ULO, DIR>(base, cols, dp0, cv, w, m, o);
   }
 
 #if defined(__CUDA_ARCH__)
@@ -1170,9 +1182,11 @@ struct BiTile {
 
   template <int S, int COLS, int ULO, int DIR>
   static __device__ __forceinline__ void dense_rows2(const float *base, int cols, int dp0, const float *cv,
-                                                     const float (&w)[kTT], unsigned long long (&mp)[kMaxLoop / 2 + 1]) {
+                                                     const float (&w)[kTT], unsigned long long (&mp)[kMaxLoop / 2 + 1],
+                                                     const int (&o)[4]) {
     if (dp0 - S >= 5) {
       const float *row = base - S * (COLS > 0 ? COLS : cols);
+      if constexpr (DIR < 0) row += o[S & 3];
       float qsat = 0;
       if constexpr (dn_row_has_sat(S, ULO)) {
 #pragma unroll
@@ -1180,7 +1194,7 @@ struct BiTile {
       }
       dense_cols2<S, (ULO / 2) * 2, ULO, DIR>(row, cv, w, qsat, mp);
     }
-    if constexpr (S < kMaxLoop) dense_rows2<S + 1, COLS, ULO, DIR>(base, cols, dp0, cv, w, mp);
+    if constexpr (S < kMaxLoop) dense_rows2<S + 1, COLS, ULO, DIR>(base, cols, dp0, cv, w, mp, o);
   }
 #endif
 
@@ -1242,6 +1256,7 @@ struct BiTile {
       }
     }
     if (i >= 1) {
+      const int kNoOff[4] = {0, 0, 0, 0};
       // pass B: generic interior loops out of the shared-memory tile, dense over groups of kTT outer spans
       // (the outer-pair weights of the next group are loaded while this group is being evaluated)
       real wn[kTT];
@@ -1259,10 +1274,10 @@ struct BiTile {
 #pragma unroll
         for (int k = 0; k < kTT; ++k) wn[k] = (dp0 + kTT + k <= dpmax) ? c.ld(B_STEMO, dp0 + kTT + k + 2, g - 1) : (real)0;
 #if defined(__CUDA_ARCH__)
-        if constexpr (sizeof(real) == 4) dense_rows2<1, COLS, ULO, 1>(tile + (dp0 - 5) * cols + t, cols, dp0, cv, w, mp);
+        if constexpr (sizeof(real) == 4) dense_rows2<1, COLS, ULO, 1>(tile + (dp0 - 5) * cols + t, cols, dp0, cv, w, mp, kNoOff);
         else
 #endif
-          dense_rows<1, COLS, ULO, 1>(tile + (dp0 - 5) * cols + t, cols, dp0, cv, w, ml);
+          dense_rows<1, COLS, ULO, 1>(tile + (dp0 - 5) * cols + t, cols, dp0, cv, w, ml, kNoOff);
       }
 #if defined(__CUDA_ARCH__)
       if constexpr (sizeof(real) == 4) {
@@ -1356,6 +1371,10 @@ struct BiTile {
           }
         }
       }
+      // row_off() of the inner rows dp0 - S by S mod 4 (dp0 advances in steps of kTT = 4: the same for every group)
+      int o[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) o[k] = row_off(ge, false, delta + 5 - k);
       real wn[kTT];
 #pragma unroll
       for (int k = 0; k < kTT; ++k)
@@ -1374,10 +1393,10 @@ struct BiTile {
           wn[k] = (dp0 + kTT + k <= dpmax) ? c.ld(B_STEMO, dp0 + kTT + k + 2, g2 - dp0 - kTT - k - 1) : (real)0;
 #if defined(__CUDA_ARCH__)
         if constexpr (sizeof(real) == 4)
-          dense_rows2<1, COLS, ULO, -1>(tile + (dp0 - 5) * cols + t + 31, cols, dp0, cv, w, mp);
+          dense_rows2<1, COLS, ULO, -1>(tile + (dp0 - 5) * cols + t + 31, cols, dp0, cv, w, mp, o);
         else
 #endif
-          dense_rows<1, COLS, ULO, -1>(tile + (dp0 - 5) * cols + t + 31, cols, dp0, cv, w, mr);
+          dense_rows<1, COLS, ULO, -1>(tile + (dp0 - 5) * cols + t + 31, cols, dp0, cv, w, mr, o);
       }
 #if defined(__CUDA_ARCH__)
       if constexpr (sizeof(real) == 4) {
@@ -1415,9 +1434,12 @@ struct BiTile {
       }
       const int umax = imin(kMaxLoop, dp - 5);
       const real *base = tile + (dp - 5) * cols + t + 31;
+      const real *bo[4];  // + row_off() of span dp - u2, by u2 mod 4
+#pragma unroll
+      for (int k = 0; k < 4; ++k) bo[k] = base + row_off(ge, false, dp - k);
 #pragma unroll
       for (int u2 = ULO; u2 <= kMaxLoop; ++u2)
-        if (u2 <= umax) bsum[u2] += bseB * base[-u2 - u2 * cols];  // cell (i, j'-u2), span dp-u2
+        if (u2 <= umax) bsum[u2] += bseB * bo[u2 & 3][-u2 - u2 * cols];  // cell (i, j'-u2), span dp-u2
     }
 #pragma unroll
     for (int u2 = ULO; u2 <= kMaxLoop; ++u2)

@@ -173,19 +173,20 @@ void run_biloop_tiled(EmuT<real> &e, int TXb) {
   const typename Core<real>::Ctx &c = e.c;
   typename BT::Geo ge;
   ge.TXb = TXb;
-  ge.cols = TXb + 32;
   ge.rows = c.W - 5 > 0 ? c.W - 5 : 0;
-  std::vector<real> tile((size_t)ge.rows * ge.cols + 1);
+  std::vector<real> tile((size_t)ge.rows * BT::tile_cols(false, TXb) + 1);
   std::vector<uint8_t> list((size_t)(c.W + 1) * TXb);
   std::vector<typename BT::Strand> st(TXb);
   for (int side = 0; side < 2; side++)
     for (long long g0 = 0; g0 < c.NC; g0 += TXb) {
       ge.g0 = g0;
-      auto fill = [&](int arr) {
-        for (int x = 0; x < ge.cols; x++) {
+      ge.cols = BT::tile_cols(side == 0, TXb);
+      auto fill = [&](int arr) {  // what the bulk copy + masking of the device kernel leave in shared memory
+        std::fill(tile.begin(), tile.end(), std::numeric_limits<real>::quiet_NaN());  // slack elements are never read
+        for (int x = 0; x < TXb + 32; x++) {
           const int lim = BT::tile_col_limit(c, ge, side == 0, x);
           for (int r = 5; r < 5 + ge.rows; r++)
-            tile[(size_t)(r - 5) * ge.cols + x] = BT::tile_elem(c, ge, side == 0, arr, r, x, lim);
+            tile[(size_t)(r - 5) * ge.cols + x + BT::row_off(ge, side == 0, r)] = BT::tile_elem(c, ge, side == 0, arr, r, x, lim);
         }
       };
       fill(A_STEMI);
