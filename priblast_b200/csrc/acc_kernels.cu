@@ -508,8 +508,11 @@ void launch_biloop(const typename Core<real>::Ctx &k, unsigned grid, int TXb, si
 #undef PRIB_BI_LAUNCH
 }
 
+#ifndef PRIB_FIN_CTAS
+#define PRIB_FIN_CTAS 8
+#endif
 template <typename real>
-__global__ void __launch_bounds__(kThreads, 8) k_finalize(typename Core<real>::Ctx c) {
+__global__ void __launch_bounds__(kThreads, PRIB_FIN_CTAS) k_finalize(typename Core<real>::Ctx c) {
   const long long g = (long long)blockIdx.x * kThreads + threadIdx.x;
   if (g < c.NC) Core<real>::finalize_position(c, g);
 }

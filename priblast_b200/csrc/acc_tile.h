@@ -1229,19 +1229,23 @@ struct BiTile {
     // (X_SUFH, restructured raccess.cpp:546-561 -- same Beta_stem loads as the list), the list of the closing spans
     // and, for delta == 2, the 2x1 / 2x2 special loops
     const int dpmax = i >= 1 ? imin(W - 1, L - 1 - i) : -1;
+    const uint8_t s0 = s[0], s1 = s[1];  // a sequence column always has a successor (padding)
     real suf = 0;
     for (int dd0 = W; dd0 >= 4; dd0 -= 8) {
       real bv[8];  // 8 independent loads in flight (the list update is a serial chain on the loaded values)
+      uint8_t sv[9];  // bases dd0 .. dd0 - 8 (a closing span needs its own and the next one)
 #pragma unroll
       for (int k = 0; k < 8; ++k) bv[k] = (dd0 - k >= 4 && dd0 - k - 1 <= dpmax) ? c.ld(B_STEM, dd0 - k + 1, g - 1) : (real)0;
+#pragma unroll
+      for (int k = 0; k < 9; ++k) sv[k] = (dd0 - k >= 3 && dd0 - k - 1 <= dpmax) ? s[dd0 - k] : (uint8_t)0;
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         const int dd = dd0 - k, dp = dd - 1;
         if (dd < 4) break;
         const real bse = bv[k];
         if (bse != 0) {
-          const int te = T.bp[s[0]][s[dd]];
-          suf += bse * T.hpB[dd] * (dd - 1 != 3 ? T.e_mmH[te][s[1]][s[dd - 1]] : T.tau[te]);
+          const int te = T.bp[s0][sv[k]];
+          suf += bse * T.hpB[dd] * (dd - 1 != 3 ? T.e_mmH[te][s1][sv[k + 1]] : T.tau[te]);
           if (dp >= delta + 5) {
             list[cnt * TXb + t] = (uint8_t)dp;
             ++cnt;
