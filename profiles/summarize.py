@@ -1,6 +1,6 @@
 """Turns the raw ncu outputs brought back in gpurun_out/ into the tracked summaries under profiles/<round>/.
 
-  python profiles/summarize.py r1 gpurun_out/launches_r1.csv gpurun_out/prof_r1_full.ncu-rep <nt_per_launch>
+  python profiles/summarize.py r1 gpurun_out/launches_r1.csv gpurun_out/prof_r1_full.ncu-rep|raw.csv <nt_per_launch>
 
  * launches csv  : `ncu --metrics gpu__time_duration.sum --clock-control none --csv` of the bench command
  * .ncu-rep      : `ncu --set full --clock-control none --import-source on` of profiles/prof_driver.py
@@ -70,7 +70,10 @@ def main():
         for k, (n, t) in sorted(tot.items(), key=lambda kv: -kv[1][1]):
             f.write(f"{k},{n},{t:.3f},{100 * t / whole:.1f}\n")
     # ---- full capture -> selected counters
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    # (a .csv argument is the `ncu -i <rep> --page raw --csv` output made on the GPU box: a report with sources can
+    # exceed what gpurun copies back)
+    raw = open(rep).read() if rep.endswith(".csv") else subprocess.run(
+        ["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rr = list(csv.reader(raw.splitlines()))
     h, units = rr[0], rr[1]
     summ = []
