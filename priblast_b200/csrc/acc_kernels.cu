@@ -655,6 +655,13 @@ struct prib_ctx {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk0 = nullptr, evk1 = nullptr;
   cudaEvent_t evp[PRIB_NUM_PHASES + 1] = {};
   bool phases_pending = false, kernel_timed = true, stage_timed = true;
+  // prib_acc_run: the stage fills the arena batch by batch and launches each batch as soon as it is staged, so the
+  // host copy of batch k + 1 runs under the kernels of batch k (prib_acc_stage / _compute on their own do not)
+  struct Pipelined {
+    bool on = false, launched = false;
+    const char *const *seq = nullptr;
+    long long fpos = 0;
+  } pipe;
   Engine<float> e32;
   Engine<double> e64;
   ExactEngine *ex = nullptr;  // mode 2: the reference's own arithmetic (acc_exact.h)
@@ -899,6 +906,8 @@ int make_batch(prib_ctx *c, const std::vector<int> &ids, const std::vector<long 
   return PRIB_OK;
 }
 
+int launch_staged_batch(prib_ctx *c, const Batch &b);
+
 // Greedy partition of `order` (already longest-first; the bytes of order[k] lie in the arena in this order, starting
 // at raw_begin) into batches that fit `max_cols` columns.
 int partition(prib_ctx *c, const std::vector<int> &order, long long max_cols, const std::vector<long long> &acc_abs,
@@ -925,8 +934,14 @@ int partition(prib_ctx *c, const std::vector<int> &order, long long max_cols, co
     if (ids.empty())
       return fail(PRIB_ECUDA, "sequence " + std::to_string(order[pos]) + " does not fit the device DP budget");
     if (used == out.size()) out.emplace_back();
+    if (c->pipe.on)  // the bytes of this batch, into their place in the arena
+      for (int q : ids) std::memcpy(c->h_arena + c->seq_pos[q], c->pipe.seq[q], (size_t)c->seq_len[q]);
     int rc = make_batch(c, ids, ao, co, out[used], raw_begin);
     if (rc != PRIB_OK) return rc;
+    if (c->pipe.on) {
+      rc = launch_staged_batch(c, out[used]);
+      if (rc != PRIB_OK) return rc;
+    }
     raw_begin += bytes;
     ++used;
   }
@@ -1121,6 +1136,41 @@ int settle_kernel_time(prib_ctx *c) {
   return PRIB_OK;
 }
 
+// What has to be on the stream before the first batch of a compute pass: start-of-pass event, the zeroed output image
+// (entries the kernels never write -- acc tail, cond head -- must read 0: raccess.cpp:487-488) and the page-locked
+// buffer the range flags of all batches come back to.
+int compute_prologue(prib_ctx *c) {
+  if (settle_kernel_time(c) != PRIB_OK) return PRIB_ECUDA;
+  CU(cudaEventRecord(c->evk0, c->stream));
+  CU(cudaMemsetAsync(c->d_out, 0, (size_t)std::max<long long>(c->out_floats, 1) * sizeof(float), c->stream));
+  CU(cudaMemsetAsync(c->d_bad, 0, sizeof(int32_t), c->stream));
+  const long long nflags = (long long)c->seq_len.size();
+  if (c->use_fp32 && c->h_flags_cap < nflags) {
+    CU(cudaStreamSynchronize(c->stream));
+    if (c->h_flags) cudaFreeHost(c->h_flags);
+    c->h_flags = nullptr;
+    c->h_flags_cap = 0;
+    CU(cudaMallocHost(&c->h_flags, sizeof(int32_t) * (size_t)std::max<long long>(nflags, 1)));
+    c->h_flags_cap = std::max<long long>(nflags, 1);
+  }
+  c->pipe.fpos = 0;
+  return PRIB_OK;
+}
+
+// All kernels of one staged batch, and the copy of its range flags behind them (no wait).
+int launch_staged_batch(prib_ctx *c, const Batch &b) {
+  if (b.n == 0) return PRIB_OK;
+  int rc = c->ex ? run_batch_exact(c, b) : c->use_fp32 ? run_batch<float>(c, b, true) : run_batch<double>(c, b, true);
+  if (rc != PRIB_OK) return rc;
+  c->cnt.sequences += b.n;
+  c->cnt.nucleotides += b.nt;
+  if (c->use_fp32) {
+    CU(cudaMemcpyAsync(c->h_flags + c->pipe.fpos, b.d_flags, sizeof(int32_t) * (size_t)b.n, cudaMemcpyDeviceToHost, c->stream));
+    c->pipe.fpos += b.n;
+  }
+  return PRIB_OK;
+}
+
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------
@@ -1302,16 +1352,11 @@ int prib_acc_stage(prib_ctx *c, int32_t n, const char *const *seq, const int32_t
     for (int k = 0; k < n; k++) {
       const int q = order[k];
       c->seq_pos[q] = (long long)p;
-      std::memcpy(c->h_arena + p, seq[q], (size_t)len[q]);
+      if (!c->pipe.on) std::memcpy(c->h_arena + p, seq[q], (size_t)len[q]);  // (pipelined: batch by batch, in partition)
       p += (size_t)len[q];
     }
     c->h_arena_used = p;
   }
-  CU(cudaEventRecord(c->ev0, c->stream));
-  int rc = partition(c, order, max_cols, acc_abs, cond_abs, c->batches, &c->n_batches, 0);
-  if (rc != PRIB_OK) return rc;
-  CU(cudaEventRecord(c->ev1, c->stream));
-  c->stage_timed = false;
   if (o > c->out_cap || !c->d_out) {
     if (c->d_out) cudaFree(c->d_out);
     c->d_out = nullptr;
@@ -1319,6 +1364,19 @@ int prib_acc_stage(prib_ctx *c, int32_t n, const char *const *seq, const int32_t
     CU(cudaMalloc(&c->d_out, (size_t)std::max<long long>(o, 1) * sizeof(float)));
     c->out_cap = std::max<long long>(o, 1);
   }
+  if (c->pipe.on) {
+    c->pipe.seq = seq;
+    int rc = compute_prologue(c);
+    if (rc != PRIB_OK) return rc;
+  }
+  CU(cudaEventRecord(c->ev0, c->stream));
+  if (c->pipe.on) CU(cudaEventRecord(c->ev1, c->stream));  // copies and kernels interleave: no separate copy time
+  int rc = partition(c, order, max_cols, acc_abs, cond_abs, c->batches, &c->n_batches, 0);
+  c->pipe.seq = nullptr;
+  if (rc != PRIB_OK) return rc;
+  if (!c->pipe.on) CU(cudaEventRecord(c->ev1, c->stream));
+  c->stage_timed = false;
+  c->pipe.launched = c->pipe.on;
   c->staged = true;
   return PRIB_OK;
 }
@@ -1328,35 +1386,18 @@ int prib_acc_compute(prib_ctx *c) {
   if (!c) return fail(PRIB_EINVAL, "null context");
   if (!c->staged) return fail(PRIB_ESTATE, "prib_acc_compute called before prib_acc_stage");
   CU(cudaSetDevice(c->prm.device));
-  if (settle_kernel_time(c) != PRIB_OK) return PRIB_ECUDA;
-  CU(cudaEventRecord(c->evk0, c->stream));
-  // entries the kernels never write (acc tail, cond head) must read 0: raccess.cpp:487-488
-  CU(cudaMemsetAsync(c->d_out, 0, (size_t)std::max<long long>(c->out_floats, 1) * sizeof(float), c->stream));
-  CU(cudaMemsetAsync(c->d_bad, 0, sizeof(int32_t), c->stream));
-  // range flags of all batches come back with ONE wait after the last batch (each batch has its own flag array)
-  long long nflags = 0;
-  for (size_t bi = 0; bi < c->n_batches; ++bi) nflags += c->batches[bi].n;
-  if (c->use_fp32 && c->h_flags_cap < nflags) {
-    CU(cudaStreamSynchronize(c->stream));
-    if (c->h_flags) cudaFreeHost(c->h_flags);
-    c->h_flags = nullptr;
-    c->h_flags_cap = 0;
-    CU(cudaMallocHost(&c->h_flags, sizeof(int32_t) * (size_t)std::max<long long>(nflags, 1)));
-    c->h_flags_cap = std::max<long long>(nflags, 1);
-  }
-  long long fpos = 0;
-  for (size_t bi = 0; bi < c->n_batches; ++bi) {
-    const Batch &b = c->batches[bi];
-    if (b.n == 0) continue;
-    int rc = c->ex ? run_batch_exact(c, b) : c->use_fp32 ? run_batch<float>(c, b, true) : run_batch<double>(c, b, true);
+  if (c->pipe.launched) {
+    c->pipe.launched = false;  // prib_acc_run: the stage has launched every batch already
+  } else {
+    int rc = compute_prologue(c);
     if (rc != PRIB_OK) return rc;
-    c->cnt.sequences += b.n;
-    c->cnt.nucleotides += b.nt;
-    if (c->use_fp32) {
-      CU(cudaMemcpyAsync(c->h_flags + fpos, b.d_flags, sizeof(int32_t) * (size_t)b.n, cudaMemcpyDeviceToHost, c->stream));
-      fpos += b.n;
+    for (size_t bi = 0; bi < c->n_batches; ++bi) {
+      rc = launch_staged_batch(c, c->batches[bi]);
+      if (rc != PRIB_OK) return rc;
     }
   }
+  // range flags of all batches come back with ONE wait after the last batch (each batch has its own flag array)
+  long long fpos = 0;
   std::vector<int> flagged;
   if (c->use_fp32) {
     CU(cudaStreamSynchronize(c->stream));
@@ -1485,8 +1526,14 @@ int prib_acc_fetch(prib_ctx *c, float *out, const int64_t *acc_off, const int64_
 
 int prib_acc_run(prib_ctx *c, int32_t n, const char *const *seq, const int32_t *len, float *out,
                  const int64_t *acc_off, const int64_t *cond_off) {
+  if (!c) return fail(PRIB_EINVAL, "null context");
+  c->pipe.on = true;  // stage and launch batch by batch
   int rc = prib_acc_stage(c, n, seq, len);
-  if (rc != PRIB_OK) return rc;
+  c->pipe.on = false;
+  if (rc != PRIB_OK) {
+    c->pipe.launched = false;
+    return rc;
+  }
   rc = prib_acc_compute(c);
   if (rc != PRIB_OK) return rc;
   return prib_acc_fetch(c, out, acc_off, cond_off);

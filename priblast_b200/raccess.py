@@ -21,6 +21,19 @@ import numpy as np
 from . import _capi
 
 
+def _probe_bytes_offset():
+    """Byte offset of the character data inside a CPython `bytes` object, or None if the layout is not the expected
+    one (then Raccess._marshal copies instead of pointing)."""
+    off = bytes.__basicsize__ - 1
+    for probe in (b"pRIblast", bytes(range(1, 200))):
+        if ctypes.string_at(id(probe) + off, len(probe)) != probe:
+            return None
+    return off
+
+
+_BYTES_OFFSET = _probe_bytes_offset()
+
+
 def _as_bytes(seq) -> bytes:
     if isinstance(seq, bytes):
         return seq
@@ -130,20 +143,30 @@ class Raccess:
 
     # -- batched form (what the db step uses) -------------------------------------------------------
     def _marshal(self, seqs: Iterable):
-        """(keep-alive, n, lens, char**) for the C ABI.  The sequences are joined into one buffer and the pointer
-        array is computed with numpy: building a ctypes array of n `c_char_p` costs ~0.6 us per sequence, more than
-        the host-to-device copy of the bases."""
+        """(keep-alive, n, lens, char**) for the C ABI.  No copy of the bases on this side: the pointer array holds
+        the addresses of the `bytes` objects' own buffers (the library makes the one host copy, into its page-locked
+        arena, batch by batch under the kernels of the previous batch).  Building a ctypes array of n `c_char_p`
+        costs ~0.6 us per sequence and joining the sequences into one buffer ~0.4 ns per base -- either is more
+        than the host-to-device copy of the bases -- so the addresses are computed with numpy from `id()` and the
+        data offset of a CPython bytes object, checked once at import (`_BYTES_OFFSET`); if that check ever fails the
+        sequences are joined into one buffer instead."""
         bs = [s if type(s) is bytes else _as_bytes(s) for s in seqs]
         n = len(bs)
         lens = np.fromiter(map(len, bs), dtype=np.int32, count=n)
-        blob = np.frombuffer(b"".join(bs) or b"\0", dtype=np.uint8)
-        ptrs = np.empty(max(n, 1), dtype=np.uint64)
-        ptrs[0] = blob.ctypes.data
-        if n > 1:
-            np.cumsum(lens[:-1], dtype=np.uint64, out=ptrs[1:n])
-            ptrs[1:n] += np.uint64(blob.ctypes.data)
+        if _BYTES_OFFSET is not None:
+            ptrs = np.fromiter(map(id, bs), dtype=np.uint64, count=n) if n else np.zeros(1, dtype=np.uint64)
+            ptrs += np.uint64(_BYTES_OFFSET)
+            keep = bs
+        else:
+            blob = np.frombuffer(b"".join(bs) or b"\0", dtype=np.uint8)
+            ptrs = np.empty(max(n, 1), dtype=np.uint64)
+            ptrs[0] = blob.ctypes.data
+            if n > 1:
+                np.cumsum(lens[:-1], dtype=np.uint64, out=ptrs[1:n])
+                ptrs[1:n] += np.uint64(blob.ctypes.data)
+            keep = blob
         arr = ptrs.ctypes.data_as(ctypes.POINTER(ctypes.c_char_p))
-        return (blob, ptrs), n, lens, arr
+        return (keep, ptrs), n, lens, arr
 
     def run_batch(self, seqs: Iterable, out: np.ndarray | None = None):
         """All sequences in one C-ABI call; returns [(acc, cond), ...] as views into one buffer."""
