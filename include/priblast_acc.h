@@ -78,7 +78,10 @@ void prib_acc_destroy(prib_ctx *ctx);
  *                    (entries len-delta+1 .. len-1 are 0, as in raccess.cpp:487,510-517).
  *   cond_off[k]    : float offset of the len[k] conditional-accessibility values
  *                    (entries 0 .. delta-1 are 0, raccess.cpp:488,519-527).
- * Blocking.  Results do not depend on batching or on the number of GPUs used by the caller. */
+ * Blocking.  Results do not depend on batching or on the number of GPUs used by the caller.  The call pipelines
+ * its own stages: the bases are copied (once) into a page-locked arena batch by batch and each batch is launched as
+ * soon as it is staged, so the host copy of one batch runs under the kernels of the previous one; seq[] must stay
+ * valid until the call returns.  `h2d_ms` is not accumulated for this call (copies and kernels interleave). */
 int prib_acc_run(prib_ctx *ctx, int32_t n, const char *const *seq, const int32_t *len, float *out,
                  const int64_t *acc_off, const int64_t *cond_off);
 
