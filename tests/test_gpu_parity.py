@@ -177,6 +177,33 @@ def test_staged_api_and_counters():
     assert cnt["nucleotides"] >= nt and cnt["kernel_ms"] > 0 and cnt["kernel_launches"] > 0
 
 
+def test_pipelined_run_equals_the_split_calls_over_several_batches():
+    """prib_acc_run fills its arena and launches batch by batch; prib_acc_stage + _compute + _fetch stage everything
+    first.  Same bits either way, over several device batches and with a sequence the FP64 engine has to redo; a
+    second prib_acc_compute on what the pipelined run staged must work too."""
+    hairpin = next(c["seq"] for c in GOLDEN if c["name"] == "perfect_hairpin_L70")
+    seqs = _cfg2_sample(40) + [hairpin.encode() if isinstance(hairpin, str) else hairpin] + _cfg2_sample(48)[40:]
+    r = rac(70, 5, max_batch_bytes=400 << 20)
+    c0 = r.counters()
+    want = r.run_batch(seqs)
+    c1 = r.counters()
+    assert c1["batches"] - c0["batches"] > 2 and c1["fp64_rerun_sequences"] - c0["fp64_rerun_sequences"] >= 1
+    r.compute()  # again, on the batches the run left staged
+    again = r_fetch_after_run(r, seqs)
+    r.stage(seqs)
+    r.compute()
+    got = r.fetch()
+    for (a, c), (b, d), (e, f) in zip(want, got, again):
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32)) and np.array_equal(c.view(np.uint32), d.view(np.uint32))
+        assert np.array_equal(a.view(np.uint32), e.view(np.uint32)) and np.array_equal(c.view(np.uint32), f.view(np.uint32))
+
+
+def r_fetch_after_run(r, seqs):
+    """fetch() of the Python mirror needs the lengths of the staged set (run_batch does not record them)."""
+    r._staged_lens = np.array([len(s) for s in seqs], np.int32)
+    return r.fetch()
+
+
 def test_record_bytes_match_reference_file():
     """`.acc` record of one sequence equals the fixture's record layout with GPU numbers inside."""
     case = next(c for c in GOLDEN if c["name"] == "rand_L100_W70_d5")
