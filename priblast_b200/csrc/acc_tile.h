@@ -1029,6 +1029,12 @@ struct BiTile {
   typedef Core<real> K;
   typedef typename K::Ctx Ctx;
   typedef typename K::SmallTables ST;
+  // outer spans handled together by the dense pass (a multiple of 4: the right tile's row offsets repeat every 4 spans)
+#ifndef PRIB_BI_TT
+#define PRIB_BI_TT 4
+#endif
+  static constexpr int kTB = PRIB_BI_TT;
+  static constexpr int kSmin = 5 - kTB;  // first source-row offset: loop size 4 of the LAST span of a group
 
   struct Geo {
     long long g0;  // first owned column
@@ -1068,18 +1074,18 @@ struct BiTile {
   }
 
   // ---------------------------------------------------------------------------------------------
-  // Dense, time-tiled generic pass.  Outer spans dp0 + k (k = 0..kTT-1) of one column are handled together:
+  // Dense, time-tiled generic pass.  Outer spans dp0 + k (k = 0..kTB-1) of one column are handled together:
   // tile row dp0 - S (inner span) holds, at offset DIR * u, the inner cell of the loops with kept strand
   // length u and loop size S + k for target k, so
   //     m[u] += row[DIR * u] * sum_k w[k] * conv[u][S + k - u]
-  // with w[k] = Beta_stemO of the outer pair (0 when it does not close).  Where all kTT coefficients sit in
+  // with w[k] = Beta_stemO of the outer pair (0 when it does not close).  Where all kTB coefficients sit in
   // the saturated ninio zone (|u1 - u2| >= 6) the inner sum does not depend on u and is formed once per row.
   // All indices are compile-time: conv[][] entries are constant-bank operands.
   // ---------------------------------------------------------------------------------------------
   static PRIB_HD constexpr bool dn_valid(int u, int sum) { return sum <= kMaxLoop && sum - u >= 1 && sum >= 4 && !(u == 2 && sum == 4); }
   static PRIB_HD constexpr bool dn_sat(int u, int sum) { return (2 * u - sum >= 6) || (sum - 2 * u >= 6); }
   static PRIB_HD constexpr bool dn_allsat(int u, int S) {
-    for (int k = 0; k < kTT; ++k)
+    for (int k = 0; k < kTB; ++k)
       if (!dn_valid(u, S + k) || !dn_sat(u, S + k)) return false;
     return true;
   }
@@ -1089,13 +1095,13 @@ struct BiTile {
     return false;
   }
   static PRIB_HD constexpr bool dn_any(int u, int S) {
-    for (int k = 0; k < kTT; ++k)
+    for (int k = 0; k < kTB; ++k)
       if (dn_valid(u, S + k)) return true;
     return false;
   }
 
   template <int S, int U, int ULO, int DIR>
-  static PRIB_HD void dense_cols(const real *row, const real *cv, const real (&w)[kTT], real qsat,
+  static PRIB_HD void dense_cols(const real *row, const real *cv, const real (&w)[kTB], real qsat,
                                  real (&m)[kMaxLoop + 1]) {
     if constexpr (dn_any(U, S)) {
       real q;
@@ -1104,7 +1110,7 @@ struct BiTile {
       } else {
         q = 0;
 #pragma unroll
-        for (int k = 0; k < kTT; ++k)
+        for (int k = 0; k < kTB; ++k)
           if (dn_valid(U, S + k)) q += w[k] * cv[U * 32 + (S + k - U)];
       }
       m[U] += row[DIR * U] * q;
@@ -1113,19 +1119,19 @@ struct BiTile {
   }
 
   template <int S, int COLS, int ULO, int DIR>
-  static PRIB_HD void dense_rows(const real *base, int cols, int dp0, const real *cv, const real (&w)[kTT],
+  static PRIB_HD void dense_rows(const real *base, int cols, int dp0, int hi, const real *cv, const real (&w)[kTB],
                                  real (&m)[kMaxLoop + 1], const int (&o)[4]) {
-    if (dp0 - S >= 5) {  // uniform: inner spans below 5 hold no stems
+    if (dp0 - S >= 5 && (S >= 1 || dp0 - S <= hi)) {  // uniform: inner spans below 5 hold no stems; the tile ends at span hi
       const real *row = base - S * (COLS > 0 ? COLS : cols);
       if constexpr (DIR < 0) row += o[S & 3];  // right tile: row_off() of span dp0 - S
       real qsat = 0;
       if constexpr (dn_row_has_sat(S, ULO)) {
 #pragma unroll
-        for (int k = 0; k < kTT; ++k) qsat += w[k] * cv[(S + k - 1) * 32 + 1];  // conv[sum - 1][1]: saturated, sum >= 8
+        for (int k = 0; k < kTB; ++k) qsat += w[k] * cv[(S + k - 1) * 32 + 1];  // conv[sum - 1][1]: saturated, sum >= 8
       }
       dense_cols<S, ULO, ULO, DIR>(row, cv, w, qsat, m);
     }
-    if constexpr (S < kMaxLoop) dense_rows<S + 1, COLS, ULO, DIR>(base, cols, dp0, cv, w, m, o);
+    if constexpr (S < kMaxLoop) dense_rows<S + 1, COLS, ULO, DIR>(base, cols, dp0, hi, cv, w, m, o);
   }
 
 #if defined(__CUDA_ARCH__)
@@ -1142,20 +1148,20 @@ struct BiTile {
 
   // coefficient q of strand length U for source row S (see dense_cols), scalar
   template <int S, int U>
-  static __device__ __forceinline__ float dense_q(const float *cv, const float (&w)[kTT], float qsat) {
+  static __device__ __forceinline__ float dense_q(const float *cv, const float (&w)[kTB], float qsat) {
     if constexpr (dn_allsat(U, S)) {
       return qsat;
     } else {
       float q = 0;
 #pragma unroll
-      for (int k = 0; k < kTT; ++k)
+      for (int k = 0; k < kTB; ++k)
         if (dn_valid(U, S + k)) q += w[k] * cv[U * 32 + (S + k - U)];
       return q;
     }
   }
 
   template <int S, int U, int ULO, int DIR>
-  static __device__ __forceinline__ void dense_cols2(const float *row, const float *cv, const float (&w)[kTT], float qsat,
+  static __device__ __forceinline__ void dense_cols2(const float *row, const float *cv, const float (&w)[kTB], float qsat,
                                                      unsigned long long (&mp)[kMaxLoop / 2 + 1]) {
     constexpr bool v0 = dn_use(U, S, ULO), v1 = dn_use(U + 1, S, ULO);
     if constexpr (v0 || v1) {
@@ -1165,7 +1171,7 @@ struct BiTile {
         // constant bank
         qq = 0;
 #pragma unroll
-        for (int k = 0; k < kTT; ++k) {
+        for (int k = 0; k < kTB; ++k) {
           const bool a = dn_valid(U, S + k), b = dn_valid(U + 1, S + k);
           if (a || b) ffma2_bcast(qq, w[k], g_convpair_f[U * 32 + S + k]);  // the table holds 0 where a loop does not exist
         }
@@ -1181,20 +1187,20 @@ struct BiTile {
   }
 
   template <int S, int COLS, int ULO, int DIR>
-  static __device__ __forceinline__ void dense_rows2(const float *base, int cols, int dp0, const float *cv,
-                                                     const float (&w)[kTT], unsigned long long (&mp)[kMaxLoop / 2 + 1],
+  static __device__ __forceinline__ void dense_rows2(const float *base, int cols, int dp0, int hi, const float *cv,
+                                                     const float (&w)[kTB], unsigned long long (&mp)[kMaxLoop / 2 + 1],
                                                      const int (&o)[4]) {
-    if (dp0 - S >= 5) {
+    if (dp0 - S >= 5 && (S >= 1 || dp0 - S <= hi)) {
       const float *row = base - S * (COLS > 0 ? COLS : cols);
       if constexpr (DIR < 0) row += o[S & 3];
       float qsat = 0;
       if constexpr (dn_row_has_sat(S, ULO)) {
 #pragma unroll
-        for (int k = 0; k < kTT; ++k) qsat += w[k] * cv[(S + k - 1) * 32 + 1];
+        for (int k = 0; k < kTB; ++k) qsat += w[k] * cv[(S + k - 1) * 32 + 1];
       }
       dense_cols2<S, (ULO / 2) * 2, ULO, DIR>(row, cv, w, qsat, mp);
     }
-    if constexpr (S < kMaxLoop) dense_rows2<S + 1, COLS, ULO, DIR>(base, cols, dp0, cv, w, mp, o);
+    if constexpr (S < kMaxLoop) dense_rows2<S + 1, COLS, ULO, DIR>(base, cols, dp0, hi, cv, w, mp, o);
   }
 #endif
 
@@ -1261,27 +1267,27 @@ struct BiTile {
     }
     if (i >= 1) {
       const int kNoOff[4] = {0, 0, 0, 0};
-      // pass B: generic interior loops out of the shared-memory tile, dense over groups of kTT outer spans
+      // pass B: generic interior loops out of the shared-memory tile, dense over groups of kTB outer spans
       // (the outer-pair weights of the next group are loaded while this group is being evaluated)
-      real wn[kTT];
+      real wn[kTB];
 #pragma unroll
-      for (int k = 0; k < kTT; ++k) wn[k] = (delta + 5 + k <= dpmax) ? c.ld(B_STEMO, delta + 5 + k + 2, g - 1) : (real)0;
+      for (int k = 0; k < kTB; ++k) wn[k] = (delta + 5 + k <= dpmax) ? c.ld(B_STEMO, delta + 5 + k + 2, g - 1) : (real)0;
 #if defined(__CUDA_ARCH__)
       unsigned long long mp[kMaxLoop / 2 + 1];  // FP32 engine: packed accumulators (m[2j], m[2j + 1])
 #pragma unroll
       for (int u = 0; u <= kMaxLoop / 2; ++u) mp[u] = 0;
 #endif
-      for (int dp0 = delta + 5; dp0 <= dpmax; dp0 += kTT) {
-        real w[kTT];
+      for (int dp0 = delta + 5; dp0 <= dpmax; dp0 += kTB) {
+        real w[kTB];
 #pragma unroll
-        for (int k = 0; k < kTT; ++k) w[k] = wn[k];
+        for (int k = 0; k < kTB; ++k) w[k] = wn[k];
 #pragma unroll
-        for (int k = 0; k < kTT; ++k) wn[k] = (dp0 + kTT + k <= dpmax) ? c.ld(B_STEMO, dp0 + kTT + k + 2, g - 1) : (real)0;
+        for (int k = 0; k < kTB; ++k) wn[k] = (dp0 + kTB + k <= dpmax) ? c.ld(B_STEMO, dp0 + kTB + k + 2, g - 1) : (real)0;
 #if defined(__CUDA_ARCH__)
-        if constexpr (sizeof(real) == 4) dense_rows2<1, COLS, ULO, 1>(tile + (dp0 - 5) * cols + t, cols, dp0, cv, w, mp, kNoOff);
+        if constexpr (sizeof(real) == 4) dense_rows2<kSmin, COLS, ULO, 1>(tile + (dp0 - 5) * cols + t, cols, dp0, W - 1, cv, w, mp, kNoOff);
         else
 #endif
-          dense_rows<1, COLS, ULO, 1>(tile + (dp0 - 5) * cols + t, cols, dp0, cv, w, ml, kNoOff);
+          dense_rows<kSmin, COLS, ULO, 1>(tile + (dp0 - 5) * cols + t, cols, dp0, W - 1, cv, w, ml, kNoOff);
       }
 #if defined(__CUDA_ARCH__)
       if constexpr (sizeof(real) == 4) {
@@ -1375,32 +1381,32 @@ struct BiTile {
           }
         }
       }
-      // row_off() of the inner rows dp0 - S by S mod 4 (dp0 advances in steps of kTT = 4: the same for every group)
+      // row_off() of the inner rows dp0 - S by S mod 4 (dp0 advances in steps of kTB = 4: the same for every group)
       int o[4];
 #pragma unroll
       for (int k = 0; k < 4; ++k) o[k] = row_off(ge, false, delta + 5 - k);
-      real wn[kTT];
+      real wn[kTB];
 #pragma unroll
-      for (int k = 0; k < kTT; ++k)
+      for (int k = 0; k < kTB; ++k)
         wn[k] = (delta + 5 + k <= dpmax) ? c.ld(B_STEMO, delta + 5 + k + 2, g2 - (delta + 5) - k - 1) : (real)0;
 #if defined(__CUDA_ARCH__)
       unsigned long long mp[kMaxLoop / 2 + 1];
 #pragma unroll
       for (int u = 0; u <= kMaxLoop / 2; ++u) mp[u] = 0;
 #endif
-      for (int dp0 = delta + 5; dp0 <= dpmax; dp0 += kTT) {
-        real w[kTT];
+      for (int dp0 = delta + 5; dp0 <= dpmax; dp0 += kTB) {
+        real w[kTB];
 #pragma unroll
-        for (int k = 0; k < kTT; ++k) w[k] = wn[k];
+        for (int k = 0; k < kTB; ++k) w[k] = wn[k];
 #pragma unroll
-        for (int k = 0; k < kTT; ++k)
-          wn[k] = (dp0 + kTT + k <= dpmax) ? c.ld(B_STEMO, dp0 + kTT + k + 2, g2 - dp0 - kTT - k - 1) : (real)0;
+        for (int k = 0; k < kTB; ++k)
+          wn[k] = (dp0 + kTB + k <= dpmax) ? c.ld(B_STEMO, dp0 + kTB + k + 2, g2 - dp0 - kTB - k - 1) : (real)0;
 #if defined(__CUDA_ARCH__)
         if constexpr (sizeof(real) == 4)
-          dense_rows2<1, COLS, ULO, -1>(tile + (dp0 - 5) * cols + t + 31, cols, dp0, cv, w, mp, o);
+          dense_rows2<kSmin, COLS, ULO, -1>(tile + (dp0 - 5) * cols + t + 31, cols, dp0, W - 1, cv, w, mp, o);
         else
 #endif
-          dense_rows<1, COLS, ULO, -1>(tile + (dp0 - 5) * cols + t + 31, cols, dp0, cv, w, mr, o);
+          dense_rows<kSmin, COLS, ULO, -1>(tile + (dp0 - 5) * cols + t + 31, cols, dp0, W - 1, cv, w, mr, o);
       }
 #if defined(__CUDA_ARCH__)
       if constexpr (sizeof(real) == 4) {
